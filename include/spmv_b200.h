@@ -1,0 +1,128 @@
+/*
+ * spmv_b200.h — C ABI of the B200-native fp64 CSR SpMV engine (y = alpha*A*x + beta*y).
+ *
+ * This is the drop-in boundary for the `cuda-b200` kernel strategy of hpcde/spmv-acc.
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, returns 0 on success
+ * and a non-zero status otherwise (the text is available from spmv_b200_last_error()).
+ * The C++ strategy launcher (src/acc/cuda-b200/cuda_b200_spmv.cpp) turns a non-zero status
+ * into std::runtime_error, which the reference harness catches (benchmark/csr_spmv.hpp:52-62).
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   sparse_csr_spmv(trans, alpha, beta, h_csr_desc, d_csr_desc, dx, dy)   src/acc/api/spmv.h:20-21
+ *        -> spmv_b200_csr_spmv            (stateless, plan cache behind it)
+ *   sparse_spmv(trans, alpha, beta, m, n, rowptr, colindex, value, x, y)   src/acc/api/spmv.h:27-28
+ *        -> spmv_b200_sparse_spmv         (same 10 arguments, nnz read on the device)
+ *   csr_adaptive_plus analyze / kernel / destroy phases                    src/acc/hip-csr-adaptive-plus/csr_adaptive_plus_spmv.cpp:16-73
+ *        -> spmv_b200_plan_create / spmv_b200_execute / spmv_b200_plan_destroy
+ *   host_spmv caller pattern of the CLI (H2D y0, spmv, D2H y)              cli/main.cpp:99-118
+ *        -> spmv_b200_hostmat_create / spmv_b200_hostmat_spmv / spmv_b200_hostmat_destroy
+ *
+ * All device pointers are owned by the caller and must stay valid for the life of a plan.
+ * Indices are 0-based int32, values fp64, rows may be empty, columns need not be sorted.
+ */
+#ifndef SPMV_B200_H
+#define SPMV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPMV_B200_ABI_VERSION 1
+
+/* status codes */
+#define SPMV_B200_OK 0
+#define SPMV_B200_ERR_ARG 1
+#define SPMV_B200_ERR_CUDA 2
+#define SPMV_B200_ERR_UNSUPPORTED 3
+
+/* option flags */
+#define SPMV_B200_FLAG_NO_TMA 1u       /* stream tiles with plain loads instead of cp.async.bulk            */
+#define SPMV_B200_FLAG_BETA0_SKIP_Y 2u /* beta==0: do not read y (cuSPARSE semantics); default reads y so   */
+                                       /* that NaN/Inf in y propagate exactly like cli/verification.cpp:64  */
+
+/* row bins (by nnz per row) and tile kinds (which per-bin kernel streams a row block) */
+enum { SPMV_B200_BIN_SHORT = 0, SPMV_B200_BIN_MEDIUM = 1, SPMV_B200_BIN_LONG = 2, SPMV_B200_BIN_VERYLONG = 3 };
+enum { SPMV_B200_KIND_SHORT = 0, SPMV_B200_KIND_MEDIUM = 1, SPMV_B200_KIND_MIXED = 2 };
+
+typedef struct spmv_b200_options {
+  int32_t tile_nnz;   /* nnz per row block (multiple of 256, >= 256); 0 = default (2048)            */
+  int32_t short_max;  /* rows with nnz <= short_max are SHORT; 0 = default (8)                       */
+  int32_t medium_max; /* rows with nnz <= medium_max are MEDIUM, multiple of 4, <= tile_nnz; 0 = 128 */
+  int32_t vec_div;    /* MEDIUM kernel: lanes per row = pow2ceil(avg_nnz / vec_div); 0 = default (8) */
+  uint32_t flags;     /* SPMV_B200_FLAG_*                                                            */
+} spmv_b200_options;
+
+typedef struct spmv_b200_plan_info {
+  int32_t m, n;
+  int64_t nnz;
+  int32_t tile_nnz, short_max, medium_max, vec_div;
+  uint32_t flags;
+  int32_t uses_tma;          /* 1 if tiles are streamed with cp.async.bulk                      */
+  int32_t ntiles;            /* number of nnz-balanced row blocks                                */
+  int32_t tiles_per_kind[3]; /* SHORT / MEDIUM / MIXED                                           */
+  int32_t nsplit_rows;       /* rows whose partial sums are combined by the fix-up kernel       */
+  int32_t launches_per_execute;
+  int64_t bin_rows[4];       /* rows per bin: short / medium / long / very long                 */
+  int64_t bin_nnz[4];        /* nnz per bin                                                      */
+  int64_t smem_bytes;        /* dynamic shared memory per CTA of the streaming kernels          */
+  int64_t workspace_bytes;   /* device memory owned by the plan                                 */
+} spmv_b200_plan_info;
+
+/* arrays that spmv_b200_plan_export can copy to the host (for bit-exact analysis checks) */
+enum {
+  SPMV_B200_EXPORT_TILE_ROW = 0,   /* int32 [ntiles+1]  first row owned by each tile (lower_bound of t*T in rowptr) */
+  SPMV_B200_EXPORT_TILE_ELEM = 1,  /* int32 [ntiles+1]  first nnz streamed by each tile                              */
+  SPMV_B200_EXPORT_TILE_SPLIT = 2, /* uint8 [ntiles+1]  1 if a long row is split at the tile's leading boundary      */
+  SPMV_B200_EXPORT_TILE_KIND = 3,  /* uint8 [ntiles]    SPMV_B200_KIND_*                                             */
+  SPMV_B200_EXPORT_TILE_PART = 4,  /* int32 [ntiles+1]  largest r with rowptr[r] <= t*T (merge-path partition)       */
+  SPMV_B200_EXPORT_ROW_BIN = 5,    /* uint8 [m]         SPMV_B200_BIN_* per row                                      */
+  SPMV_B200_EXPORT_SPLIT_ROWS = 6, /* int32 [3*nsplit]  (row, first tile, last tile) per split row                   */
+  SPMV_B200_EXPORT_TILE_MAXLEN = 7 /* int32 [ntiles]    longest row owned by each tile                               */
+};
+
+typedef struct spmv_b200_plan spmv_b200_plan;
+typedef struct spmv_b200_hostmat spmv_b200_hostmat;
+
+int spmv_b200_abi_version(void);
+const char *spmv_b200_last_error(void);
+
+/* ---- plan lifecycle: analyze once, execute many times (stream is a cudaStream_t, may be NULL) ---- */
+int spmv_b200_plan_create(spmv_b200_plan **out, int32_t m, int32_t n, int64_t nnz, const int32_t *d_rowptr,
+                          const int32_t *d_colidx, const double *d_val, const spmv_b200_options *opt, void *stream);
+int spmv_b200_execute(spmv_b200_plan *plan, double alpha, double beta, const double *d_x, double *d_y, void *stream);
+int spmv_b200_plan_destroy(spmv_b200_plan *plan);
+int spmv_b200_plan_get_info(const spmv_b200_plan *plan, spmv_b200_plan_info *info);
+/* copies one analysis array to host memory; returns the number of bytes through *bytes_out. dst may be NULL to query */
+int spmv_b200_plan_export(spmv_b200_plan *plan, int32_t what, void *h_dst, int64_t capacity_bytes, int64_t *bytes_out);
+
+/* ---- stateless entry points with the reference's argument lists (device pointers, null stream) ---- */
+int spmv_b200_csr_spmv(int32_t trans, double alpha, double beta, int32_t m, int32_t n, int32_t nnz,
+                       const int32_t *d_rowptr, const int32_t *d_colidx, const double *d_val, const double *d_x,
+                       double *d_y);
+int spmv_b200_sparse_spmv(int32_t trans, double alpha, double beta, int32_t m, int32_t n, const int32_t *d_rowptr,
+                          const int32_t *d_colidx, const double *d_val, const double *d_x, double *d_y);
+int spmv_b200_cache_invalidate(void); /* drop every cached plan (call after rewriting a matrix in place) */
+int spmv_b200_cache_size(void);
+
+/* ---- host-buffer path: matrix uploaded and analysed once, vectors copied every call ---- */
+int spmv_b200_hostmat_create(spmv_b200_hostmat **out, int32_t m, int32_t n, int64_t nnz, const int32_t *h_rowptr,
+                             const int32_t *h_colidx, const double *h_val, const spmv_b200_options *opt);
+int spmv_b200_hostmat_spmv(spmv_b200_hostmat *hm, double alpha, double beta, const double *h_x, double *h_y);
+int spmv_b200_hostmat_destroy(spmv_b200_hostmat *hm);
+/* one-shot: upload, analyse, multiply, download, free */
+int spmv_b200_host_spmv(double alpha, double beta, int32_t m, int32_t n, int64_t nnz, const int32_t *h_rowptr,
+                        const int32_t *h_colidx, const double *h_val, const double *h_x, double *h_y);
+
+/* ---- row sharding for multi-GPU runs: bounds[g] = lower_bound(rowptr, g*nnz/nshards), bounds[nshards] = m ---- */
+int spmv_b200_shard_bounds(int32_t m, int64_t nnz, const int32_t *d_rowptr, int32_t nshards, int32_t *h_bounds,
+                           void *stream);
+/* blocks of x (block = 2^block_shift entries) referenced by the matrix: h_bitmap[b] = 1 if any colidx lies in block b */
+int spmv_b200_col_block_bitmap(int64_t nnz, const int32_t *d_colidx, int32_t n, int32_t block_shift,
+                               uint8_t *h_bitmap, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPMV_B200_H */

@@ -1,0 +1,220 @@
+"""Host-side mirror of the reference's kernel API for the `cuda-b200` strategy.
+
+Names and argument meaning follow the reference (all citations relative to the reference tree):
+  * ``CsrDesc``            <-> ``csr_desc<int,double>``  (src/acc/api/types.h:25-41)
+  * ``sparse_csr_spmv``    <-> ``sparse_csr_spmv(trans, alpha, beta, h_csr_desc, d_csr_desc, dx, dy)``
+                               (src/acc/api/spmv.h:20-21, dispatch in src/acc/strategy_picker.cpp:19-65)
+  * ``sparse_spmv``        <-> deprecated 10-argument entry (src/acc/api/spmv.h:27-28, spmv_imp.cpp:10-18)
+  * ``SpmvPlan``           <-> analyze / kernel / destroy of csr-adaptive-plus
+                               (src/acc/hip-csr-adaptive-plus/csr_adaptive_plus_spmv.cpp:16-73)
+  * ``HostMatrix``         <-> the CLI's host-buffer pattern (cli/utils.hpp:94-116, cli/main.cpp:99-118)
+
+Everything calls the C ABI of ``libspmv_b200.so`` through ctypes with raw device pointers; torch is used only to
+own device memory and streams. y is updated in place, like the reference. Errors raise ``SpmvB200Error`` (the C++
+launcher raises ``std::runtime_error``, which the reference harness catches: benchmark/csr_spmv.hpp:52-62).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import FLAG_BETA0_SKIP_Y, FLAG_NO_TMA, Options, PlanInfo, SpmvB200Error, check  # noqa: F401
+
+operation_none = 0       # src/acc/api/types.h:8
+operation_transpose = 1
+
+
+def _ptr(t: Any) -> int:
+    """Raw address of a torch tensor / numpy array / int."""
+    if t is None:
+        return 0
+    if isinstance(t, int):
+        return t
+    if hasattr(t, "data_ptr"):
+        return int(t.data_ptr())
+    if isinstance(t, np.ndarray):
+        return int(t.ctypes.data)
+    raise TypeError(f"cannot take the address of {type(t)}")
+
+
+def _current_stream() -> int:
+    import torch
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+@dataclass
+class CsrDesc:
+    """Non-owning CSR view: rows, cols, nnz and three arrays (int32 row_ptr[rows+1], int32 col_index[nnz], fp64 values[nnz])."""
+    rows: int
+    cols: int
+    nnz: int
+    row_ptr: Any
+    col_index: Any
+    values: Any
+
+    def as_const(self) -> "CsrDesc":  # var_csr_desc::as_const, src/acc/api/types.h:22
+        return self
+
+
+def _require_device(t: Any, name: str, dtype: str) -> None:
+    if hasattr(t, "is_cuda"):
+        if not t.is_cuda:
+            raise SpmvB200Error(f"{name} must live in device memory (got a CPU tensor); there is no CPU fallback")
+        if str(t.dtype) != f"torch.{dtype}":
+            raise SpmvB200Error(f"{name} must be {dtype}, got {t.dtype}")
+        if not t.is_contiguous():
+            raise SpmvB200Error(f"{name} must be contiguous")
+
+
+def sparse_csr_spmv(trans: int, alpha: float, beta: float, h_csr_desc: Optional[CsrDesc], d_csr_desc: CsrDesc,
+                    dx: Any, dy: Any) -> None:
+    """y = alpha*A*x + beta*y on the current device, in place on ``dy``; returns without synchronising.
+
+    ``h_csr_desc`` is accepted for signature compatibility and never dereferenced (it may alias device memory when
+    entered through ``sparse_spmv``, see src/acc/api/spmv_imp.cpp:14-17)."""
+    d = d_csr_desc
+    _require_device(d.row_ptr, "d_csr_desc.row_ptr", "int32")
+    _require_device(d.col_index, "d_csr_desc.col_index", "int32")
+    _require_device(d.values, "d_csr_desc.values", "float64")
+    _require_device(dx, "dx", "float64")
+    _require_device(dy, "dy", "float64")
+    rc = _lib.lib().spmv_b200_csr_spmv(int(trans), float(alpha), float(beta), int(d.rows), int(d.cols), int(d.nnz),
+                                       _ptr(d.row_ptr), _ptr(d.col_index), _ptr(d.values), _ptr(dx), _ptr(dy))
+    check(rc, "sparse_csr_spmv")
+
+
+def sparse_spmv(htrans: int, halpha: float, hbeta: float, hm: int, hn: int, rowptr: Any, colindex: Any, value: Any,
+                x: Any, y: Any) -> None:
+    """The deprecated C-style entry of the reference with its exact argument list (device pointers)."""
+    for t, nme, dt in ((rowptr, "rowptr", "int32"), (colindex, "colindex", "int32"), (value, "value", "float64"),
+                       (x, "x", "float64"), (y, "y", "float64")):
+        _require_device(t, nme, dt)
+    rc = _lib.lib().spmv_b200_sparse_spmv(int(htrans), float(halpha), float(hbeta), int(hm), int(hn), _ptr(rowptr),
+                                          _ptr(colindex), _ptr(value), _ptr(x), _ptr(y))
+    check(rc, "sparse_spmv")
+
+
+def cache_invalidate() -> None:
+    check(_lib.lib().spmv_b200_cache_invalidate(), "cache_invalidate")
+
+
+def cache_size() -> int:
+    return int(_lib.lib().spmv_b200_cache_size())
+
+
+def make_options(tile_nnz: int = 0, short_max: int = 0, medium_max: int = 0, vec_div: int = 0,
+                 flags: int = 0) -> Options:
+    return Options(tile_nnz, short_max, medium_max, vec_div, flags)
+
+
+class SpmvPlan:
+    """One-time row analysis + repeated execution (analyze / kernel / destroy)."""
+
+    def __init__(self, d_csr_desc: CsrDesc, options: Optional[Options] = None, stream: Optional[int] = None):
+        d = d_csr_desc
+        _require_device(d.row_ptr, "row_ptr", "int32")
+        _require_device(d.col_index, "col_index", "int32")
+        _require_device(d.values, "values", "float64")
+        self._keep = (d.row_ptr, d.col_index, d.values)  # the plan borrows these device arrays
+        self._h = C.c_void_p()
+        self.desc = d
+        rc = _lib.lib().spmv_b200_plan_create(C.byref(self._h), int(d.rows), int(d.cols), int(d.nnz),
+                                              _ptr(d.row_ptr), _ptr(d.col_index), _ptr(d.values),
+                                              C.byref(options) if options is not None else None,
+                                              _current_stream() if stream is None else stream)
+        check(rc, "plan_create")
+
+    def execute(self, alpha: float, beta: float, dx: Any, dy: Any, stream: Optional[int] = None) -> None:
+        if not self._h:
+            raise SpmvB200Error("plan was destroyed")
+        _require_device(dx, "dx", "float64")
+        _require_device(dy, "dy", "float64")
+        rc = _lib.lib().spmv_b200_execute(self._h, float(alpha), float(beta), _ptr(dx), _ptr(dy),
+                                          _current_stream() if stream is None else stream)
+        check(rc, "execute")
+
+    def info(self) -> PlanInfo:
+        out = PlanInfo()
+        check(_lib.lib().spmv_b200_plan_get_info(self._h, C.byref(out)), "plan_get_info")
+        return out
+
+    def export(self, name: str) -> np.ndarray:
+        what = _lib.EXPORT_IDS[name]
+        nbytes = C.c_int64(0)
+        check(_lib.lib().spmv_b200_plan_export(self._h, what, None, 0, C.byref(nbytes)), "plan_export(size)")
+        dt = np.dtype(_lib.EXPORT_DTYPES[name])
+        out = np.zeros(nbytes.value // dt.itemsize, dtype=dt)
+        if nbytes.value:
+            check(_lib.lib().spmv_b200_plan_export(self._h, what, out.ctypes.data, nbytes.value, None), "plan_export")
+        return out
+
+    def destroy(self) -> None:
+        if self._h:
+            h, self._h = self._h, C.c_void_p()
+            check(_lib.lib().spmv_b200_plan_destroy(h), "plan_destroy")
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class HostMatrix:
+    """Matrix given in host memory: uploaded + analysed once; every ``spmv`` copies x, y0 in and y out."""
+
+    def __init__(self, rows: int, cols: int, rowptr: np.ndarray, colindex: np.ndarray, value: np.ndarray,
+                 options: Optional[Options] = None):
+        self._h = C.c_void_p()
+        self.rows, self.cols, self.nnz = int(rows), int(cols), int(len(value))
+        rc = _lib.lib().spmv_b200_hostmat_create(C.byref(self._h), self.rows, self.cols, self.nnz, _ptr(rowptr),
+                                                 _ptr(colindex), _ptr(value),
+                                                 C.byref(options) if options is not None else None)
+        check(rc, "hostmat_create")
+
+    def spmv(self, alpha: float, beta: float, h_x: Any, h_y: Any) -> None:
+        check(_lib.lib().spmv_b200_hostmat_spmv(self._h, float(alpha), float(beta), _ptr(h_x), _ptr(h_y)),
+              "hostmat_spmv")
+
+    def destroy(self) -> None:
+        if self._h:
+            h, self._h = self._h, C.c_void_p()
+            check(_lib.lib().spmv_b200_hostmat_destroy(h), "hostmat_destroy")
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def host_spmv(alpha: float, beta: float, rows: int, cols: int, rowptr: np.ndarray, colindex: np.ndarray,
+              value: np.ndarray, x: np.ndarray, y: np.ndarray) -> None:
+    """One-shot host-buffer SpMV on the GPU (upload, analyse, multiply, download). In place on ``y``."""
+    rc = _lib.lib().spmv_b200_host_spmv(float(alpha), float(beta), int(rows), int(cols), int(len(value)),
+                                        _ptr(rowptr), _ptr(colindex), _ptr(value), _ptr(x), _ptr(y))
+    check(rc, "host_spmv")
+
+
+def shard_bounds(d_rowptr: Any, rows: int, nshards: int) -> np.ndarray:
+    """nnz-balanced contiguous row shards: bounds[g] = lower_bound(rowptr, g*nnz/nshards) (int32, length nshards+1)."""
+    _require_device(d_rowptr, "rowptr", "int32")
+    out = np.zeros(nshards + 1, dtype=np.int32)
+    check(_lib.lib().spmv_b200_shard_bounds(int(rows), -1, _ptr(d_rowptr), int(nshards), out.ctypes.data,
+                                            _current_stream()), "shard_bounds")
+    return out
+
+
+def col_block_bitmap(d_colindex: Any, nnz: int, cols: int, block_shift: int) -> np.ndarray:
+    """uint8 bitmap over blocks of 2^block_shift entries of x: 1 if the matrix references the block."""
+    nblocks = (cols + (1 << block_shift) - 1) >> block_shift
+    out = np.zeros(nblocks, dtype=np.uint8)
+    if nnz > 0:
+        _require_device(d_colindex, "colindex", "int32")
+    check(_lib.lib().spmv_b200_col_block_bitmap(int(nnz), _ptr(d_colindex), int(cols), int(block_shift),
+                                                out.ctypes.data, _current_stream()), "col_block_bitmap")
+    return out

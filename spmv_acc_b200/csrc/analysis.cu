@@ -1,0 +1,359 @@
+// One-time row analysis of a CSR matrix (part 1 of the hot path): bins rows by nnz, cuts the nnz range into
+// nnz-balanced row blocks ("tiles"), decides which long rows are split across tiles, and tags every tile with the
+// kernel kind that will stream it. Every output is an integer array and is reproduced bit-for-bit by the CPU
+// restatement in oracle/analysis_port.c.
+//
+// Reference analogues (what this replaces, not how): the serial host analysis of csr-adaptive-plus
+// (src/acc/hip-csr-adaptive-plus/csr_adaptive_plus_analyze.cpp:12-98), the break-point pre-pass of flat
+// (src/acc/hip-flat/flat_imp.inl:107-152), the merge-path partition (benchmark/merge-path/merge_path_partition.h:7-17)
+// and the 4-sample selector of adaptive (src/acc/hip-adaptive/adaptive.cpp:16-67).
+//
+// Specification (T = tile_nnz, L = medium_max, S = short_max, base = rowptr[0], end = rowptr[m]):
+//   ntiles      = max(1, ceil((end-base)/T)) if m > 0 else 0
+//   target(t)   = min(base + t*T, end)
+//   tile_row[t] = 0 if t == 0; m if t == ntiles; else min{ r in [0,m] : rowptr[r] >= target(t) }
+//   tile_part[t]= max{ r in [0,m] : rowptr[r] <= target(t) }            (the reference's merge-path partition S[t])
+//   a row "straddles" boundary t (0 < t < ntiles) when rowptr[tile_row[t]] > target(t); it is row tile_row[t]-1.
+//   tile_split[t] = 1 iff the straddling row is longer than L (its partial sums are combined by the fix-up kernel);
+//                   a straddling row of length <= L is streamed entirely by the tile that owns its first element.
+//   tile_elem[t]  = base if t == 0; end if t == ntiles; target(t) if tile_split[t]; else rowptr[tile_row[t]]
+//   row r is owned by tile min(floor((rowptr[r]-base)/T), ntiles-1); tile_maxlen[t] = max nnz of the rows it owns.
+//   tile_kind[t]  = MIXED if tile_split[t] or tile_split[t+1] or tile_maxlen[t] > L;
+//                   SHORT if tile_maxlen[t] <= S; else MEDIUM.
+//   bin(r) = SHORT if nnz_r <= S; MEDIUM if nnz_r <= L; LONG if nnz_r <= T; else VERYLONG.
+#include <algorithm>
+#include <vector>
+
+#include "internal.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ int lower_bound_rowptr(const int *__restrict__ rowptr, int m, long long target) {
+  // first index in [0, m] with rowptr[idx] >= target (rowptr[m] >= target is guaranteed by the caller)
+  int lo = 0, hi = m;
+  while (lo < hi) {
+    const int mid = lo + ((hi - lo) >> 1);
+    if ((long long)__ldg(rowptr + mid) < target)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ int last_le_rowptr(const int *__restrict__ rowptr, int m, long long target) {
+  // largest index in [0, m] with rowptr[idx] <= target (rowptr[0] <= target is guaranteed by the caller)
+  int lo = 0, hi = m + 1;
+  while (lo < hi - 1) {
+    const int mid = lo + ((hi - lo) >> 1);
+    if ((long long)__ldg(rowptr + mid) <= target)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256)
+    k_tile_bounds(const int *__restrict__ rowptr, int m, int ntiles, int T, int medium_max, int *__restrict__ tile_row,
+                  int *__restrict__ tile_elem, unsigned char *__restrict__ tile_split, int *__restrict__ tile_part,
+                  int *__restrict__ tile_aux) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > ntiles)
+    return;
+  const long long base = __ldg(rowptr);
+  const long long end = __ldg(rowptr + m);
+  long long target = base + (long long)t * T;
+  if (target > end)
+    target = end;
+  int row, elem, aux = 0;
+  unsigned char split = 0;
+  if (t == 0) {
+    row = 0;
+    elem = (int)base;
+  } else if (t == ntiles) {
+    row = m;
+    elem = (int)end;
+  } else {
+    row = lower_bound_rowptr(rowptr, m, target);
+    const int row_start = __ldg(rowptr + row);
+    elem = row_start;
+    if ((long long)row_start > target) { // row-1 straddles this boundary
+      const int len = row_start - __ldg(rowptr + row - 1);
+      if (len > medium_max) {
+        split = 1;
+        elem = (int)target;
+        aux = row_start; // end of the split row
+      }
+    }
+  }
+  tile_row[t] = row;
+  tile_elem[t] = elem;
+  tile_split[t] = split;
+  tile_aux[t] = aux;
+  tile_part[t] = last_le_rowptr(rowptr, m, target);
+}
+
+__global__ void __launch_bounds__(256)
+    k_row_stats(const int *__restrict__ rowptr, int m, int ntiles, int T, int short_max, int medium_max,
+                int *__restrict__ tile_maxlen, unsigned long long *__restrict__ hist /* [8] rows[4] | nnz[4] */) {
+  __shared__ unsigned long long sh[8];
+  if (threadIdx.x < 8)
+    sh[threadIdx.x] = 0ull;
+  __syncthreads();
+  const long long base = __ldg(rowptr);
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += (long long)gridDim.x * blockDim.x) {
+    const int s = __ldg(rowptr + r);
+    const int len = __ldg(rowptr + r + 1) - s;
+    const int bin = len <= short_max ? 0 : (len <= medium_max ? 1 : (len <= T ? 2 : 3));
+    atomicAdd(&sh[bin], 1ull);
+    atomicAdd(&sh[4 + bin], (unsigned long long)len);
+    long long t = ((long long)s - base) / T;
+    if (t > ntiles - 1)
+      t = ntiles - 1;
+    if (len > 0)
+      atomicMax(tile_maxlen + t, len);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && sh[threadIdx.x] != 0ull)
+    atomicAdd(hist + threadIdx.x, sh[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256)
+    k_tile_kind(int ntiles, int short_max, int medium_max, const int *__restrict__ tile_maxlen,
+                const unsigned char *__restrict__ tile_split, unsigned char *__restrict__ tile_kind) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles)
+    return;
+  const int ml = tile_maxlen[t];
+  unsigned char k;
+  if (tile_split[t] || tile_split[t + 1] || ml > medium_max)
+    k = SPMV_B200_KIND_MIXED;
+  else if (ml <= short_max)
+    k = SPMV_B200_KIND_SHORT;
+  else
+    k = SPMV_B200_KIND_MEDIUM;
+  tile_kind[t] = k;
+}
+
+__global__ void __launch_bounds__(256) k_row_bins(const int *__restrict__ rowptr, int m, int T, int short_max,
+                                                   int medium_max, unsigned char *__restrict__ out) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += (long long)gridDim.x * blockDim.x) {
+    const int len = __ldg(rowptr + r + 1) - __ldg(rowptr + r);
+    out[r] = (unsigned char)(len <= short_max ? 0 : (len <= medium_max ? 1 : (len <= T ? 2 : 3)));
+  }
+}
+
+__global__ void __launch_bounds__(256) k_shard_bounds(const int *__restrict__ rowptr, int m, int nshards,
+                                                       int *__restrict__ bounds) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > nshards)
+    return;
+  const long long base = __ldg(rowptr);
+  const long long total = (long long)__ldg(rowptr + m) - base;
+  if (g == 0)
+    bounds[g] = 0;
+  else if (g == nshards)
+    bounds[g] = m;
+  else
+    bounds[g] = lower_bound_rowptr(rowptr, m, base + (total * g) / nshards);
+}
+
+__global__ void __launch_bounds__(256)
+    k_col_block_bitmap(const int *__restrict__ col, long long nnz, int block_shift, unsigned int *__restrict__ bitmap) {
+  // bitmap is one 32-bit word per block (0/1); integer OR is order independent, hence deterministic.
+  int last = -1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (long long)gridDim.x * blockDim.x) {
+    const int b = __ldg(col + i) >> block_shift;
+    if (b != last) {
+      if (bitmap[b] == 0u)
+        bitmap[b] = 1u;
+      last = b;
+    }
+  }
+}
+
+static inline int grid_for(long long n, int threads, int cap) {
+  long long g = (n + threads - 1) / threads;
+  if (g < 1)
+    g = 1;
+  if (g > cap)
+    g = cap;
+  return (int)g;
+}
+
+int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
+  const int m = p->m;
+  if (m == 0) {
+    p->ntiles = 0;
+    return SPMV_B200_OK;
+  }
+  // base / end of the nnz range (rowptr may be a view into a larger matrix: rowptr[0] need not be 0)
+  int h_be[2];
+  B200_CUDA(cudaMemcpyAsync(&h_be[0], p->rowptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  B200_CUDA(cudaMemcpyAsync(&h_be[1], p->rowptr + m, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  B200_CUDA(cudaStreamSynchronize(stream));
+  const long long total = (long long)h_be[1] - (long long)h_be[0];
+  if (total < 0) {
+    set_error("rowptr is not monotone: rowptr[m] < rowptr[0]");
+    return SPMV_B200_ERR_ARG;
+  }
+  if (p->nnz >= 0 && p->nnz != total) {
+    set_error("nnz argument does not match rowptr[m] - rowptr[0]");
+    return SPMV_B200_ERR_ARG;
+  }
+  p->nnz = total;
+  p->elem_end = h_be[1];
+  const long long nt = std::max<long long>(1, (total + p->T - 1) / p->T);
+  if (nt > 0x7ffffff0LL) {
+    set_error("too many tiles");
+    return SPMV_B200_ERR_ARG;
+  }
+  const int ntiles = (int)nt;
+  p->ntiles = ntiles;
+
+  int *tile_aux = nullptr;
+  unsigned long long *d_hist = nullptr;
+  size_t ws = 0;
+  B200_CUDA(cudaMalloc(&p->tile_row, sizeof(int) * (ntiles + 1)));
+  B200_CUDA(cudaMalloc(&p->tile_elem, sizeof(int) * (ntiles + 1)));
+  B200_CUDA(cudaMalloc(&p->tile_part, sizeof(int) * (ntiles + 1)));
+  B200_CUDA(cudaMalloc(&p->tile_split, ntiles + 1));
+  B200_CUDA(cudaMalloc(&p->tile_maxlen, sizeof(int) * ntiles));
+  B200_CUDA(cudaMalloc(&p->tile_kind, ntiles));
+  B200_CUDA(cudaMalloc(&tile_aux, sizeof(int) * (ntiles + 1)));
+  B200_CUDA(cudaMalloc(&d_hist, sizeof(unsigned long long) * 8));
+  ws += sizeof(int) * (size_t)(ntiles + 1) * 3 + (ntiles + 1) + sizeof(int) * (size_t)ntiles + ntiles;
+  B200_CUDA(cudaMemsetAsync(p->tile_maxlen, 0, sizeof(int) * ntiles, stream));
+  B200_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 8, stream));
+
+  k_tile_bounds<<<grid_for(ntiles + 1, 256, 1 << 30), 256, 0, stream>>>(p->rowptr, m, ntiles, p->T, p->medium_max,
+                                                                         p->tile_row, p->tile_elem, p->tile_split,
+                                                                         p->tile_part, tile_aux);
+  k_row_stats<<<grid_for(m, 256, 148 * 16), 256, 0, stream>>>(p->rowptr, m, ntiles, p->T, p->short_max, p->medium_max,
+                                                               p->tile_maxlen, d_hist);
+  k_tile_kind<<<grid_for(ntiles, 256, 1 << 30), 256, 0, stream>>>(ntiles, p->short_max, p->medium_max, p->tile_maxlen,
+                                                                   p->tile_split, p->tile_kind);
+  B200_CUDA(cudaGetLastError());
+
+  // finalise on the host: compact per-kind tile lists (ascending tile id) and the split-row table
+  std::vector<unsigned char> h_kind(ntiles), h_split(ntiles + 1);
+  std::vector<int> h_row(ntiles + 1), h_aux(ntiles + 1);
+  unsigned long long h_hist[8];
+  B200_CUDA(cudaMemcpyAsync(h_kind.data(), p->tile_kind, ntiles, cudaMemcpyDeviceToHost, stream));
+  B200_CUDA(cudaMemcpyAsync(h_split.data(), p->tile_split, ntiles + 1, cudaMemcpyDeviceToHost, stream));
+  B200_CUDA(cudaMemcpyAsync(h_row.data(), p->tile_row, sizeof(int) * (ntiles + 1), cudaMemcpyDeviceToHost, stream));
+  B200_CUDA(cudaMemcpyAsync(h_aux.data(), tile_aux, sizeof(int) * (ntiles + 1), cudaMemcpyDeviceToHost, stream));
+  B200_CUDA(cudaMemcpyAsync(h_hist, d_hist, sizeof(h_hist), cudaMemcpyDeviceToHost, stream));
+  B200_CUDA(cudaStreamSynchronize(stream));
+  B200_CUDA(cudaFree(tile_aux));
+  B200_CUDA(cudaFree(d_hist));
+  for (int b = 0; b < 4; ++b) {
+    p->bin_rows[b] = (long long)h_hist[b];
+    p->bin_nnz[b] = (long long)h_hist[4 + b];
+  }
+
+  std::vector<int> lists[3];
+  for (int t = 0; t < ntiles; ++t)
+    lists[h_kind[t]].push_back(t);
+  for (int k = 0; k < 3; ++k) {
+    p->count[k] = (int)lists[k].size();
+    // when every tile has the same kind the kernel indexes tiles by blockIdx directly (no list)
+    if (p->count[k] > 0 && p->count[k] < ntiles) {
+      B200_CUDA(cudaMalloc(&p->list[k], sizeof(int) * lists[k].size()));
+      B200_CUDA(cudaMemcpyAsync(p->list[k], lists[k].data(), sizeof(int) * lists[k].size(), cudaMemcpyHostToDevice,
+                                stream));
+      ws += sizeof(int) * lists[k].size();
+    }
+  }
+  // split rows: boundary t is the first split boundary of its row iff the row is owned by tile t-1
+  std::vector<int> srow, st0, st1;
+  const long long base = h_be[0];
+  for (int t = 1; t < ntiles; ++t) {
+    if (!h_split[t])
+      continue;
+    const int r = h_row[t] - 1;
+    if (h_row[t - 1] <= r) { // row r starts in tile t-1
+      srow.push_back(r);
+      st0.push_back(t - 1);
+      long long t1 = ((long long)h_aux[t] - 1 - base) / p->T;
+      if (t1 > ntiles - 1)
+        t1 = ntiles - 1;
+      st1.push_back((int)t1);
+    }
+  }
+  p->nsplit = (int)srow.size();
+  if (p->nsplit > 0) {
+    std::vector<int> packed;
+    packed.reserve(3 * srow.size());
+    packed.insert(packed.end(), srow.begin(), srow.end());
+    packed.insert(packed.end(), st0.begin(), st0.end());
+    packed.insert(packed.end(), st1.begin(), st1.end());
+    B200_CUDA(cudaMalloc(&p->split_rows, sizeof(int) * packed.size()));
+    B200_CUDA(cudaMemcpyAsync(p->split_rows, packed.data(), sizeof(int) * packed.size(), cudaMemcpyHostToDevice,
+                              stream));
+    B200_CUDA(cudaMalloc(&p->partials, sizeof(double) * 2 * (size_t)ntiles));
+    B200_CUDA(cudaMemsetAsync(p->partials, 0, sizeof(double) * 2 * (size_t)ntiles, stream));
+    ws += sizeof(int) * packed.size() + sizeof(double) * 2 * (size_t)ntiles;
+  }
+  B200_CUDA(cudaStreamSynchronize(stream));
+  p->workspace_bytes = ws;
+  return SPMV_B200_OK;
+}
+
+int analysis_row_bins(const spmv_b200_plan *p, unsigned char *d_out, cudaStream_t stream) {
+  if (p->m == 0)
+    return SPMV_B200_OK;
+  k_row_bins<<<grid_for(p->m, 256, 148 * 16), 256, 0, stream>>>(p->rowptr, p->m, p->T, p->short_max, p->medium_max,
+                                                                 d_out);
+  B200_CUDA(cudaGetLastError());
+  return SPMV_B200_OK;
+}
+
+int shard_bounds_run(int m, long long nnz, const int *d_rowptr, int nshards, int *h_bounds, cudaStream_t stream) {
+  (void)nnz;
+  if (nshards < 1 || m < 0) {
+    set_error("shard_bounds: nshards must be >= 1 and m >= 0");
+    return SPMV_B200_ERR_ARG;
+  }
+  if (m == 0) {
+    for (int g = 0; g <= nshards; ++g)
+      h_bounds[g] = 0;
+    return SPMV_B200_OK;
+  }
+  int *d_bounds = nullptr;
+  B200_CUDA(cudaMalloc(&d_bounds, sizeof(int) * (nshards + 1)));
+  k_shard_bounds<<<grid_for(nshards + 1, 256, 1 << 20), 256, 0, stream>>>(d_rowptr, m, nshards, d_bounds);
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(h_bounds, d_bounds, sizeof(int) * (nshards + 1), cudaMemcpyDeviceToHost, stream));
+  B200_CUDA(cudaStreamSynchronize(stream));
+  B200_CUDA(cudaFree(d_bounds));
+  return SPMV_B200_OK;
+}
+
+int col_block_bitmap_run(long long nnz, const int *d_col, int n, int block_shift, unsigned char *h_bitmap,
+                         cudaStream_t stream) {
+  if (block_shift < 0 || block_shift > 30 || n < 0) {
+    set_error("col_block_bitmap: bad block_shift or n");
+    return SPMV_B200_ERR_ARG;
+  }
+  const long long nblocks = ((long long)n + (1LL << block_shift) - 1) >> block_shift;
+  if (nblocks == 0)
+    return SPMV_B200_OK;
+  unsigned int *d_bm = nullptr;
+  B200_CUDA(cudaMalloc(&d_bm, sizeof(unsigned int) * nblocks));
+  B200_CUDA(cudaMemsetAsync(d_bm, 0, sizeof(unsigned int) * nblocks, stream));
+  if (nnz > 0) {
+    k_col_block_bitmap<<<grid_for(nnz, 256, 148 * 16), 256, 0, stream>>>(d_col, nnz, block_shift, d_bm);
+    B200_CUDA(cudaGetLastError());
+  }
+  std::vector<unsigned int> h(nblocks);
+  B200_CUDA(cudaMemcpyAsync(h.data(), d_bm, sizeof(unsigned int) * nblocks, cudaMemcpyDeviceToHost, stream));
+  B200_CUDA(cudaStreamSynchronize(stream));
+  B200_CUDA(cudaFree(d_bm));
+  for (long long b = 0; b < nblocks; ++b)
+    h_bitmap[b] = h[b] ? 1 : 0;
+  return SPMV_B200_OK;
+}
+
+} // namespace b200

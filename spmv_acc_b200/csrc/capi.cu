@@ -1,0 +1,445 @@
+// C ABI of libspmv_b200.so (declared in include/spmv_b200.h).
+//
+// Plan lifecycle mirrors the analyze / kernel / destroy phases of the reference's csr-adaptive-plus strategy
+// (src/acc/hip-csr-adaptive-plus/csr_adaptive_plus_spmv.cpp:16-73); the stateless entry points mirror
+// sparse_csr_spmv (src/acc/api/spmv.h:20-21) and the deprecated sparse_spmv (src/acc/api/spmv_imp.cpp:10-18).
+#include <cstdio>
+#include <cstring>
+#include <list>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "internal.cuh"
+
+namespace b200 {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  char buf[512];
+  std::snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+  g_last_error = buf;
+  return SPMV_B200_ERR_CUDA;
+}
+
+static int free_plan_arrays(spmv_b200_plan *p) {
+  void *ptrs[] = {p->tile_row, p->tile_elem, p->tile_split, p->tile_part, p->tile_maxlen, p->tile_kind,
+                  p->list[0],  p->list[1],   p->list[2],    p->split_rows, p->partials};
+  int rc = SPMV_B200_OK;
+  for (void *q : ptrs)
+    if (q && cudaFree(q) != cudaSuccess)
+      rc = SPMV_B200_ERR_CUDA;
+  return rc;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int spmv_b200_abi_version(void) { return SPMV_B200_ABI_VERSION; }
+
+const char *spmv_b200_last_error(void) { return g_last_error.c_str(); }
+
+int spmv_b200_plan_create(spmv_b200_plan **out, int32_t m, int32_t n, int64_t nnz, const int32_t *d_rowptr,
+                          const int32_t *d_colidx, const double *d_val, const spmv_b200_options *opt, void *stream) {
+  if (!out) {
+    set_error("plan_create: out is NULL");
+    return SPMV_B200_ERR_ARG;
+  }
+  *out = nullptr;
+  if (m < 0 || n < 0 || nnz > 0x7fffffffLL) {
+    set_error("plan_create: m, n must be >= 0 and nnz < 2^31 (int32 indices)");
+    return SPMV_B200_ERR_ARG;
+  }
+  if (m > 0 && !d_rowptr) {
+    set_error("plan_create: rowptr is NULL");
+    return SPMV_B200_ERR_ARG;
+  }
+  spmv_b200_plan *p = new (std::nothrow) spmv_b200_plan();
+  if (!p) {
+    set_error("plan_create: out of host memory");
+    return SPMV_B200_ERR_ARG;
+  }
+  p->m = m;
+  p->n = n;
+  p->nnz = nnz; // < 0: take it from rowptr
+  p->rowptr = d_rowptr;
+  p->col = d_colidx;
+  p->val = d_val;
+  p->T = (opt && opt->tile_nnz) ? opt->tile_nnz : kDefaultTile;
+  p->short_max = (opt && opt->short_max) ? opt->short_max : kDefaultShort;
+  p->medium_max = (opt && opt->medium_max) ? opt->medium_max : kDefaultMedium;
+  p->vec_div = (opt && opt->vec_div) ? opt->vec_div : kDefaultVecDiv;
+  p->flags = opt ? opt->flags : 0u;
+  if (p->T < 256 || p->T > 16384 || (p->T % 256) != 0 || p->medium_max < 4 || (p->medium_max % 4) != 0 ||
+      p->medium_max > p->T || p->short_max < 1 || p->short_max > p->medium_max || p->vec_div < 1) {
+    set_error("plan_create: invalid options (tile_nnz multiple of 256 in [256,16384]; medium_max multiple of 4 in "
+              "[4,tile_nnz]; 1 <= short_max <= medium_max; vec_div >= 1)");
+    delete p;
+    return SPMV_B200_ERR_ARG;
+  }
+  const bool aligned = ((reinterpret_cast<uintptr_t>(d_val) & 15u) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(d_colidx) & 15u) == 0);
+  p->uses_tma = aligned && !(p->flags & SPMV_B200_FLAG_NO_TMA);
+  int rc = kernels_configure(p);
+  if (rc == SPMV_B200_OK)
+    rc = analysis_run(p, static_cast<cudaStream_t>(stream));
+  if (rc != SPMV_B200_OK) {
+    free_plan_arrays(p);
+    delete p;
+    return rc;
+  }
+  if (p->nnz > 0 && (!d_colidx || !d_val)) {
+    set_error("plan_create: colidx / val is NULL but the matrix has non-zeros");
+    free_plan_arrays(p);
+    delete p;
+    return SPMV_B200_ERR_ARG;
+  }
+  *out = p;
+  return SPMV_B200_OK;
+}
+
+int spmv_b200_execute(spmv_b200_plan *plan, double alpha, double beta, const double *d_x, double *d_y, void *stream) {
+  if (!plan) {
+    set_error("execute: plan is NULL");
+    return SPMV_B200_ERR_ARG;
+  }
+  if ((plan->m > 0 && !d_y) || (plan->nnz > 0 && !d_x)) {
+    set_error("execute: x or y is NULL");
+    return SPMV_B200_ERR_ARG;
+  }
+  return kernels_launch(plan, alpha, beta, d_x, d_y, static_cast<cudaStream_t>(stream));
+}
+
+int spmv_b200_plan_destroy(spmv_b200_plan *plan) {
+  if (!plan)
+    return SPMV_B200_OK;
+  const int rc = free_plan_arrays(plan);
+  delete plan;
+  if (rc != SPMV_B200_OK)
+    set_error("plan_destroy: cudaFree failed");
+  return rc;
+}
+
+int spmv_b200_plan_get_info(const spmv_b200_plan *p, spmv_b200_plan_info *info) {
+  if (!p || !info) {
+    set_error("plan_get_info: NULL argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  std::memset(info, 0, sizeof(*info));
+  info->m = p->m;
+  info->n = p->n;
+  info->nnz = p->nnz;
+  info->tile_nnz = p->T;
+  info->short_max = p->short_max;
+  info->medium_max = p->medium_max;
+  info->vec_div = p->vec_div;
+  info->flags = p->flags;
+  info->uses_tma = p->uses_tma ? 1 : 0;
+  info->ntiles = p->ntiles;
+  int launches = 0;
+  for (int k = 0; k < 3; ++k) {
+    info->tiles_per_kind[k] = p->count[k];
+    launches += p->count[k] > 0 ? 1 : 0;
+  }
+  launches += p->nsplit > 0 ? 1 : 0;
+  info->nsplit_rows = p->nsplit;
+  info->launches_per_execute = launches;
+  for (int b = 0; b < 4; ++b) {
+    info->bin_rows[b] = p->bin_rows[b];
+    info->bin_nnz[b] = p->bin_nnz[b];
+  }
+  info->smem_bytes = (int64_t)p->smem_bytes;
+  info->workspace_bytes = (int64_t)p->workspace_bytes;
+  return SPMV_B200_OK;
+}
+
+int spmv_b200_plan_export(spmv_b200_plan *p, int32_t what, void *h_dst, int64_t capacity_bytes, int64_t *bytes_out) {
+  if (!p) {
+    set_error("plan_export: plan is NULL");
+    return SPMV_B200_ERR_ARG;
+  }
+  const void *src = nullptr;
+  int64_t bytes = 0;
+  const int64_t nt = p->ntiles;
+  switch (what) {
+  case SPMV_B200_EXPORT_TILE_ROW:
+    src = p->tile_row;
+    bytes = p->m > 0 ? 4 * (nt + 1) : 0;
+    break;
+  case SPMV_B200_EXPORT_TILE_ELEM:
+    src = p->tile_elem;
+    bytes = p->m > 0 ? 4 * (nt + 1) : 0;
+    break;
+  case SPMV_B200_EXPORT_TILE_SPLIT:
+    src = p->tile_split;
+    bytes = p->m > 0 ? (nt + 1) : 0;
+    break;
+  case SPMV_B200_EXPORT_TILE_KIND:
+    src = p->tile_kind;
+    bytes = nt;
+    break;
+  case SPMV_B200_EXPORT_TILE_PART:
+    src = p->tile_part;
+    bytes = p->m > 0 ? 4 * (nt + 1) : 0;
+    break;
+  case SPMV_B200_EXPORT_TILE_MAXLEN:
+    src = p->tile_maxlen;
+    bytes = 4 * nt;
+    break;
+  case SPMV_B200_EXPORT_SPLIT_ROWS:
+    src = p->split_rows;
+    bytes = 12 * (int64_t)p->nsplit;
+    break;
+  case SPMV_B200_EXPORT_ROW_BIN:
+    bytes = p->m;
+    break;
+  default:
+    set_error("plan_export: unknown array id");
+    return SPMV_B200_ERR_ARG;
+  }
+  if (bytes_out)
+    *bytes_out = bytes;
+  if (!h_dst || bytes == 0)
+    return SPMV_B200_OK;
+  if (capacity_bytes < bytes) {
+    set_error("plan_export: destination too small");
+    return SPMV_B200_ERR_ARG;
+  }
+  if (what == SPMV_B200_EXPORT_ROW_BIN) {
+    unsigned char *d_tmp = nullptr;
+    B200_CUDA(cudaMalloc(&d_tmp, (size_t)bytes));
+    int rc = analysis_row_bins(p, d_tmp, nullptr);
+    if (rc == SPMV_B200_OK && cudaMemcpy(h_dst, d_tmp, (size_t)bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = cuda_fail(cudaGetLastError(), "cudaMemcpy(row bins)", __FILE__, __LINE__);
+    cudaFree(d_tmp);
+    return rc;
+  }
+  B200_CUDA(cudaMemcpy(h_dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+  return SPMV_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stateless entry points: a small plan cache keyed on the device pointers and the shape
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct CacheKey {
+  const void *rowptr, *col, *val;
+  int m, n, device;
+  bool operator==(const CacheKey &o) const {
+    return rowptr == o.rowptr && col == o.col && val == o.val && m == o.m && n == o.n && device == o.device;
+  }
+};
+struct CacheEntry {
+  CacheKey key;
+  spmv_b200_plan *plan;
+};
+std::mutex g_cache_mutex;
+std::list<CacheEntry> g_cache; // most recently used first
+constexpr size_t kCacheCapacity = 16;
+
+int cached_plan(int m, int n, long long nnz, const int *rowptr, const int *col, const double *val,
+                spmv_b200_plan **out) {
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  const CacheKey key{rowptr, col, val, m, n, dev};
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  for (auto it = g_cache.begin(); it != g_cache.end(); ++it) {
+    if (it->key == key && (nnz < 0 || it->plan->nnz == nnz)) {
+      g_cache.splice(g_cache.begin(), g_cache, it);
+      *out = g_cache.front().plan;
+      return SPMV_B200_OK;
+    }
+  }
+  spmv_b200_plan *p = nullptr;
+  const int rc = spmv_b200_plan_create(&p, m, n, nnz, rowptr, col, val, nullptr, nullptr);
+  if (rc != SPMV_B200_OK)
+    return rc;
+  g_cache.push_front(CacheEntry{key, p});
+  while (g_cache.size() > kCacheCapacity) {
+    // plans may still have kernels in flight on the null stream; cudaFree synchronises implicitly
+    spmv_b200_plan_destroy(g_cache.back().plan);
+    g_cache.pop_back();
+  }
+  *out = p;
+  return SPMV_B200_OK;
+}
+} // namespace
+
+int spmv_b200_csr_spmv(int32_t trans, double alpha, double beta, int32_t m, int32_t n, int32_t nnz,
+                       const int32_t *d_rowptr, const int32_t *d_colidx, const double *d_val, const double *d_x,
+                       double *d_y) {
+  if (trans != 0) { // src/acc/api/types.h:8 — only operation_none is supported by the reference as well
+    set_error("csr_spmv: only operation_none (trans = 0) is supported");
+    return SPMV_B200_ERR_UNSUPPORTED;
+  }
+  spmv_b200_plan *p = nullptr;
+  const int rc = cached_plan(m, n, nnz, d_rowptr, d_colidx, d_val, &p);
+  if (rc != SPMV_B200_OK)
+    return rc;
+  return spmv_b200_execute(p, alpha, beta, d_x, d_y, nullptr);
+}
+
+int spmv_b200_sparse_spmv(int32_t trans, double alpha, double beta, int32_t m, int32_t n, const int32_t *d_rowptr,
+                          const int32_t *d_colidx, const double *d_val, const double *d_x, double *d_y) {
+  // src/acc/api/spmv_imp.cpp:14 reads rowptr[hm] on the host; here nnz comes from the device inside the analysis
+  if (trans != 0) {
+    set_error("sparse_spmv: only operation_none (trans = 0) is supported");
+    return SPMV_B200_ERR_UNSUPPORTED;
+  }
+  spmv_b200_plan *p = nullptr;
+  const int rc = cached_plan(m, n, -1, d_rowptr, d_colidx, d_val, &p);
+  if (rc != SPMV_B200_OK)
+    return rc;
+  return spmv_b200_execute(p, alpha, beta, d_x, d_y, nullptr);
+}
+
+int spmv_b200_cache_invalidate(void) {
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  int rc = SPMV_B200_OK;
+  for (auto &e : g_cache)
+    if (spmv_b200_plan_destroy(e.plan) != SPMV_B200_OK)
+      rc = SPMV_B200_ERR_CUDA;
+  g_cache.clear();
+  return rc;
+}
+
+int spmv_b200_cache_size(void) {
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  return (int)g_cache.size();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-buffer path (the CLI's pattern: matrix uploaded once, y0 copied in and y copied out around every call,
+// cli/utils.hpp:94-116 and cli/main.cpp:99-118)
+// ---------------------------------------------------------------------------------------------------------------
+struct spmv_b200_hostmat {
+  int m = 0, n = 0;
+  long long nnz = 0;
+  int *d_rowptr = nullptr;
+  int *d_col = nullptr;
+  double *d_val = nullptr;
+  double *d_x = nullptr;
+  double *d_y = nullptr;
+  spmv_b200_plan *plan = nullptr;
+  cudaStream_t stream = nullptr;
+};
+
+int spmv_b200_hostmat_destroy(spmv_b200_hostmat *hm) {
+  if (!hm)
+    return SPMV_B200_OK;
+  if (hm->stream)
+    cudaStreamSynchronize(hm->stream);
+  spmv_b200_plan_destroy(hm->plan);
+  cudaFree(hm->d_rowptr);
+  cudaFree(hm->d_col);
+  cudaFree(hm->d_val);
+  cudaFree(hm->d_x);
+  cudaFree(hm->d_y);
+  if (hm->stream)
+    cudaStreamDestroy(hm->stream);
+  delete hm;
+  return SPMV_B200_OK;
+}
+
+static int hostmat_build(spmv_b200_hostmat *hm, const int32_t *h_rowptr, const int32_t *h_colidx, const double *h_val,
+                         const spmv_b200_options *opt) {
+  const size_t m = (size_t)hm->m, n = (size_t)hm->n, nnz = (size_t)hm->nnz;
+  B200_CUDA(cudaStreamCreateWithFlags(&hm->stream, cudaStreamNonBlocking));
+  B200_CUDA(cudaMalloc(&hm->d_rowptr, sizeof(int) * (m + 1)));
+  B200_CUDA(cudaMalloc(&hm->d_col, sizeof(int) * (nnz ? nnz : 1)));
+  B200_CUDA(cudaMalloc(&hm->d_val, sizeof(double) * (nnz ? nnz : 1)));
+  B200_CUDA(cudaMalloc(&hm->d_x, sizeof(double) * (n ? n : 1)));
+  B200_CUDA(cudaMalloc(&hm->d_y, sizeof(double) * (m ? m : 1)));
+  B200_CUDA(cudaMemcpyAsync(hm->d_rowptr, h_rowptr, sizeof(int) * (m + 1), cudaMemcpyHostToDevice, hm->stream));
+  if (nnz) {
+    B200_CUDA(cudaMemcpyAsync(hm->d_col, h_colidx, sizeof(int) * nnz, cudaMemcpyHostToDevice, hm->stream));
+    B200_CUDA(cudaMemcpyAsync(hm->d_val, h_val, sizeof(double) * nnz, cudaMemcpyHostToDevice, hm->stream));
+  }
+  return spmv_b200_plan_create(&hm->plan, hm->m, hm->n, hm->nnz, hm->d_rowptr, hm->d_col, hm->d_val, opt, hm->stream);
+}
+
+int spmv_b200_hostmat_create(spmv_b200_hostmat **out, int32_t m, int32_t n, int64_t nnz, const int32_t *h_rowptr,
+                             const int32_t *h_colidx, const double *h_val, const spmv_b200_options *opt) {
+  if (!out || m < 0 || n < 0 || nnz < 0 || nnz > 0x7fffffffLL || !h_rowptr || (nnz > 0 && (!h_colidx || !h_val))) {
+    set_error("hostmat_create: invalid argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  *out = nullptr;
+  spmv_b200_hostmat *hm = new (std::nothrow) spmv_b200_hostmat();
+  if (!hm) {
+    set_error("hostmat_create: out of host memory");
+    return SPMV_B200_ERR_ARG;
+  }
+  hm->m = m;
+  hm->n = n;
+  hm->nnz = nnz;
+  const int rc = hostmat_build(hm, h_rowptr, h_colidx, h_val, opt);
+  if (rc != SPMV_B200_OK) {
+    const std::string keep = g_last_error;
+    spmv_b200_hostmat_destroy(hm);
+    g_last_error = keep;
+    return rc;
+  }
+  *out = hm;
+  return SPMV_B200_OK;
+}
+
+int spmv_b200_hostmat_spmv(spmv_b200_hostmat *hm, double alpha, double beta, const double *h_x, double *h_y) {
+  if (!hm || (hm->n > 0 && !h_x) || (hm->m > 0 && !h_y)) {
+    set_error("hostmat_spmv: invalid argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  if (hm->n > 0)
+    B200_CUDA(cudaMemcpyAsync(hm->d_x, h_x, sizeof(double) * (size_t)hm->n, cudaMemcpyHostToDevice, hm->stream));
+  if (hm->m > 0)
+    B200_CUDA(cudaMemcpyAsync(hm->d_y, h_y, sizeof(double) * (size_t)hm->m, cudaMemcpyHostToDevice, hm->stream));
+  const int rc = spmv_b200_execute(hm->plan, alpha, beta, hm->d_x, hm->d_y, hm->stream);
+  if (rc != SPMV_B200_OK)
+    return rc;
+  if (hm->m > 0)
+    B200_CUDA(cudaMemcpyAsync(h_y, hm->d_y, sizeof(double) * (size_t)hm->m, cudaMemcpyDeviceToHost, hm->stream));
+  B200_CUDA(cudaStreamSynchronize(hm->stream));
+  return SPMV_B200_OK;
+}
+
+int spmv_b200_host_spmv(double alpha, double beta, int32_t m, int32_t n, int64_t nnz, const int32_t *h_rowptr,
+                        const int32_t *h_colidx, const double *h_val, const double *h_x, double *h_y) {
+  spmv_b200_hostmat *hm = nullptr;
+  int rc = spmv_b200_hostmat_create(&hm, m, n, nnz, h_rowptr, h_colidx, h_val, nullptr);
+  if (rc != SPMV_B200_OK)
+    return rc;
+  rc = spmv_b200_hostmat_spmv(hm, alpha, beta, h_x, h_y);
+  const std::string keep = g_last_error;
+  spmv_b200_hostmat_destroy(hm);
+  g_last_error = keep;
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sharding helpers
+// ---------------------------------------------------------------------------------------------------------------
+int spmv_b200_shard_bounds(int32_t m, int64_t nnz, const int32_t *d_rowptr, int32_t nshards, int32_t *h_bounds,
+                           void *stream) {
+  if (!h_bounds || (m > 0 && !d_rowptr)) {
+    set_error("shard_bounds: NULL argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  return shard_bounds_run(m, nnz, d_rowptr, nshards, h_bounds, static_cast<cudaStream_t>(stream));
+}
+
+int spmv_b200_col_block_bitmap(int64_t nnz, const int32_t *d_colidx, int32_t n, int32_t block_shift,
+                               uint8_t *h_bitmap, void *stream) {
+  if (!h_bitmap || (nnz > 0 && !d_colidx)) {
+    set_error("col_block_bitmap: NULL argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  return col_block_bitmap_run(nnz, d_colidx, n, block_shift, h_bitmap, static_cast<cudaStream_t>(stream));
+}
+
+} // extern "C"

@@ -1,0 +1,109 @@
+// Internal declarations shared by the translation units of libspmv_b200.so.
+// Nothing here is part of the ABI; the ABI is include/spmv_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "spmv_b200.h"
+
+namespace b200 {
+
+constexpr int kThreads = 256;     // threads per CTA of every streaming kernel
+constexpr int kRowChunk = 1024;   // row pointers staged in shared memory per pass (rows per pass = kRowChunk)
+constexpr int kSerialMax = 16;    // MIXED kernel: rows up to this length are reduced by one thread
+constexpr int kDefaultTile = 2048;
+constexpr int kDefaultShort = 8;
+constexpr int kDefaultMedium = 128;
+constexpr int kDefaultVecDiv = 8;
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define B200_CUDA(call)                                                                                               \
+  do {                                                                                                                 \
+    cudaError_t _e = (call);                                                                                           \
+    if (_e != cudaSuccess)                                                                                             \
+      return ::b200::cuda_fail(_e, #call, __FILE__, __LINE__);                                                         \
+  } while (0)
+
+// Arguments of the streaming kernels (passed by value).
+struct SpmvArgs {
+  const int *__restrict__ rowptr;
+  const int *__restrict__ col;
+  const double *__restrict__ val;
+  const double *__restrict__ x;
+  double *__restrict__ y;
+  double alpha, beta;
+  const int *__restrict__ tile_row;             // [ntiles+1]
+  const int *__restrict__ tile_elem;            // [ntiles+1]
+  const unsigned char *__restrict__ tile_split; // [ntiles+1]
+  const int *__restrict__ list;                 // tiles of this kind, or nullptr when every tile has this kind
+  double *__restrict__ partials;                // [2*ntiles]: head fragment, tail fragment of each tile
+  long long nnz; // absolute index one past the last element of the matrix (bounds the TMA size)
+  int cap;      // element capacity of the shared-memory tile
+  int vec_div;  // MEDIUM: lanes per row = pow2ceil(avg / vec_div)
+  int read_y;   // 0: beta == 0 and SPMV_B200_FLAG_BETA0_SKIP_Y
+};
+
+struct FixupArgs {
+  const int *__restrict__ split_row; // [nsplit]
+  const int *__restrict__ split_t0;  // [nsplit] tile that owns the row (tail fragment)
+  const int *__restrict__ split_t1;  // [nsplit] last tile holding a fragment of the row
+  const double *__restrict__ partials;
+  double *__restrict__ y;
+  double alpha, beta;
+  int nsplit;
+  int read_y;
+};
+
+} // namespace b200
+
+struct spmv_b200_plan {
+  int m = 0, n = 0;
+  long long nnz = 0;      // rowptr[m] - rowptr[0]
+  long long elem_end = 0; // rowptr[m]
+  const int *rowptr = nullptr;
+  const int *col = nullptr;
+  const double *val = nullptr;
+  int T = 0, short_max = 0, medium_max = 0, vec_div = 0;
+  unsigned flags = 0;
+  int device = 0;
+  bool uses_tma = false;
+  int ntiles = 0;
+  int cap = 0;
+  size_t smem_bytes = 0;
+  // device arrays owned by the plan
+  int *tile_row = nullptr;
+  int *tile_elem = nullptr;
+  unsigned char *tile_split = nullptr;
+  int *tile_part = nullptr;
+  int *tile_maxlen = nullptr;
+  unsigned char *tile_kind = nullptr;
+  int *list[3] = {nullptr, nullptr, nullptr};
+  int count[3] = {0, 0, 0};
+  int nsplit = 0;
+  int *split_rows = nullptr; // [3*nsplit]: row, t0, t1 (struct of arrays: rows | t0 | t1)
+  double *partials = nullptr;
+  long long bin_rows[4] = {0, 0, 0, 0};
+  long long bin_nnz[4] = {0, 0, 0, 0};
+  size_t workspace_bytes = 0;
+};
+
+namespace b200 {
+
+// analysis.cu
+int analysis_run(spmv_b200_plan *p, cudaStream_t stream);
+int analysis_row_bins(const spmv_b200_plan *p, unsigned char *d_out, cudaStream_t stream);
+int shard_bounds_run(int m, long long nnz, const int *d_rowptr, int nshards, int *h_bounds, cudaStream_t stream);
+int col_block_bitmap_run(long long nnz, const int *d_col, int n, int block_shift, unsigned char *h_bitmap,
+                         cudaStream_t stream);
+
+// kernels.cu
+int kernels_configure(spmv_b200_plan *p);
+int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y,
+                   cudaStream_t stream);
+
+} // namespace b200
