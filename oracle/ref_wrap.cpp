@@ -21,7 +21,11 @@
 
 #include "hip-csr-adaptive-plus/csr_adaptive_plus_analyze.h"
 
+static std::string g_ref_error;
+
 extern "C" {
+
+const char *ref_last_error() { return g_ref_error.c_str(); }
 
 void ref_host_spmv_axpby(double alpha, double beta, const double *value, const int *rowptr, const int *colindex,
                          int m, int n, int nnz, const double *x, double *y) {
@@ -104,7 +108,8 @@ ref_csr_handle *ref_read_csr_text(const char *path) {
     int *c, *r;
     rd.as_raw_ptr(v, c, r, x);
     return from_raw(rd.rows(), rd.cols(), rd.nnz(), v, c, r, x);
-  } catch (...) {
+  } catch (const std::exception &e) {
+    g_ref_error = e.what();
     return nullptr;
   }
 }
@@ -135,7 +140,8 @@ ref_csr_handle *ref_read_mtx(const char *path) {
     delete[] csr.col_index;
     delete[] csr.row_ptr;
     return h;
-  } catch (...) {
+  } catch (const std::exception &e) {
+    g_ref_error = e.what();
     return nullptr;
   }
 }

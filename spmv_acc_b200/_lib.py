@@ -90,8 +90,8 @@ def gen() -> C.CDLL:
         G = _load("libspmv_b200_gen.so")
         vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
         G.spmv_b200_gen_vector.argtypes = [i64, u64, vp, vp]
-        G.spmv_b200_gen_stencil2d_counts.argtypes = [i32, i64, i64, vp, vp]
-        G.spmv_b200_gen_stencil2d_fill.argtypes = [i32, i64, i64, vp, vp, vp, vp]
+        G.spmv_b200_gen_stencil2d_counts.argtypes = [i32, i32, i64, i64, vp, vp]
+        G.spmv_b200_gen_stencil2d_fill.argtypes = [i32, i32, i64, i64, vp, vp, vp, vp]
         G.spmv_b200_gen_stencil3d_counts.argtypes = [i32, i64, i64, vp, vp]
         G.spmv_b200_gen_stencil3d_fill.argtypes = [i32, i64, i64, vp, vp, vp, vp]
         G.spmv_b200_gen_uniform_fill.argtypes = [i64, i64, i32, i32, u64, vp, vp, vp]

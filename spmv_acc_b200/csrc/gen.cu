@@ -33,16 +33,16 @@ __global__ void k_vector(long long n, unsigned long long seed, double *__restric
     out[i] = sym_unit(hash3(seed, (unsigned long long)i, 0x5eedull));
 }
 
-// ---- 2D 5-point Laplacian on an N x N grid, Dirichlet truncation, row = i*N + j, columns ascending ----
-__global__ void k_s2d_counts(int N, long long r_lo, long long r_hi, int *__restrict__ counts) {
+// ---- 2D 5-point Laplacian on an NY x N grid (NY grid rows of N points), Dirichlet truncation, row = i*N + j ----
+__global__ void k_s2d_counts(int N, int NY, long long r_lo, long long r_hi, int *__restrict__ counts) {
   for (long long r = r_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; r < r_hi;
        r += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(r / N), j = (int)(r % N);
-    counts[r - r_lo] = 1 + (i > 0) + (i < N - 1) + (j > 0) + (j < N - 1);
+    counts[r - r_lo] = 1 + (i > 0) + (i < NY - 1) + (j > 0) + (j < N - 1);
   }
 }
 
-__global__ void k_s2d_fill(int N, long long r_lo, long long r_hi, const int *__restrict__ rowptr,
+__global__ void k_s2d_fill(int N, int NY, long long r_lo, long long r_hi, const int *__restrict__ rowptr,
                            int *__restrict__ col, double *__restrict__ val) {
   for (long long r = r_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; r < r_hi;
        r += (long long)gridDim.x * blockDim.x) {
@@ -52,7 +52,7 @@ __global__ void k_s2d_fill(int N, long long r_lo, long long r_hi, const int *__r
     if (j > 0) { col[p] = (int)(r - 1); val[p++] = -1.0; }
     col[p] = (int)r; val[p++] = 4.0;
     if (j < N - 1) { col[p] = (int)(r + 1); val[p++] = -1.0; }
-    if (i < N - 1) { col[p] = (int)(r + N); val[p++] = -1.0; }
+    if (i < NY - 1) { col[p] = (int)(r + N); val[p++] = -1.0; }
   }
 }
 
@@ -168,16 +168,16 @@ GEN_API int spmv_b200_gen_vector(long long n, unsigned long long seed, double *d
   return done(s);
 }
 
-GEN_API int spmv_b200_gen_stencil2d_counts(int N, long long r_lo, long long r_hi, int *d_counts, void *stream) {
+GEN_API int spmv_b200_gen_stencil2d_counts(int N, int NY, long long r_lo, long long r_hi, int *d_counts, void *stream) {
   auto s = static_cast<cudaStream_t>(stream);
-  if (r_hi > r_lo) k_s2d_counts<<<grid_for(r_hi - r_lo), 256, 0, s>>>(N, r_lo, r_hi, d_counts);
+  if (r_hi > r_lo) k_s2d_counts<<<grid_for(r_hi - r_lo), 256, 0, s>>>(N, NY, r_lo, r_hi, d_counts);
   return done(s);
 }
 
-GEN_API int spmv_b200_gen_stencil2d_fill(int N, long long r_lo, long long r_hi, const int *d_rowptr, int *d_col,
+GEN_API int spmv_b200_gen_stencil2d_fill(int N, int NY, long long r_lo, long long r_hi, const int *d_rowptr, int *d_col,
                                          double *d_val, void *stream) {
   auto s = static_cast<cudaStream_t>(stream);
-  if (r_hi > r_lo) k_s2d_fill<<<grid_for(r_hi - r_lo), 256, 0, s>>>(N, r_lo, r_hi, d_rowptr, d_col, d_val);
+  if (r_hi > r_lo) k_s2d_fill<<<grid_for(r_hi - r_lo), 256, 0, s>>>(N, NY, r_lo, r_hi, d_rowptr, d_col, d_val);
   return done(s);
 }
 

@@ -75,12 +75,14 @@ def _rowptr_from_counts(counts: np.ndarray) -> np.ndarray:
 # ----------------------------------------------------------------------------------------------------------------
 # numpy generators
 # ----------------------------------------------------------------------------------------------------------------
-def stencil2d_numpy(N: int, r_lo: int = 0, r_hi: Optional[int] = None) -> Csr:
-    r_hi = N * N if r_hi is None else r_hi
+def stencil2d_numpy(N: int, r_lo: int = 0, r_hi: Optional[int] = None, NY: Optional[int] = None) -> Csr:
+    """5-point Laplacian on a grid of NY rows x N points (NY defaults to N)."""
+    NY = N if NY is None else NY
+    r_hi = NY * N if r_hi is None else r_hi
     r = np.arange(r_lo, r_hi, dtype=np.int64)
     i, j = r // N, r % N
     offs = [(-N, i > 0, -1.0), (-1, j > 0, -1.0), (0, np.ones_like(i, bool), 4.0), (1, j < N - 1, -1.0),
-            (N, i < N - 1, -1.0)]
+            (N, i < NY - 1, -1.0)]
     counts = sum(m.astype(np.int64) for _, m, _ in offs)
     rowptr = _rowptr_from_counts(counts)
     col = np.zeros(int(rowptr[-1]), np.int32)
@@ -91,7 +93,7 @@ def stencil2d_numpy(N: int, r_lo: int = 0, r_hi: Optional[int] = None) -> Csr:
         col[idx] = (r[mask] + off).astype(np.int32)
         val[idx] = v
         pos[mask] += 1
-    return Csr(r_hi - r_lo, N * N, rowptr, col, val)
+    return Csr(r_hi - r_lo, NY * N, rowptr, col, val)
 
 
 def stencil3d_numpy(N: int, r_lo: int = 0, r_hi: Optional[int] = None) -> Csr:
@@ -230,29 +232,40 @@ def _rowptr_from_counts_device(counts):
     return rp.to(torch.int32)
 
 
-def _stencil_device(kind: str, N: int, total_rows: int, r_lo: int, r_hi: Optional[int]) -> Csr:
+def _stencil_device(kind: str, dims: tuple, total_rows: int, r_lo: int, r_hi: Optional[int]) -> Csr:
     import torch
     r_hi = total_rows if r_hi is None else r_hi
     rows = r_hi - r_lo
     G = _lib.gen()
     counts = torch.empty(rows, dtype=torch.int32, device="cuda")
-    _ck(getattr(G, f"spmv_b200_gen_{kind}_counts")(N, r_lo, r_hi, counts.data_ptr(), _stream()), "gen counts")
+    _ck(getattr(G, f"spmv_b200_gen_{kind}_counts")(*dims, r_lo, r_hi, counts.data_ptr(), _stream()), "gen counts")
     rowptr = _rowptr_from_counts_device(counts)
     del counts
     nnz = int(rowptr[-1])
     col = torch.empty(nnz, dtype=torch.int32, device="cuda")
     val = torch.empty(nnz, dtype=torch.float64, device="cuda")
-    _ck(getattr(G, f"spmv_b200_gen_{kind}_fill")(N, r_lo, r_hi, rowptr.data_ptr(), col.data_ptr(), val.data_ptr(),
-                                                  _stream()), "gen fill")
+    _ck(getattr(G, f"spmv_b200_gen_{kind}_fill")(*dims, r_lo, r_hi, rowptr.data_ptr(), col.data_ptr(),
+                                                  val.data_ptr(), _stream()), "gen fill")
     return Csr(rows, total_rows, rowptr, col, val)
 
 
-def stencil2d_device(N: int, r_lo: int = 0, r_hi: Optional[int] = None) -> Csr:
-    return _stencil_device("stencil2d", N, N * N, r_lo, r_hi)
+def stencil2d_device(N: int, r_lo: int = 0, r_hi: Optional[int] = None, NY: Optional[int] = None) -> Csr:
+    NY = N if NY is None else NY
+    return _stencil_device("stencil2d", (N, NY), NY * N, r_lo, r_hi)
 
 
 def stencil3d_device(N: int, r_lo: int = 0, r_hi: Optional[int] = None) -> Csr:
-    return _stencil_device("stencil3d", N, N ** 3, r_lo, r_hi)
+    return _stencil_device("stencil3d", (N,), N ** 3, r_lo, r_hi)
+
+
+def stencil_row_counts_device(kind: str, N: int, NY: Optional[int] = None):
+    """int32 nnz-per-row of the whole stencil matrix (used to place nnz-balanced shard boundaries)."""
+    import torch
+    dims = (N, N if NY is None else NY) if kind == "stencil2d" else (N,)
+    total = dims[0] * dims[1] if kind == "stencil2d" else N ** 3
+    counts = torch.empty(total, dtype=torch.int32, device="cuda")
+    _ck(getattr(_lib.gen(), f"spmv_b200_gen_{kind}_counts")(*dims, 0, total, counts.data_ptr(), _stream()), "counts")
+    return counts
 
 
 def uniform_device(m: int, n: int, k: int, seed: int = 1, r_lo: int = 0, r_hi: Optional[int] = None) -> Csr:

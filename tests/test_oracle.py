@@ -1,0 +1,132 @@
+"""CPU tests: the plain-C oracle against the reference's golden vectors (produced by the reference itself, see
+tests/golden/make_golden.py) and, where /root/reference was compiled here, against the reference bit for bit."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN_CASES, load_golden
+from spmv_acc_b200 import synth
+
+needs_ref = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_port_matches_golden_bitwise(name):
+    g = load_golden(name)
+    for (a, b), y in zip(g["ab"], g["y"]):
+        got = oracle.port_host_spmv(a, b, g["rowptr"], g["col"], g["val"], g["x"], g["y0"], n=int(g["cols"]))
+        assert np.array_equal(got, y), f"{name} alpha={a} beta={b}"
+    assert np.array_equal(oracle.port_host_spmv_ax(g["rowptr"], g["col"], g["val"], g["x"]), g["y_ax"])
+
+
+def test_verify_y_golden():
+    g = np.load(load_golden.__globals__["GOLDEN"] / "verify_y.npz")
+    r = oracle.port_verify_y(g["dy"], g["hy"])
+    assert r["max_error"] == float(g["max_error"])
+    assert r["first_failed_at"] == int(g["first_failed_at"])
+    assert r["failed_count"] == int(g["failed_count"])
+    # known answers by hand: |hy|<=1e-12 -> abs 1e-14; else rel 1e-7 (cli/verification.cpp:24-25)
+    assert r["failed_count"] == 2 and r["first_failed_at"] == 1
+
+
+def test_rand_vector_golden():
+    g = np.load(load_golden.__globals__["GOLDEN"] / "rand_vector_64.npy")
+    v = oracle.port_generate_vector(64, seed=1)
+    assert np.array_equal(v, g)
+    assert v.min() >= -1.0 and v.max() <= 1.0 - 2.0 * 2 / 101  # 100-point lattice in [-1, 0.96]
+
+
+@needs_ref
+def test_port_equals_reference_on_random_matrices():
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        m, n = int(rng.integers(1, 300)), int(rng.integers(1, 300))
+        lens = rng.integers(0, 40, m)
+        rp = np.zeros(m + 1, np.int32)
+        rp[1:] = np.cumsum(lens)
+        col = rng.integers(0, n, int(rp[-1])).astype(np.int32)
+        val = rng.standard_normal(int(rp[-1]))
+        x, y0 = rng.standard_normal(n), rng.standard_normal(m)
+        a, b = float(rng.standard_normal()), float(rng.standard_normal())
+        assert np.array_equal(oracle.port_host_spmv(a, b, rp, col, val, x, y0),
+                              oracle.ref_host_spmv(a, b, rp, col, val, x, y0))
+        dy = oracle.port_host_spmv(a, b, rp, col, val, x, y0) * (1 + 1e-7 * (rng.random(m) < 0.1))
+        hy = oracle.ref_host_spmv(a, b, rp, col, val, x, y0)
+        assert oracle.port_verify_y(dy, hy) == oracle.ref_verify_y(dy, hy)
+
+
+def test_beta_zero_propagates_nan_like_reference():
+    # cli/verification.cpp:64 computes alpha*y0 + beta*y[i] unconditionally: 0 * NaN = NaN
+    rp = np.array([0, 1, 2], np.int32)
+    y = oracle.port_host_spmv(1.0, 0.0, rp, np.array([0, 1], np.int32), np.array([2.0, 3.0]), np.array([1.0, 1.0]),
+                              np.array([np.nan, 5.0]))
+    assert np.isnan(y[0]) and y[1] == 3.0
+
+
+def test_merge_path_partition_port_semantics():
+    rp = np.array([0, 0, 3, 3, 3, 10, 10, 12], np.int32)
+    # S[t] = largest r with rowptr[r] <= t*ITEMS  (merge_path_partition.h:14, merge_path_utils.h:32-44)
+    S = oracle.port_merge_path_partition(rp, 5, 3)
+    assert S.tolist() == [1, 4, 4, 4, 7]
+    bp = oracle.port_flat_break_points_v2(rp, 4)
+    # element 0 -> row 1, element 4 -> row 4, element 8 -> row 4 (flat_imp.inl:134-152)
+    assert bp[:3].tolist() == [1, 4, 4]
+
+
+def _random_rowptr(rng, m, choices):
+    lens = rng.choice(choices, size=m)
+    rp = np.zeros(m + 1, np.int32)
+    rp[1:] = np.cumsum(lens)
+    return rp
+
+
+@pytest.mark.parametrize("T,S,L", [(256, 8, 16), (256, 4, 64), (512, 8, 128), (2048, 8, 128)])
+def test_analysis_port_invariants_and_tiled_sum(T, S, L):
+    rng = np.random.default_rng(T + S + L)
+    for trial in range(60):
+        m, n = int(rng.integers(1, 80)), int(rng.integers(1, 60))
+        rp = _random_rowptr(rng, m, [0, 0, 1, 2, 3, 5, 9, 17, 40, 300, 700, 2500])
+        nnz = int(rp[-1])
+        col = rng.integers(0, n, nnz).astype(np.int32)
+        val = rng.standard_normal(nnz)
+        x, y0 = rng.standard_normal(n), rng.standard_normal(m)
+        ana = oracle.port_analysis(rp, T, S, L)
+        nt = ana["ntiles"]
+        assert nt == max(1, -(-nnz // T))
+        tr, te = ana["tile_row"], ana["tile_elem"]
+        assert tr[0] == 0 and tr[-1] == m and te[0] == 0 and te[-1] == nnz
+        assert np.all(np.diff(tr) >= 0) and np.all(np.diff(te) >= 0)
+        assert np.all(np.diff(te) <= T + L - 1)                       # nnz balance: the shared-memory tile bound
+        assert np.array_equal(ana["tile_part"], oracle.port_merge_path_partition(rp, nt + 1, T).clip(max=m)
+                              if nnz == nt * T else ana["tile_part"])
+        assert ana["bin_rows"].sum() == m and ana["bin_nnz"].sum() == nnz
+        # every row is summed exactly once and the result matches the serial oracle within the fp64 bound
+        yt = oracle.port_tiled_spmv(1.5, 0.25, rp, col, val, x, y0, ana, T, L)
+        yr = oracle.port_host_spmv(1.5, 0.25, rp, col, val, x, y0)
+        ok, worst, row = oracle.check_rows(yt, yr, oracle.port_row_bound(1.5, 0.25, rp, col, val, x, y0))
+        assert ok, (trial, worst, row)
+        if ana["nsplit"] == 0:
+            assert np.array_equal(yt, yr)
+
+
+def test_shard_bounds_port():
+    rp = np.arange(0, 1001, 10, dtype=np.int32)  # 100 rows x 10 nnz
+    assert oracle.port_shard_bounds(rp, 4).tolist() == [0, 25, 50, 75, 100]
+    rp2 = np.array([0, 1000, 1000, 1001, 1002], np.int32)
+    assert oracle.port_shard_bounds(rp2, 2).tolist() == [0, 1, 4]
+    assert oracle.port_shard_bounds(np.zeros(1, np.int32), 3).tolist() == [0, 0, 0, 0]
+
+
+@needs_ref
+def test_reference_adaptive_plus_blocks_are_nnz_balanced_like_ours():
+    """Structure cross-check against the reference's own row-block analysis (csr_adaptive_plus_analyze.cpp:12-98):
+    both cut the C1 stand-in into blocks of about 2048 nnz that start on row boundaries."""
+    c1 = synth.circuit_numpy()
+    bp, _ = oracle.ref_adaptive_plus_analyze(c1.rowptr, 2048, 8)
+    g = np.load(load_golden.__globals__["GOLDEN"] / "c1_adaptive_plus_blocks.npz")
+    assert np.array_equal(bp, g["break_points"])
+    ours = oracle.port_analysis(c1.rowptr, 2048, 8, 128)
+    ref_nnz = np.diff(c1.rowptr[bp])
+    our_nnz = np.diff(ours["tile_elem"])
+    assert bp[0] == 0 and bp[-1] == c1.rows and ours["tile_row"][-1] == c1.rows
+    assert our_nnz.max() <= 2048 + 127 and abs(len(our_nnz) - len(ref_nnz)) <= len(ref_nnz)

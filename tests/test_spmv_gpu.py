@@ -1,0 +1,275 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle (the reference's own
+host_spmv where it was compiled here, else its plain-C restatement) on identical inputs.
+
+Bar: per row |y - y_ref| <= 1e-12 * (|beta*y0_i| + |alpha| * sum_j |a_ij * x_j|)  (north star), plus the reference's
+own verify_y (rel 1e-7, cli/verification.cpp:15-38), plus bitwise run-to-run reproducibility."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN_CASES, load_golden
+from gpu_helpers import assert_parity, desc_of, gpu_spmv
+from spmv_acc_b200 import (FLAG_BETA0_SKIP_Y, FLAG_NO_TMA, CsrDesc, HostMatrix, SpmvB200Error, SpmvPlan,
+                           cache_invalidate, cache_size, host_spmv, make_options, sparse_csr_spmv, sparse_spmv, synth)
+
+pytestmark = pytest.mark.gpu
+
+AB = [(1.0, 1.0), (0.75, -0.5), (1.0, 0.0), (0.0, 2.0), (-1.25, 1e-3)]
+OPTS = {
+    "default": None,
+    "no_tma": make_options(flags=FLAG_NO_TMA),
+    "small_tiles": make_options(256, 4, 16, 2),
+    "big_tiles": make_options(8192, 16, 256, 16),
+}
+
+
+def _golden_csr(g):
+    return synth.Csr(int(g["rows"]), int(g["cols"]), g["rowptr"], g["col"], g["val"])
+
+
+@pytest.mark.parametrize("opt", list(OPTS))
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_vectors(name, opt):
+    """Committed fixtures: inputs and expected y produced by the reference's host_spmv (tests/golden/make_golden.py)."""
+    g = load_golden(name)
+    h = _golden_csr(g)
+    for (a, b), y_ref in zip(g["ab"], g["y"]):
+        y, _ = gpu_spmv(h, g["x"], g["y0"], float(a), float(b), OPTS[opt], repeat=2)
+        assert_parity(h, g["x"], g["y0"], float(a), float(b), y, y_ref, what=f"{name}/{opt}/a={a},b={b}")
+
+
+def _ragged(seed, m, n, choices):
+    rng = np.random.default_rng(seed)
+    lens = rng.choice(choices, size=m)
+    rp = np.zeros(m + 1, np.int32)
+    rp[1:] = np.cumsum(lens)
+    nnz = int(rp[-1])
+    return synth.Csr(m, n, rp, rng.integers(0, n, nnz).astype(np.int32), rng.standard_normal(nnz))
+
+
+def _families():
+    yield "stencil2d_200", synth.stencil2d_numpy(200)
+    yield "stencil3d_24", synth.stencil3d_numpy(24)
+    yield "uniform_3000x5000_32", synth.uniform_numpy(3000, 5000, 32, seed=1)
+    yield "rmat_s14", synth.rmat_numpy(14, 16, seed=1)
+    yield "ragged_mixed", _ragged(3, 5000, 3000, [0, 0, 1, 2, 3, 5, 9, 17, 40, 130, 300, 700, 5000])
+    yield "giant_rows", _ragged(4, 40, 4096, [0, 1, 3, 60000, 250000])
+    yield "all_len_1", _ragged(5, 9000, 100, [1])
+    yield "many_empty", _ragged(6, 20000, 50, [0, 0, 0, 0, 0, 0, 0, 2])
+    yield "medium_129", _ragged(7, 2000, 7000, [127, 128, 129, 130])
+
+
+@pytest.mark.parametrize("opt", list(OPTS))
+def test_seeded_families_against_oracle(opt):
+    for name, h in _families():
+        x = synth.vector_numpy(h.cols, 2)
+        y0 = synth.vector_numpy(h.rows, 3)
+        for a, b in AB[:3]:
+            y, info = gpu_spmv(h, x, y0, a, b, OPTS[opt], repeat=2)
+            assert_parity(h, x, y0, a, b, y, what=f"{name}/{opt}/a={a},b={b}")
+
+
+def test_kinds_are_exercised():
+    """Each per-bin kernel and the fix-up pass must actually run somewhere in this suite."""
+    seen = np.zeros(3, dtype=np.int64)
+    splits = 0
+    for name, h in _families():
+        d = synth.to_device(h)
+        p = SpmvPlan(desc_of(d))
+        i = p.info()
+        seen += np.array(list(i.tiles_per_kind))
+        splits += i.nsplit_rows
+        assert i.uses_tma == 1
+        p.destroy()
+    assert np.all(seen > 0) and splits > 0
+
+
+def test_edge_shapes():
+    import torch
+    # m = 0
+    p = SpmvPlan(CsrDesc(0, 5, 0, torch.zeros(1, dtype=torch.int32, device="cuda"),
+                         torch.zeros(1, dtype=torch.int32, device="cuda"),
+                         torch.zeros(1, dtype=torch.float64, device="cuda")))
+    p.execute(1.0, 1.0, torch.zeros(5, dtype=torch.float64, device="cuda"),
+              torch.zeros(1, dtype=torch.float64, device="cuda"))
+    assert p.info().ntiles == 0
+    p.destroy()
+    # nnz = 0, m > 0: y = beta * y
+    h = synth.Csr(300, 4, np.zeros(301, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    y0 = np.arange(300.0)
+    y, _ = gpu_spmv(h, np.ones(4), y0, 3.0, -2.0)
+    assert np.array_equal(y, -2.0 * y0)
+    # exactly one tile boundary inside a row, nnz an exact multiple of the tile size
+    h = _ragged(9, 8, 64, [512])
+    x, y0 = synth.vector_numpy(64, 1), synth.vector_numpy(8, 2)
+    y, info = gpu_spmv(h, x, y0, 1.0, 1.0, make_options(256, 8, 16))
+    assert_parity(h, x, y0, 1.0, 1.0, y, what="exact multiple")
+    assert info.nsplit_rows == 8
+
+
+def test_beta_zero_semantics():
+    """Default follows the oracle (0 * NaN = NaN, cli/verification.cpp:64); the opt-in flag skips the read of y."""
+    h = synth.stencil2d_numpy(20)
+    x = synth.vector_numpy(h.cols, 2)
+    y0 = synth.vector_numpy(h.rows, 3)
+    y0[7] = np.nan
+    y, _ = gpu_spmv(h, x, y0, 1.0, 0.0)
+    y_ref = oracle.best_host_spmv(1.0, 0.0, h.rowptr, h.col, h.val, x, y0)
+    assert np.isnan(y[7]) and np.isnan(y_ref[7])
+    assert np.array_equal(np.isnan(y), np.isnan(y_ref))
+    y2, _ = gpu_spmv(h, x, y0, 1.0, 0.0, make_options(flags=FLAG_BETA0_SKIP_Y))
+    assert not np.isnan(y2).any()
+    y0[7] = 0.0
+    assert_parity(h, x, y0, 1.0, 0.0, y2, what="beta0 skip")
+
+
+def test_rowptr_view_and_misaligned_pointers():
+    """rowptr may be a window of a larger matrix (rowptr[0] != 0) and value/colindex may be unaligned for TMA."""
+    import torch
+    h = _ragged(12, 4000, 2500, [0, 1, 2, 3, 5, 9, 17, 40, 300, 3000])
+    x = synth.vector_numpy(h.cols, 2)
+    d = synth.to_device(h)
+    dx = torch.from_numpy(x).cuda()
+    lo, hi = 1234, 3456
+    y0 = synth.vector_numpy(hi - lo, 3)
+    dy = torch.from_numpy(y0).cuda()
+    view = CsrDesc(hi - lo, h.cols, int(h.rowptr[hi] - h.rowptr[lo]), d.rowptr[lo:hi + 1], d.col, d.val)
+    p = SpmvPlan(view, make_options(256, 8, 16))
+    p.execute(0.5, 2.0, dx, dy)
+    torch.cuda.synchronize()
+    sub = synth.Csr(hi - lo, h.cols, h.rowptr[lo:hi + 1] - h.rowptr[lo], h.col[h.rowptr[lo]:h.rowptr[hi]],
+                    h.val[h.rowptr[lo]:h.rowptr[hi]])
+    assert_parity(sub, x, y0, 0.5, 2.0, dy.cpu().numpy(), what="rowptr view")
+    p.destroy()
+    # misaligned value / colindex pointers -> the plan must fall back to plain loads by itself
+    col_pad = torch.zeros(h.nnz + 1, dtype=torch.int32, device="cuda")
+    val_pad = torch.zeros(h.nnz + 1, dtype=torch.float64, device="cuda")
+    col_pad[1:] = d.col
+    val_pad[1:] = d.val
+    mis = CsrDesc(h.rows, h.cols, h.nnz, d.rowptr, col_pad[1:], val_pad[1:])
+    p = SpmvPlan(mis)
+    assert p.info().uses_tma == 0
+    y0 = synth.vector_numpy(h.rows, 5)
+    dy = torch.from_numpy(y0).cuda()
+    p.execute(1.0, 1.0, dx, dy)
+    torch.cuda.synchronize()
+    assert_parity(h, x, y0, 1.0, 1.0, dy.cpu().numpy(), what="misaligned")
+    p.destroy()
+
+
+def test_reference_shaped_entry_points_and_plan_cache():
+    """sparse_csr_spmv / sparse_spmv keep the reference's argument lists (src/acc/api/spmv.h:20-28)."""
+    import torch
+    cache_invalidate()
+    g = load_golden("c1_circuit")
+    h = _golden_csr(g)
+    d = synth.to_device(h)
+    desc = desc_of(d)
+    dx = torch.from_numpy(g["x"]).cuda()
+    # the CLI's call pattern: alpha = beta = 1, y0 copied in before every call (cli/main.cpp:94-118)
+    for _ in range(3):
+        dy = torch.from_numpy(g["y0"]).cuda()
+        sparse_csr_spmv(0, 1.0, 1.0, desc.as_const(), desc.as_const(), dx, dy)
+    torch.cuda.synchronize()
+    assert cache_size() == 1
+    assert_parity(h, g["x"], g["y0"], 1.0, 1.0, dy.cpu().numpy(), g["y"][0], what="sparse_csr_spmv")
+    dy = torch.from_numpy(g["y0"]).cuda()
+    sparse_spmv(0, 0.75, -0.5, h.rows, h.cols, d.rowptr, d.col, d.val, dx, dy)
+    torch.cuda.synchronize()
+    assert cache_size() == 1
+    assert_parity(h, g["x"], g["y0"], 0.75, -0.5, dy.cpu().numpy(), g["y"][1], what="sparse_spmv")
+    with pytest.raises(SpmvB200Error):
+        sparse_csr_spmv(1, 1.0, 1.0, desc, desc, dx, dy)  # operation_transpose is unsupported, as in the reference
+    with pytest.raises(SpmvB200Error):
+        sparse_csr_spmv(0, 1.0, 1.0, desc, desc, dx.cpu(), dy)  # host memory is refused: there is no CPU fallback
+    cache_invalidate()
+    assert cache_size() == 0
+
+
+def test_host_buffer_path():
+    g = load_golden("c4_rmat_s11")
+    h = _golden_csr(g)
+    hm = HostMatrix(h.rows, h.cols, h.rowptr, h.col, h.val)
+    for (a, b), y_ref in zip(g["ab"], g["y"]):
+        y = g["y0"].copy()
+        hm.spmv(float(a), float(b), g["x"], y)
+        assert_parity(h, g["x"], g["y0"], float(a), float(b), y, y_ref, what="hostmat")
+    hm.destroy()
+    y = g["y0"].copy()
+    host_spmv(1.0, 1.0, h.rows, h.cols, h.rowptr, h.col, h.val, g["x"], y)
+    assert_parity(h, g["x"], g["y0"], 1.0, 1.0, y, g["y"][0], what="host_spmv")
+
+
+def test_bad_options_are_rejected():
+    d = synth.to_device(synth.stencil2d_numpy(8))
+    for bad in (make_options(100), make_options(2048, 8, 4096), make_options(2048, 300, 128), make_options(2048, 8, 126)):
+        with pytest.raises(SpmvB200Error):
+            SpmvPlan(desc_of(d), bad)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json sizes: size-independent properties (the serial oracle would take too long for every test run)
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_size_c2_properties():
+    """C2: 2D 5-point Laplacian on a 4096^2 grid (16.8M rows, 83.9M nnz)."""
+    import torch
+    N = 4096
+    d = synth.stencil2d_device(N)
+    p = SpmvPlan(desc_of(d))
+    ones = torch.ones(d.cols, dtype=torch.float64, device="cuda")
+    y = torch.zeros(d.rows, dtype=torch.float64, device="cuda")
+    p.execute(1.0, 0.0, ones, y)
+    # known answer: A*1 = 4 - (number of neighbours) -> 0 in the interior, 1 on edges, 2 in corners (exact in fp64)
+    yy = y.view(N, N)
+    assert float(yy[1:-1, 1:-1].abs().max()) == 0.0
+    assert float(yy[0, 1:-1].min()) == 1.0 and float(yy[0, 1:-1].max()) == 1.0
+    assert float(yy[0, 0]) == 2.0 and float(yy[-1, -1]) == 2.0
+    assert float(y.sum()) == 4.0 * (N - 2) + 4 * 2.0
+    # linearity + epilogue: A(2u + 3v) == 2Au + 3Av exactly is not guaranteed in fp64; check within the bound
+    u, v = synth.vector_device(d.cols, 2), synth.vector_device(d.cols, 3)
+    yu, yv, yw = (torch.zeros_like(y) for _ in range(3))
+    p.execute(1.0, 0.0, u, yu)
+    p.execute(1.0, 0.0, v, yv)
+    p.execute(1.0, 0.0, 2.0 * u + 3.0 * v, yw)
+    err = (yw - (2.0 * yu + 3.0 * yv)).abs().max()
+    assert float(err) <= 64 * 8 * 2.2e-16 * 5
+    # bitwise reproducibility and alpha/beta epilogue at full size
+    y1 = synth.vector_device(d.rows, 4)
+    y2 = y1.clone()
+    p.execute(0.75, -0.5, u, y1)
+    p.execute(0.75, -0.5, u, y2)
+    assert torch.equal(y1, y2)
+    assert float((y1 - (0.75 * yu - 0.5 * synth.vector_device(d.rows, 4))).abs().max()) <= 1e-14
+    # a sampled block of rows against the oracle
+    lo, hi = 4096 * 1000 + 17, 4096 * 1000 + 17 + 20000
+    rp = d.rowptr[lo:hi + 1].cpu().numpy()
+    sub = synth.Csr(hi - lo, d.cols, rp - rp[0], d.col[rp[0]:rp[-1]].cpu().numpy(), d.val[rp[0]:rp[-1]].cpu().numpy())
+    y_ref = oracle.best_host_spmv(1.0, 0.0, sub.rowptr, sub.col, sub.val, u.cpu().numpy(), np.zeros(hi - lo))
+    bound = oracle.port_row_bound(1.0, 0.0, sub.rowptr, sub.col, sub.val, u.cpu().numpy(), np.zeros(hi - lo))
+    ok, worst, row = oracle.check_rows(yu[lo:hi].cpu().numpy(), y_ref, bound)
+    assert ok, (worst, row)
+    p.destroy()
+
+
+def test_full_size_c4_rmat_row_sums():
+    """C4: R-MAT scale 24 (16.8M rows, 268M nnz, longest row ~370k nnz): A*1 equals the per-row sums of the values,
+    computed independently with a segmented reduction, within the fp64 bound; bitwise reproducible."""
+    import torch
+    d = synth.rmat_device(24, 16, seed=1)
+    p = SpmvPlan(desc_of(d))
+    info = p.info()
+    assert info.nsplit_rows > 0 and info.bin_rows[3] > 0 and info.tiles_per_kind[2] > 0
+    ones = torch.ones(d.cols, dtype=torch.float64, device="cuda")
+    y = torch.zeros(d.rows, dtype=torch.float64, device="cuda")
+    p.execute(1.0, 0.0, ones, y)
+    y2 = torch.zeros_like(y)
+    p.execute(1.0, 0.0, ones, y2)
+    assert torch.equal(y, y2)
+    lens = (d.rowptr[1:] - d.rowptr[:-1]).to(torch.int64)
+    row_of = torch.repeat_interleave(torch.arange(d.rows, device="cuda"), lens)
+    ref = torch.zeros_like(y).index_add_(0, row_of, d.val)
+    absum = torch.zeros_like(y).index_add_(0, row_of, d.val.abs())
+    # index_add_ is itself a floating-point reduction in another order: allow its error as well
+    assert bool(((y - ref).abs() <= 2e-12 * absum + 1e-300).all())
+    assert int((lens == 0).sum()) > 0 and float(y[lens == 0].abs().max()) == 0.0
+    p.destroy()
