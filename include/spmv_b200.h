@@ -41,17 +41,19 @@ extern "C" {
 #define SPMV_B200_FLAG_NO_TMA 1u       /* stream tiles with plain loads instead of cp.async.bulk            */
 #define SPMV_B200_FLAG_BETA0_SKIP_Y 2u /* beta==0: do not read y (cuSPARSE semantics); default reads y so   */
                                        /* that NaN/Inf in y propagate exactly like cli/verification.cpp:64  */
+#define SPMV_B200_FLAG_GATHER_NO_L1 8u /* gather x with L1::no_allocate                                             */
+#define SPMV_B200_FLAG_L2_PERSIST_X 4u /* mark x as persisting in L2 for the SpMV launches (irregular gathers)      */
 
 /* row bins (by nnz per row) and tile kinds (which per-bin kernel streams a row block) */
 enum { SPMV_B200_BIN_SHORT = 0, SPMV_B200_BIN_MEDIUM = 1, SPMV_B200_BIN_LONG = 2, SPMV_B200_BIN_VERYLONG = 3 };
 enum { SPMV_B200_KIND_SHORT = 0, SPMV_B200_KIND_MEDIUM = 1, SPMV_B200_KIND_MIXED = 2 };
 
 typedef struct spmv_b200_options {
-  int32_t tile_nnz;   /* nnz per row block (multiple of 256, >= 256); 0 = default (2048)            */
+  int32_t tile_nnz;   /* nnz per row block (multiple of 256 in [256,16384]); 0 = from the average row length */
   int32_t short_max;  /* rows with nnz <= short_max are SHORT; 0 = default (8)                       */
   int32_t medium_max; /* rows with nnz <= medium_max are MEDIUM, multiple of 4, <= tile_nnz; 0 = 128 */
-  int32_t vec_div;    /* MEDIUM kernel: lanes per row = pow2ceil(avg_nnz / vec_div); 0 = default (8) */
-  uint32_t flags;     /* SPMV_B200_FLAG_*                                                            */
+  int32_t vec_div;    /* MEDIUM kernel: lanes per row = pow2ceil(avg_nnz / vec_div); 0 = default (16) */
+  uint32_t flags;     /* SPMV_B200_FLAG_* ; bits 8-11 / 12-15 select SHORT / MEDIUM kernel variants (tuning) */
 } spmv_b200_options;
 
 typedef struct spmv_b200_plan_info {

@@ -36,6 +36,7 @@ class PlanInfo(C.Structure):
 
 FLAG_NO_TMA = 1
 FLAG_BETA0_SKIP_Y = 2
+FLAG_L2_PERSIST_X = 4
 
 EXPORT_IDS = {"tile_row": 0, "tile_elem": 1, "tile_split": 2, "tile_kind": 3, "tile_part": 4, "row_bin": 5,
               "split_rows": 6, "tile_maxlen": 7}

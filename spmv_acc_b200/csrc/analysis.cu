@@ -182,16 +182,16 @@ static inline int grid_for(long long n, int threads, int cap) {
   return (int)g;
 }
 
-int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
-  const int m = p->m;
-  if (m == 0) {
-    p->ntiles = 0;
+int analysis_prepare(spmv_b200_plan *p, cudaStream_t stream) {
+  // base / end of the nnz range (rowptr may be a view into a larger matrix: rowptr[0] need not be 0)
+  if (p->m == 0) {
+    p->nnz = 0;
+    p->elem_end = 0;
     return SPMV_B200_OK;
   }
-  // base / end of the nnz range (rowptr may be a view into a larger matrix: rowptr[0] need not be 0)
   int h_be[2];
   B200_CUDA(cudaMemcpyAsync(&h_be[0], p->rowptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  B200_CUDA(cudaMemcpyAsync(&h_be[1], p->rowptr + m, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  B200_CUDA(cudaMemcpyAsync(&h_be[1], p->rowptr + p->m, sizeof(int), cudaMemcpyDeviceToHost, stream));
   B200_CUDA(cudaStreamSynchronize(stream));
   const long long total = (long long)h_be[1] - (long long)h_be[0];
   if (total < 0) {
@@ -203,7 +203,19 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
     return SPMV_B200_ERR_ARG;
   }
   p->nnz = total;
+  p->elem_base = h_be[0];
   p->elem_end = h_be[1];
+  return SPMV_B200_OK;
+}
+
+int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
+  const int m = p->m;
+  if (m == 0) {
+    p->ntiles = 0;
+    return SPMV_B200_OK;
+  }
+  const long long total = p->nnz;
+  const int h_be[2] = {(int)p->elem_base, (int)p->elem_end};
   const long long nt = std::max<long long>(1, (total + p->T - 1) / p->T);
   if (nt > 0x7ffffff0LL) {
     set_error("too many tiles");

@@ -25,6 +25,26 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
   return SPMV_B200_ERR_CUDA;
 }
 
+// Tile size when the caller does not fix it: one pass of the 256 threads over the rows of a tile. A tile of T nnz
+// holds T/avg rows; the row kernels give each row V = pow2ceil(avg / vec_div) lanes, so T = avg * 256 / V makes every
+// lane group own exactly one row (fewest round trips to memory per CTA). Clamped to [1024, 4096], multiple of 256.
+static int auto_tile(const spmv_b200_plan *p) {
+  if (p->m <= 0 || p->nnz <= 0)
+    return 2048;
+  const double avg = (double)p->nnz / (double)p->m;
+  int want = (int)((avg + p->vec_div - 1) / p->vec_div);
+  int V = 1;
+  while (V < want && V < 32)
+    V <<= 1;
+  const double t = avg * (kThreads / V);
+  int T = (int)(t / 256.0) * 256; // rounded down: one more row than lane groups would cost a second pass
+  if (T < 1024)
+    T = 1024;
+  if (T > 4096)
+    T = 4096;
+  return T;
+}
+
 static int free_plan_arrays(spmv_b200_plan *p) {
   void *ptrs[] = {p->tile_row, p->tile_elem, p->tile_split, p->tile_part, p->tile_maxlen, p->tile_kind,
                   p->list[0],  p->list[1],   p->list[2],    p->split_rows, p->partials};
@@ -71,7 +91,7 @@ int spmv_b200_plan_create(spmv_b200_plan **out, int32_t m, int32_t n, int64_t nn
   p->rowptr = d_rowptr;
   p->col = d_colidx;
   p->val = d_val;
-  p->T = (opt && opt->tile_nnz) ? opt->tile_nnz : kDefaultTile;
+  p->T = (opt && opt->tile_nnz) ? opt->tile_nnz : 2048; // provisional; the automatic choice needs nnz (below)
   p->short_max = (opt && opt->short_max) ? opt->short_max : kDefaultShort;
   p->medium_max = (opt && opt->medium_max) ? opt->medium_max : kDefaultMedium;
   p->vec_div = (opt && opt->vec_div) ? opt->vec_div : kDefaultVecDiv;
@@ -86,7 +106,15 @@ int spmv_b200_plan_create(spmv_b200_plan **out, int32_t m, int32_t n, int64_t nn
   const bool aligned = ((reinterpret_cast<uintptr_t>(d_val) & 15u) == 0) &&
                        ((reinterpret_cast<uintptr_t>(d_colidx) & 15u) == 0);
   p->uses_tma = aligned && !(p->flags & SPMV_B200_FLAG_NO_TMA);
-  int rc = kernels_configure(p);
+  int rc = analysis_prepare(p, static_cast<cudaStream_t>(stream));
+  if (rc == SPMV_B200_OK && !(opt && opt->tile_nnz))
+    p->T = auto_tile(p);
+  if (p->T < p->medium_max)
+    p->T = (p->medium_max + 255) / 256 * 256;
+  if (rc == SPMV_B200_OK && !((p->flags >> 8) & 0xf) && p->m > 0 && (double)p->nnz / p->m > 6.0)
+    p->flags |= 1u << 8; // SHORT rows of 7+ nnz: gather 8 per round instead of 6 (variant table in kernels.cu)
+  if (rc == SPMV_B200_OK)
+    rc = kernels_configure(p);
   if (rc == SPMV_B200_OK)
     rc = analysis_run(p, static_cast<cudaStream_t>(stream));
   if (rc != SPMV_B200_OK) {

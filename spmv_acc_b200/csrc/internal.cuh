@@ -12,12 +12,12 @@
 namespace b200 {
 
 constexpr int kThreads = 256;     // threads per CTA of every streaming kernel
-constexpr int kRowChunk = 1024;   // row pointers staged in shared memory per pass (rows per pass = kRowChunk)
+constexpr int kRowChunk = 512;    // row pointers staged in shared memory per pass (rows per pass = kRowChunk)
 constexpr int kSerialMax = 16;    // MIXED kernel: rows up to this length are reduced by one thread
-constexpr int kDefaultTile = 2048;
+constexpr int kDefaultTile = 0; // 0 = chosen from the average row length (see auto_tile in capi.cu)
 constexpr int kDefaultShort = 8;
 constexpr int kDefaultMedium = 128;
-constexpr int kDefaultVecDiv = 8;
+constexpr int kDefaultVecDiv = 16;
 
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
@@ -46,6 +46,7 @@ struct SpmvArgs {
   int cap;      // element capacity of the shared-memory tile
   int vec_div;  // MEDIUM: lanes per row = pow2ceil(avg / vec_div)
   int read_y;   // 0: beta == 0 and SPMV_B200_FLAG_BETA0_SKIP_Y
+  int gather_na; // 1: x gathers use L1::no_allocate
 };
 
 struct FixupArgs {
@@ -64,6 +65,7 @@ struct FixupArgs {
 struct spmv_b200_plan {
   int m = 0, n = 0;
   long long nnz = 0;      // rowptr[m] - rowptr[0]
+  long long elem_base = 0; // rowptr[0]
   long long elem_end = 0; // rowptr[m]
   const int *rowptr = nullptr;
   const int *col = nullptr;
@@ -75,6 +77,8 @@ struct spmv_b200_plan {
   int ntiles = 0;
   int cap = 0;
   size_t smem_bytes = 0;
+  size_t persist_bytes = 0, max_window_bytes = 0; // L2 persistence for x (SPMV_B200_FLAG_L2_PERSIST_X)
+  int variant_short = 0, variant_medium = 0; // kernel variants (option flag bits 8-11 / 12-15)
   // device arrays owned by the plan
   int *tile_row = nullptr;
   int *tile_elem = nullptr;
@@ -95,6 +99,7 @@ struct spmv_b200_plan {
 namespace b200 {
 
 // analysis.cu
+int analysis_prepare(spmv_b200_plan *p, cudaStream_t stream); // reads rowptr[0], rowptr[m]
 int analysis_run(spmv_b200_plan *p, cudaStream_t stream);
 int analysis_row_bins(const spmv_b200_plan *p, unsigned char *d_out, cudaStream_t stream);
 int shard_bounds_run(int m, long long nnz, const int *d_rowptr, int nshards, int *h_bounds, cudaStream_t stream);

@@ -22,6 +22,8 @@
 // line_enhance_spmv_imp.inl:11-95), flat (src/acc/hip-flat/flat_imp_one_pass.hpp:15-77, which uses atomicAdd and
 // assumes beta == 1), merge-path reduction + update (benchmark/merge-path/merge_path_reduction.h:80-136,
 // merge_path_update.h:8-64). The epilogue y = alpha*sum + beta*y follows cli/verification.cpp:64.
+#include <cstdlib>
+
 #include "internal.cuh"
 
 namespace b200 {
@@ -82,6 +84,13 @@ __device__ __forceinline__ int ld_stream_s32(const int *p) {
   return v;
 }
 
+// x gather through the read-only path; `na` selects L1::no_allocate (the line is not kept in L1)
+__device__ __forceinline__ double gather_x(const double *__restrict__ x, int c, int na) {
+  if (na)
+    return ld_stream_f64(x + c);
+  return __ldg(x + c);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // tile streaming: global -> shared. Element i of the tile lives at smem index (i - a0), a0 = elem_begin & ~3.
 // ---------------------------------------------------------------------------------------------------------------
@@ -121,24 +130,6 @@ __device__ __forceinline__ void tile_issue_loads(const SpmvArgs &a, int a0, int 
   }
 }
 
-// sum_{k = k0, k0+stride, ... < e} sval[k] * x[scol[k]], accumulated left to right, gathers issued four at a time
-__device__ __forceinline__ double row_dot(const double *__restrict__ sval, const int *__restrict__ scol,
-                                          const double *__restrict__ x, int k, const int e, const int stride) {
-  double sum = 0.0;
-  for (; k + 3 * stride < e; k += 4 * stride) {
-    const int c0 = scol[k], c1 = scol[k + stride], c2 = scol[k + 2 * stride], c3 = scol[k + 3 * stride];
-    const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
-    const double v0 = sval[k], v1 = sval[k + stride], v2 = sval[k + 2 * stride], v3 = sval[k + 3 * stride];
-    sum = fma(v0, x0, sum);
-    sum = fma(v1, x1, sum);
-    sum = fma(v2, x2, sum);
-    sum = fma(v3, x3, sum);
-  }
-  for (; k < e; k += stride)
-    sum = fma(sval[k], __ldg(x + scol[k]), sum);
-  return sum;
-}
-
 __device__ __forceinline__ void store_y(const SpmvArgs &a, int row, double sum) {
   // cli/verification.cpp:64  y[i] = alpha * y0 + beta * y[i]
   const double yv = a.read_y ? a.y[row] : 0.0;
@@ -148,7 +139,10 @@ __device__ __forceinline__ void store_y(const SpmvArgs &a, int row, double sum) 
 // ---------------------------------------------------------------------------------------------------------------
 // SHORT (VEC = false) and MEDIUM (VEC = true) tiles: every owned row lies completely inside the tile
 // ---------------------------------------------------------------------------------------------------------------
-template <bool TMA, bool VEC>
+// W = x gathers issued back to back per row and round, R = rows handled by one lane group at a time. All W*R gathers
+// of a round are in flight before the first FMA, and y is fetched before the tile has landed, so that a CTA exposes
+// one round trip to memory per phase (tile, gathers) instead of one per batch of four elements.
+template <bool TMA, bool VEC, int W, int R>
 __global__ void __launch_bounds__(kThreads) k_spmv_rows(const SpmvArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
@@ -173,9 +167,17 @@ __global__ void __launch_bounds__(kThreads) k_spmv_rows(const SpmvArgs a) {
       ++lv;
   }
   const int V = 1 << lv;
-  const int G = kThreads >> lv; // rows per pass
+  const int G = kThreads >> lv; // rows per lane-group pass
   const int g = tid >> lv;
   const int l = tid & (V - 1);
+
+  // y of the first pass, requested while the tile is still in flight
+  double ypre[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    const int r = q * G + g;
+    ypre[q] = (a.read_y && l == 0 && r < nrows && r < kRowChunk) ? a.y[r0 + r] : 0.0;
+  }
 
   for (int cb = 0;; cb += kRowChunk) {
     int nr = nrows - cb;
@@ -189,20 +191,59 @@ __global__ void __launch_bounds__(kThreads) k_spmv_rows(const SpmvArgs a) {
     if (TMA && cb == 0)
       mbar_wait(&bar, 0);
 
-    for (int rb = 0; rb < nr; rb += G) {
-      const int r = rb + g;
-      const bool act = r < nr;
-      double sum = 0.0;
-      if (act) {
-        const int s = srow[r] - a0, e = srow[r + 1] - a0;
-        sum = row_dot(sval, scol, a.x, s + l, e, V);
+    for (int rb = 0; rb < nr; rb += R * G) {
+      int k[R], e[R];
+      double sum[R], yv[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const int r = rb + q * G + g;
+        const bool act = r < nr;
+        k[q] = act ? srow[r] - a0 + l : 0;
+        e[q] = act ? srow[r + 1] - a0 : 0;
+        sum[q] = 0.0;
+        if (cb == 0 && rb == 0)
+          yv[q] = ypre[q];
+        else
+          yv[q] = (a.read_y && act && l == 0) ? a.y[r0 + cb + r] : 0.0;
       }
-      if (VEC) {
-        for (int off = V >> 1; off > 0; off >>= 1)
-          sum += __shfl_down_sync(0xffffffffu, sum, off, V);
+      for (;;) {
+        double xv[R][W];
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            const int kk = k[q] + j * V;
+            xv[q][j] = (kk < e[q]) ? gather_x(a.x, scol[kk], a.gather_na) : 0.0;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            const int kk = k[q] + j * V;
+            if (kk < e[q])
+              sum[q] = fma(sval[kk], xv[q][j], sum[q]);
+          }
+        }
+        bool more = false;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          k[q] += W * V;
+          more |= k[q] < e[q];
+        }
+        if (!more)
+          break;
       }
-      if (act && l == 0)
-        store_y(a, r0 + cb + r, sum);
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        if (VEC) {
+          for (int off = V >> 1; off > 0; off >>= 1)
+            sum[q] += __shfl_down_sync(0xffffffffu, sum[q], off, V);
+        }
+        const int r = rb + q * G + g;
+        if (r < nr && l == 0) // cli/verification.cpp:64  y[i] = alpha * y0 + beta * y[i]
+          a.y[r0 + cb + r] = a.alpha * sum[q] + a.beta * yv[q];
+      }
     }
     if (cb + kRowChunk >= nrows)
       break;
@@ -262,9 +303,34 @@ __global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
   if (TMA)
     mbar_wait(&bar, 0);
 
-  // products in place: one nnz per thread and step, coalesced smem access
-  for (int i = (e0 - a0) + tid; i < e1 - a0; i += kThreads)
-    sval[i] *= __ldg(a.x + scol[i]);
+  // products in place. All gathers of a batch of 8 strided elements are issued before the first multiply; the values
+  // and indices are read into registers first because the compiler cannot prove that sval and scol do not alias.
+  {
+    const int end = e1 - a0;
+    for (int base = (e0 - a0) + tid; base < end; base += 8 * kThreads) {
+      int c[8];
+      double xv[8], v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = base + j * kThreads;
+        c[j] = (i < end) ? scol[i] : -1;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        xv[j] = (c[j] >= 0) ? gather_x(a.x, c[j], a.gather_na) : 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = base + j * kThreads;
+        v[j] = (i < end) ? sval[i] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = base + j * kThreads;
+        if (i < end)
+          sval[i] = v[j] * xv[j];
+      }
+    }
+  }
   __syncthreads();
 
   if (split_begin) { // leading elements belong to a row that started in an earlier tile
@@ -346,21 +412,55 @@ __global__ void __launch_bounds__(kThreads) k_fixup(const FixupArgs f) {
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static size_t smem_for(const spmv_b200_plan *p, bool mixed) {
-  size_t b = (size_t)p->cap * 12 + sizeof(int) * (kRowChunk + 1);
-  if (mixed)
-    b += sizeof(int) * ((size_t)p->cap / (kSerialMax + 1) + 8);
+static int cap_for(const spmv_b200_plan *p, int kind) {
+  // a tile streams at most T + (longest row that may hang over its trailing boundary) - 1 elements, plus alignment slack
+  return p->T + (kind == SPMV_B200_KIND_SHORT ? ((p->short_max + 3) & ~3) : p->medium_max) + 8;
+}
+
+static size_t smem_for(const spmv_b200_plan *p, int kind) {
+  const int cap = cap_for(p, kind);
+  size_t b = (size_t)cap * 12 + sizeof(int) * (kRowChunk + 1);
+  if (kind == SPMV_B200_KIND_MIXED)
+    b += sizeof(int) * ((size_t)cap / (kSerialMax + 1) + 8);
   return (b + 15) & ~(size_t)15;
 }
 
+typedef void (*RowsKernel)(const SpmvArgs);
+struct RowsVariant {
+  RowsKernel tma, plain;
+  const char *name;
+};
+// variant tables (index = option bits, 0 = default); every entry is a separate instantiation of k_spmv_rows
+static const RowsVariant kShortVariants[] = {
+    {k_spmv_rows<true, false, 6, 1>, k_spmv_rows<false, false, 6, 1>, "W6R1"},
+    {k_spmv_rows<true, false, 8, 1>, k_spmv_rows<false, false, 8, 1>, "W8R1"},
+    {k_spmv_rows<true, false, 4, 1>, k_spmv_rows<false, false, 4, 1>, "W4R1"},
+    {k_spmv_rows<true, false, 4, 2>, k_spmv_rows<false, false, 4, 2>, "W4R2"},
+    {k_spmv_rows<true, false, 8, 2>, k_spmv_rows<false, false, 8, 2>, "W8R2"},
+};
+static const RowsVariant kMediumVariants[] = {
+    {k_spmv_rows<true, true, 8, 1>, k_spmv_rows<false, true, 8, 1>, "W8R1"},
+    {k_spmv_rows<true, true, 4, 1>, k_spmv_rows<false, true, 4, 1>, "W4R1"},
+    {k_spmv_rows<true, true, 4, 2>, k_spmv_rows<false, true, 4, 2>, "W4R2"},
+    {k_spmv_rows<true, true, 8, 2>, k_spmv_rows<false, true, 8, 2>, "W8R2"},
+};
+constexpr int kNumShortVariants = sizeof(kShortVariants) / sizeof(kShortVariants[0]);
+constexpr int kNumMediumVariants = sizeof(kMediumVariants) / sizeof(kMediumVariants[0]);
+
 template <typename K> static int set_smem(K kernel, size_t bytes) {
   B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  // development knob: SPMV_B200_CARVEOUT=<percent of the unified L1/shared array given to shared memory>
+  if (const char *env = getenv("SPMV_B200_CARVEOUT")) {
+    const int pct = atoi(env);
+    if (pct >= 0 && pct <= 100)
+      B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+  }
   return SPMV_B200_OK;
 }
 
 int kernels_configure(spmv_b200_plan *p) {
-  p->cap = p->T + p->medium_max + 8;
-  p->smem_bytes = smem_for(p, true);
+  p->cap = cap_for(p, SPMV_B200_KIND_MIXED);
+  p->smem_bytes = smem_for(p, SPMV_B200_KIND_MIXED);
   int dev = 0, max_optin = 0;
   B200_CUDA(cudaGetDevice(&dev));
   B200_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -369,13 +469,60 @@ int kernels_configure(spmv_b200_plan *p) {
     return SPMV_B200_ERR_ARG;
   }
   p->device = dev;
+  if (p->flags & SPMV_B200_FLAG_L2_PERSIST_X) {
+    int persist_max = 0, window_max = 0;
+    B200_CUDA(cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, dev));
+    B200_CUDA(cudaDeviceGetAttribute(&window_max, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+    if (persist_max > 0) // device-wide carve-out of L2 for persisting lines; set to the maximum the device allows
+      B200_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_max));
+    p->persist_bytes = (size_t)persist_max;
+    p->max_window_bytes = (size_t)window_max;
+  }
+  p->variant_short = (int)((p->flags >> 8) & 0xf);
+  p->variant_medium = (int)((p->flags >> 12) & 0xf);
+  if (p->variant_short >= kNumShortVariants || p->variant_medium >= kNumMediumVariants) {
+    set_error("unknown kernel variant in the option flags");
+    return SPMV_B200_ERR_ARG;
+  }
   int rc;
-  const size_t sr = smem_for(p, false), sm = smem_for(p, true);
-  if ((rc = set_smem(k_spmv_rows<true, false>, sr)) || (rc = set_smem(k_spmv_rows<true, true>, sr)) ||
-      (rc = set_smem(k_spmv_rows<false, false>, sr)) || (rc = set_smem(k_spmv_rows<false, true>, sr)) ||
-      (rc = set_smem(k_spmv_mixed<true>, sm)) || (rc = set_smem(k_spmv_mixed<false>, sm)))
+  const RowsVariant &vs = kShortVariants[p->variant_short], &vm = kMediumVariants[p->variant_medium];
+  if ((rc = set_smem(vs.tma, smem_for(p, SPMV_B200_KIND_SHORT))) ||
+      (rc = set_smem(vs.plain, smem_for(p, SPMV_B200_KIND_SHORT))) ||
+      (rc = set_smem(vm.tma, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
+      (rc = set_smem(vm.plain, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
+      (rc = set_smem(k_spmv_mixed<true>, smem_for(p, SPMV_B200_KIND_MIXED))) ||
+      (rc = set_smem(k_spmv_mixed<false>, smem_for(p, SPMV_B200_KIND_MIXED))))
     return rc;
   return SPMV_B200_OK;
+}
+
+// Launch with an optional L2 access-policy window that marks x as persisting (gathers of x are the only re-used
+// data of an SpMV; value / colindex are streamed with evict-first). The window is a per-launch attribute, so the
+// caller's stream state is not modified.
+static cudaError_t launch_spmv(RowsKernel k, int grid, size_t smem, cudaStream_t stream, const SpmvArgs &a,
+                               const spmv_b200_plan *p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if ((p->flags & SPMV_B200_FLAG_L2_PERSIST_X) && p->persist_bytes > 0 && p->n > 0) {
+    size_t bytes = sizeof(double) * (size_t)p->n;
+    if (bytes > p->max_window_bytes)
+      bytes = p->max_window_bytes;
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = const_cast<double *>(a.x);
+    attr[0].val.accessPolicyWindow.num_bytes = bytes;
+    attr[0].val.accessPolicyWindow.hitRatio =
+        bytes <= p->persist_bytes ? 1.0f : (float)((double)p->persist_bytes / (double)bytes);
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, k, a);
 }
 
 int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y,
@@ -396,32 +543,31 @@ int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const dou
   a.list = nullptr;
   a.partials = p->partials;
   a.nnz = p->elem_end; // absolute index one past the last element (rowptr may be a view: rowptr[0] != 0)
-  a.cap = p->cap;
   a.vec_div = p->vec_div;
+  a.gather_na = (p->flags & SPMV_B200_FLAG_GATHER_NO_L1) ? 1 : 0;
   a.read_y = (beta == 0.0 && (p->flags & SPMV_B200_FLAG_BETA0_SKIP_Y)) ? 0 : 1;
 
-  const size_t sr = smem_for(p, false), sm = smem_for(p, true);
   const bool tma = p->uses_tma;
   if (p->count[SPMV_B200_KIND_SHORT] > 0) {
+    const RowsVariant &v = kShortVariants[p->variant_short];
     a.list = p->list[SPMV_B200_KIND_SHORT];
-    if (tma)
-      k_spmv_rows<true, false><<<p->count[SPMV_B200_KIND_SHORT], kThreads, sr, stream>>>(a);
-    else
-      k_spmv_rows<false, false><<<p->count[SPMV_B200_KIND_SHORT], kThreads, sr, stream>>>(a);
+    a.cap = cap_for(p, SPMV_B200_KIND_SHORT);
+    B200_CUDA(launch_spmv(tma ? v.tma : v.plain, p->count[SPMV_B200_KIND_SHORT], smem_for(p, SPMV_B200_KIND_SHORT),
+                          stream, a, p));
   }
   if (p->count[SPMV_B200_KIND_MEDIUM] > 0) {
+    const RowsVariant &v = kMediumVariants[p->variant_medium];
     a.list = p->list[SPMV_B200_KIND_MEDIUM];
-    if (tma)
-      k_spmv_rows<true, true><<<p->count[SPMV_B200_KIND_MEDIUM], kThreads, sr, stream>>>(a);
-    else
-      k_spmv_rows<false, true><<<p->count[SPMV_B200_KIND_MEDIUM], kThreads, sr, stream>>>(a);
+    a.cap = cap_for(p, SPMV_B200_KIND_MEDIUM);
+    B200_CUDA(launch_spmv(tma ? v.tma : v.plain, p->count[SPMV_B200_KIND_MEDIUM], smem_for(p, SPMV_B200_KIND_MEDIUM),
+                          stream, a, p));
   }
   if (p->count[SPMV_B200_KIND_MIXED] > 0) {
     a.list = p->list[SPMV_B200_KIND_MIXED];
-    if (tma)
-      k_spmv_mixed<true><<<p->count[SPMV_B200_KIND_MIXED], kThreads, sm, stream>>>(a);
-    else
-      k_spmv_mixed<false><<<p->count[SPMV_B200_KIND_MIXED], kThreads, sm, stream>>>(a);
+    a.cap = cap_for(p, SPMV_B200_KIND_MIXED);
+    const size_t sm = smem_for(p, SPMV_B200_KIND_MIXED);
+    B200_CUDA(launch_spmv(tma ? k_spmv_mixed<true> : k_spmv_mixed<false>, p->count[SPMV_B200_KIND_MIXED], sm, stream,
+                          a, p));
   }
   if (p->nsplit > 0) {
     FixupArgs f;

@@ -49,6 +49,36 @@ def time_plan(csr, opt, reps, alpha=1.0, beta=1.0):
     return ms, info
 
 
+def cusparse_ms(csr, reps, balg):
+    import ctypes as C
+    from spmv_acc_b200 import _lib
+    X = _lib.ctx()
+    x = synth.vector_device(csr.cols, 2)
+    y = synth.vector_device(csr.rows, 3)
+    out = {}
+    for alg, name in ((0, "cusparse_default"), (2, "cusparse_alg2")):
+        h = C.c_void_p()
+        rc = X.spmv_b200_ctx_cusparse_create(C.byref(h), csr.rows, csr.cols, csr.nnz, csr.rowptr.data_ptr(),
+                                             csr.col.data_ptr(), csr.val.data_ptr(), x.data_ptr(), y.data_ptr(), alg)
+        if rc:
+            out[name] = f"error {rc}"
+            continue
+        st = torch.cuda.current_stream().cuda_stream
+        for _ in range(5):
+            X.spmv_b200_ctx_cusparse_spmv(h, 1.0, 1.0, st)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            X.spmv_b200_ctx_cusparse_spmv(h, 1.0, 1.0, st)
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {"ms": round(ms, 5), "gbs": round(balg / ms / 1e6, 1)}
+        X.spmv_b200_ctx_cusparse_destroy(h)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workloads", default="c2")
@@ -56,6 +86,10 @@ def main():
     ap.add_argument("--vecdivs", default="8")
     ap.add_argument("--reps", type=int, default=50)
     ap.add_argument("--no-tma-too", action="store_true")
+    ap.add_argument("--xflags", default="0", help="extra option flags to OR in, comma list (4 = L2 persist x)")
+    ap.add_argument("--cusparse", action="store_true")
+    ap.add_argument("--svar", default="0", help="SHORT kernel variants (option flag bits 8-11)")
+    ap.add_argument("--mvar", default="0", help="MEDIUM kernel variants (option flag bits 12-15)")
     args = ap.parse_args()
     for w in args.workloads.split(","):
         csr = make(w)
@@ -63,15 +97,19 @@ def main():
         balg = synth.algorithmic_bytes(csr.rows, csr.cols, csr.nnz)
         for T in [int(t) for t in args.tiles.split(",")]:
             for vd in [int(v) for v in args.vecdivs.split(",")]:
-                for flags in ([0, FLAG_NO_TMA] if args.no_tma_too else [0]):
+                variants = [(int(a) << 8) | (int(b) << 12) for a in args.svar.split(",") for b in args.mvar.split(",")]
+                for flags in [v | f | int(xf) for v in variants for f in ([0, FLAG_NO_TMA] if args.no_tma_too else [0])
+                              for xf in args.xflags.split(",")]:
                     try:
                         ms, info = time_plan(csr, make_options(T, 0, 0, vd, flags), args.reps)
-                        print(json.dumps({"workload": w, "tile": T, "vec_div": vd, "flags": flags, "ms": round(ms, 5),
+                        print(json.dumps({"workload": w, "tile": info.tile_nnz, "vec_div": vd, "flags": flags, "svar": (flags >> 8) & 15, "mvar": (flags >> 12) & 15, "ms": round(ms, 5),
                                           "gbs": round(balg / ms / 1e6, 1), "gflops": round(2 * csr.nnz / ms / 1e6, 1),
                                           "kinds": list(info.tiles_per_kind), "split": info.nsplit_rows,
                                           "launches": info.launches_per_execute, "smem": info.smem_bytes}), flush=True)
                     except Exception as e:
-                        print(json.dumps({"workload": w, "tile": T, "error": str(e)}), flush=True)
+                        print(json.dumps({"workload": w, "tile": info.tile_nnz, "error": str(e)}), flush=True)
+        if args.cusparse:
+            print(json.dumps({"workload": w, **cusparse_ms(csr, args.reps, balg)}), flush=True)
         del csr
         torch.cuda.empty_cache()
 
