@@ -68,6 +68,8 @@ typedef struct spmv_b200_plan_info {
   int32_t launches_per_execute;
   int64_t bin_rows[4];       /* rows per bin: short / medium / long / very long                 */
   int64_t bin_nnz[4];        /* nnz per bin                                                      */
+  int64_t gather_active;     /* sampled gathers (lanes) of the gather-coalescing statistic      */
+  int64_t gather_lines;      /* distinct 128-byte lines of x those gathers touch                */
   int64_t smem_bytes;        /* dynamic shared memory per CTA of the streaming kernels          */
   int64_t workspace_bytes;   /* device memory owned by the plan                                 */
 } spmv_b200_plan_info;

@@ -153,6 +153,36 @@ int port_analysis(const int *rowptr, int m, int T, int short_max, int medium_max
   return nsplit;
 }
 
+/* Gather-coalescing statistic of analysis.cu:k_gather_stat: 4096 groups of 32 consecutive rows, middle element of every
+ * non-empty row, out[0] = active lanes, out[1] = distinct (colindex >> 4) per group summed over the groups. */
+void port_gather_stat(const int *rowptr, const int *col, int m, long long *out) {
+  const int samples = 4096;
+  out[0] = 0;
+  out[1] = 0;
+  const long long span = m > 32 ? (long long)(m - 32) : 0;
+  for (int w = 0; w < samples; w++) {
+    int lines[32];
+    int nl = 0;
+    for (int lane = 0; lane < 32; lane++) {
+      const long long r = (span * w) / samples + lane;
+      if (r >= m)
+        continue;
+      const int s = rowptr[r], e = rowptr[r + 1];
+      if (e <= s)
+        continue;
+      const int line = col[s + ((e - s) >> 1)] >> 4;
+      out[0] += 1;
+      int seen = 0;
+      for (int q = 0; q < nl; q++)
+        if (lines[q] == line)
+          seen = 1;
+      if (!seen)
+        lines[nl++] = line;
+    }
+    out[1] += nl;
+  }
+}
+
 /* bounds[g] = lower_bound(rowptr, base + total * g / nshards), bounds[0] = 0, bounds[nshards] = m */
 void port_shard_bounds(const int *rowptr, int m, int nshards, int *bounds) {
   if (m == 0) {

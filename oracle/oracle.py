@@ -17,7 +17,7 @@ REFERENCE = Path("/root/reference")
 __all__ = [
     "build", "have_ref", "port_host_spmv", "port_host_spmv_ax", "port_verify_y", "port_verify", "port_row_bound",
     "port_generate_vector", "port_merge_path_partition", "port_flat_break_points_v2", "port_analysis",
-    "port_shard_bounds", "port_tiled_spmv", "ref_host_spmv", "ref_host_spmv_ax", "ref_verify_y",
+    "port_shard_bounds", "port_gather_stat", "port_tiled_spmv", "ref_host_spmv", "ref_host_spmv_ax", "ref_verify_y",
     "ref_adaptive_plus_analyze", "ref_read", "ref_generate_vector", "best_host_spmv", "check_rows",
 ]
 
@@ -38,6 +38,8 @@ def build(with_ref: bool = True) -> None:
     targets = ["all"]
     if with_ref and REFERENCE.exists():
         targets += ["ref", "ref-gpu"]
+        if (HERE.parent / "spmv_acc_b200" / "lib" / "libspmv_b200.so").exists():
+            targets += ["ref-cli"]
     res = subprocess.run(["make", "-s", "-C", str(HERE), *targets], capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"oracle build failed:\n{res.stdout}\n{res.stderr}")
@@ -233,6 +235,15 @@ def port_analysis(rowptr, tile_nnz=2048, short_max=8, medium_max=128):
         "tile_part": tile_part, "tile_maxlen": tile_maxlen, "tile_kind": tile_kind, "row_bin": row_bin,
         "bin_rows": bin_rows, "bin_nnz": bin_nnz, "nsplit": ns, "split_rows": split_rows,
     }
+
+
+def port_gather_stat(rowptr, col):
+    """(active lanes, distinct 128-byte lines) of the sampled gather-coalescing statistic."""
+    rowptr, col = _c(rowptr, _i32), _c(col, _i32)
+    out = np.zeros(2, np.int64)
+    _port_lib().port_gather_stat(_p(rowptr, C.c_int), _p(col, C.c_int), C.c_int(rowptr.size - 1),
+                                 _p(out, C.c_longlong))
+    return int(out[0]), int(out[1])
 
 
 def port_shard_bounds(rowptr, nshards):

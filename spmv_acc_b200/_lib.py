@@ -31,7 +31,8 @@ class PlanInfo(C.Structure):
                 ("short_max", C.c_int32), ("medium_max", C.c_int32), ("vec_div", C.c_int32), ("flags", C.c_uint32),
                 ("uses_tma", C.c_int32), ("ntiles", C.c_int32), ("tiles_per_kind", C.c_int32 * 3),
                 ("nsplit_rows", C.c_int32), ("launches_per_execute", C.c_int32), ("bin_rows", C.c_int64 * 4),
-                ("bin_nnz", C.c_int64 * 4), ("smem_bytes", C.c_int64), ("workspace_bytes", C.c_int64)]
+                ("bin_nnz", C.c_int64 * 4), ("gather_active", C.c_int64), ("gather_lines", C.c_int64),
+                ("smem_bytes", C.c_int64), ("workspace_bytes", C.c_int64)]
 
 
 FLAG_NO_TMA = 1

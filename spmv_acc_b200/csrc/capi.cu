@@ -28,16 +28,27 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 // Tile size when the caller does not fix it: one pass of the 256 threads over the rows of a tile. A tile of T nnz
 // holds T/avg rows; the row kernels give each row V = pow2ceil(avg / vec_div) lanes, so T = avg * 256 / V makes every
 // lane group own exactly one row (fewest round trips to memory per CTA). Clamped to [1024, 4096], multiple of 256.
+static bool irregular_gathers(const spmv_b200_plan *p) {
+  // more than half a cache line per gathered element (sampled): x gathers do not coalesce across rows
+  return p->gather_active > 0 && 2 * p->gather_lines > p->gather_active;
+}
+
 static int auto_tile(const spmv_b200_plan *p) {
   if (p->m <= 0 || p->nnz <= 0)
     return 2048;
+  // Irregular gathers are bound by the number of L1 misses in flight, which scales with the part of the unified
+  // L1/shared array left to L1: small tiles keep the shared-memory carve-out at about half of it (ncu: profiles/).
+  if (irregular_gathers(p))
+    return 1024;
   const double avg = (double)p->nnz / (double)p->m;
   int want = (int)((avg + p->vec_div - 1) / p->vec_div);
   int V = 1;
   while (V < want && V < 32)
     V <<= 1;
   const double t = avg * (kThreads / V);
-  int T = (int)(t / 256.0) * 256; // rounded down: one more row than lane groups would cost a second pass
+  // rounded down (one more row than lane groups would cost a second pass), with 5% slack so that an average just
+  // below a whole number of nnz per row (matrix boundary effects, e.g. 4.999 for the 5-point stencil) still counts
+  int T = (int)(t / 256.0 + 0.05) * 256;
   if (T < 1024)
     T = 1024;
   if (T > 4096)
@@ -107,6 +118,8 @@ int spmv_b200_plan_create(spmv_b200_plan **out, int32_t m, int32_t n, int64_t nn
                        ((reinterpret_cast<uintptr_t>(d_colidx) & 15u) == 0);
   p->uses_tma = aligned && !(p->flags & SPMV_B200_FLAG_NO_TMA);
   int rc = analysis_prepare(p, static_cast<cudaStream_t>(stream));
+  if (rc == SPMV_B200_OK && !(opt && opt->vec_div) && irregular_gathers(p))
+    p->vec_div = 8;
   if (rc == SPMV_B200_OK && !(opt && opt->tile_nnz))
     p->T = auto_tile(p);
   if (p->T < p->medium_max)
@@ -182,6 +195,8 @@ int spmv_b200_plan_get_info(const spmv_b200_plan *p, spmv_b200_plan_info *info) 
     info->bin_rows[b] = p->bin_rows[b];
     info->bin_nnz[b] = p->bin_nnz[b];
   }
+  info->gather_active = p->gather_active;
+  info->gather_lines = p->gather_lines;
   info->smem_bytes = (int64_t)p->smem_bytes;
   info->workspace_bytes = (int64_t)p->workspace_bytes;
   return SPMV_B200_OK;

@@ -65,6 +65,7 @@ struct FixupArgs {
 struct spmv_b200_plan {
   int m = 0, n = 0;
   long long nnz = 0;      // rowptr[m] - rowptr[0]
+  long long gather_active = 0, gather_lines = 0; // sampled gather-coalescing statistic (analysis.cu)
   long long elem_base = 0; // rowptr[0]
   long long elem_end = 0; // rowptr[m]
   const int *rowptr = nullptr;

@@ -51,6 +51,8 @@ def test_analysis_arrays_bit_exact(opts):
         assert list(info.bin_rows) == ref["bin_rows"].tolist(), name
         assert list(info.bin_nnz) == ref["bin_nnz"].tolist(), name
         assert info.nsplit_rows == ref["nsplit"]
+        if h.nnz > 0:
+            assert (info.gather_active, info.gather_lines) == oracle.port_gather_stat(h.rowptr, h.col), name
         kinds = np.bincount(ref["tile_kind"], minlength=3).tolist()
         assert list(info.tiles_per_kind) == kinds
         plan.destroy()
