@@ -268,8 +268,15 @@ def run_b200(args, rank, world, local_rank):
     nnz_total = sum_over_ranks(torch, dist, world, float(csr.nnz))
     rows_total = sum_over_ranks(torch, dist, world, float(csr.rows))
     gflops = 2.0 * nnz_total / (ms_per_step * 1e-3) / 1e9
-    # roofline of the dominant kernel (rank 0's launch): algorithmic bytes of this rank's shard per launch
-    b_alg = alg_bytes(csr.rows, csr.cols if world == 1 else csr.cols, csr.nnz)
+    # roofline of the dominant kernel (rank 0's launch): algorithmic bytes of this rank's shard per launch. With
+    # several ranks x is replicated but a shard only reads the entries its columns reference (own rows + halo):
+    # count those (4096-entry blocks from the analysis) instead of the whole replicated vector.
+    if world == 1:
+        n_ref = csr.cols
+    else:
+        from spmv_acc_b200 import col_block_bitmap
+        n_ref = min(csr.cols, int(col_block_bitmap(csr.col, csr.nnz, csr.cols, 12).sum()) * 4096)
+    b_alg = alg_bytes(csr.rows, n_ref, csr.nnz)
     peak, peak_src = measured_peak()
     achieved = b_alg / (ms_per_step * 1e-3) / 1e9
     traffic = None

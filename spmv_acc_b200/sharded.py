@@ -218,7 +218,9 @@ def bench_power_loop(N: int = 384, iters: int = 100, exchange: str = "auto", war
         "value": 2.0 * nnz_total / sec_iter / 1e9, "unit": "GFLOP/s",
         "effective_gbs": (12 * nnz_total + 4 * (n + 1) + 8 * n + 16 * n) / sec_iter / 1e9,
         "exchange": loop.mode, "exchange_bytes_in_per_iter_rank0": loop.bytes_in_per_iter,
-        "x_checksum_rank0_slice": bits_checksum(loop.x[lo:hi]),
+        # bit pattern checksum of x[0 : n/16] after the last iteration: that range belongs to rank 0 for every
+        # world size <= 8, so equal values across runs with 1/2/4/8 GPUs prove bitwise-identical results
+        "x_checksum_first_16th": bits_checksum(loop.x[0:n // 16]),
         "total_timed_ms": ms,
     }
     plan.destroy()

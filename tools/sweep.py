@@ -83,7 +83,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workloads", default="c2")
     ap.add_argument("--tiles", default="1024,2048,4096,8192")
-    ap.add_argument("--vecdivs", default="8")
+    ap.add_argument("--vecdivs", default="0")
     ap.add_argument("--reps", type=int, default=50)
     ap.add_argument("--no-tma-too", action="store_true")
     ap.add_argument("--xflags", default="0", help="extra option flags to OR in, comma list (4 = L2 persist x)")
