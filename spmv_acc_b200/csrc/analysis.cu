@@ -102,17 +102,41 @@ __global__ void __launch_bounds__(256)
     sh[threadIdx.x] = 0ull;
   __syncthreads();
   const long long base = __ldg(rowptr);
+  // per-thread counters, then one warp reduction and one shared atomic per warp and counter (integer sums are
+  // order independent, so the result does not depend on the schedule)
+  unsigned long long cnt[4] = {0, 0, 0, 0}, sum[4] = {0, 0, 0, 0};
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += (long long)gridDim.x * blockDim.x) {
     const int s = __ldg(rowptr + r);
     const int len = __ldg(rowptr + r + 1) - s;
     const int bin = len <= short_max ? 0 : (len <= medium_max ? 1 : (len <= T ? 2 : 3));
-    atomicAdd(&sh[bin], 1ull);
-    atomicAdd(&sh[4 + bin], (unsigned long long)len);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      cnt[b] += (bin == b) ? 1ull : 0ull;
+      sum[b] += (bin == b) ? (unsigned long long)len : 0ull;
+    }
     long long t = ((long long)s - base) / T;
     if (t > ntiles - 1)
       t = ntiles - 1;
-    if (len > 0)
+    // most rows of a tile are no longer than the value already stored: test before paying for the atomic
+    if (len > 0 && len > tile_maxlen[t])
       atomicMax(tile_maxlen + t, len);
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      cnt[b] += __shfl_xor_sync(0xffffffffu, cnt[b], off);
+      sum[b] += __shfl_xor_sync(0xffffffffu, sum[b], off);
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (cnt[b])
+        atomicAdd(&sh[b], cnt[b]);
+      if (sum[b])
+        atomicAdd(&sh[4 + b], sum[b]);
+    }
   }
   __syncthreads();
   if (threadIdx.x < 8 && sh[threadIdx.x] != 0ull)
