@@ -42,6 +42,7 @@ extern "C" {
 #define SPMV_B200_FLAG_BETA0_SKIP_Y 2u /* beta==0: do not read y (cuSPARSE semantics); default reads y so   */
                                        /* that NaN/Inf in y propagate exactly like cli/verification.cpp:64  */
 #define SPMV_B200_FLAG_GATHER_NO_L1 8u /* gather x with L1::no_allocate                                             */
+#define SPMV_B200_FLAG_PERSISTENT 0x20000u /* row kernels as persistent CTAs with a two-stage TMA ring              */
 #define SPMV_B200_FLAG_L2_PERSIST_X 4u /* mark x as persisting in L2 for the SpMV launches (irregular gathers)      */
 
 /* row bins (by nnz per row) and tile kinds (which per-bin kernel streams a row block) */
@@ -49,7 +50,7 @@ enum { SPMV_B200_BIN_SHORT = 0, SPMV_B200_BIN_MEDIUM = 1, SPMV_B200_BIN_LONG = 2
 enum { SPMV_B200_KIND_SHORT = 0, SPMV_B200_KIND_MEDIUM = 1, SPMV_B200_KIND_MIXED = 2 };
 
 typedef struct spmv_b200_options {
-  int32_t tile_nnz;   /* nnz per row block (multiple of 256 in [256,16384]); 0 = from the average row length */
+  int32_t tile_nnz;   /* items (non-zeros + rows) per row block, multiple of 256 in [256,16384]; 0 = automatic */
   int32_t short_max;  /* rows with nnz <= short_max are SHORT; 0 = default (8)                       */
   int32_t medium_max; /* rows with nnz <= medium_max are MEDIUM, multiple of 4, <= tile_nnz; 0 = 128 */
   int32_t vec_div;    /* MEDIUM kernel: lanes per row = pow2ceil(avg_nnz / vec_div); 0 = default (16) */

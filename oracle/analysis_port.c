@@ -14,7 +14,8 @@
  *   port_adaptive_plus_blocks   is NOT restated here: the reference's csr_adaptive_plus_analyze_imp is compiled in
  *       place into oracle/_ref/libref_oracle.so and used as a cross-check of the nnz-balance property only.
  *
- * Specification of port_analysis: identical to the comment block at the top of analysis.cu.
+ * Specification of port_analysis: identical to the comment block at the top of analysis.cu (tiles balance non-zeros
+ * and rows: row r starts at merged position f(r) = rowptr[r] - base + r).
  */
 #include <stdint.h>
 #include <string.h>
@@ -24,6 +25,19 @@ static int lower_bound_rowptr(const int *rowptr, int m, long long target) {
   while (lo < hi) {
     int mid = lo + ((hi - lo) >> 1);
     if ((long long)rowptr[mid] < target)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+/* first index in [0, m] with f(idx) = rowptr[idx] - base + idx >= target */
+static int lower_bound_merge(const int *rowptr, int m, long long base, long long target) {
+  int lo = 0, hi = m;
+  while (lo < hi) {
+    int mid = lo + ((hi - lo) >> 1);
+    if ((long long)rowptr[mid] - base + mid < target)
       lo = mid + 1;
     else
       hi = mid;
@@ -64,7 +78,7 @@ int port_analysis_ntiles(const int *rowptr, int m, int T) {
   if (m == 0)
     return 0;
   long long total = (long long)rowptr[m] - (long long)rowptr[0];
-  long long nt = (total + T - 1) / T;
+  long long nt = (total + m + T - 1) / T;
   return (int)(nt < 1 ? 1 : nt);
 }
 
@@ -83,7 +97,8 @@ int port_analysis(const int *rowptr, int m, int T, int short_max, int medium_max
   const int ntiles = port_analysis_ntiles(rowptr, m, T);
   const long long base = rowptr[0], end = rowptr[m];
   for (int t = 0; t <= ntiles; t++) {
-    long long target = base + (long long)t * T;
+    const long long pos = (long long)t * T;
+    long long target = base + pos;
     if (target > end)
       target = end;
     int row, elem;
@@ -95,13 +110,14 @@ int port_analysis(const int *rowptr, int m, int T, int short_max, int medium_max
       row = m;
       elem = (int)end;
     } else {
-      row = lower_bound_rowptr(rowptr, m, target);
+      row = lower_bound_merge(rowptr, m, base, pos);
+      const long long cut = base + pos - (row - 1);
       elem = rowptr[row];
-      if ((long long)rowptr[row] > target) {
+      if (cut < (long long)rowptr[row]) {
         const int len = rowptr[row] - rowptr[row - 1];
         if (len > medium_max) {
           split = 1;
-          elem = (int)target;
+          elem = (int)cut;
         }
       }
     }
@@ -119,7 +135,7 @@ int port_analysis(const int *rowptr, int m, int T, int short_max, int medium_max
       row_bin[r] = (unsigned char)bin;
     bin_rows[bin] += 1;
     bin_nnz[bin] += len;
-    long long t = ((long long)rowptr[r] - base) / T;
+    long long t = ((long long)rowptr[r] - base + r) / T;
     if (t > ntiles - 1)
       t = ntiles - 1;
     if (len > tile_maxlen[t])
@@ -140,7 +156,7 @@ int port_analysis(const int *rowptr, int m, int T, int short_max, int medium_max
     const int r = tile_row[t] - 1;
     if (tile_row[t - 1] <= r) {
       if (split_rows && nsplit < cap_split) {
-        long long t1 = ((long long)rowptr[r + 1] - 1 - base) / T;
+        long long t1 = ((long long)rowptr[r + 1] - 1 - base + r) / T;
         if (t1 > ntiles - 1)
           t1 = ntiles - 1;
         split_rows[nsplit] = r;
@@ -154,11 +170,11 @@ int port_analysis(const int *rowptr, int m, int T, int short_max, int medium_max
 }
 
 /* Gather-coalescing statistic of analysis.cu:k_gather_stat: 4096 groups of 32 consecutive rows, middle element of every
- * non-empty row, out[0] = active lanes, out[1] = distinct (colindex >> 4) per group summed over the groups. */
-void port_gather_stat(const int *rowptr, const int *col, int m, long long *out) {
+ * non-empty row, out[0] = active lanes, out[1] = distinct (colindex >> 4) per group summed over the groups,
+ * out[2] = non-zeros of the sampled rows, out[3] = those in rows longer than medium_max. */
+void port_gather_stat(const int *rowptr, const int *col, int m, int medium_max, long long *out) {
   const int samples = 4096;
-  out[0] = 0;
-  out[1] = 0;
+  out[0] = out[1] = out[2] = out[3] = 0;
   const long long span = m > 32 ? (long long)(m - 32) : 0;
   for (int w = 0; w < samples; w++) {
     int lines[32];
@@ -168,6 +184,9 @@ void port_gather_stat(const int *rowptr, const int *col, int m, long long *out) 
       if (r >= m)
         continue;
       const int s = rowptr[r], e = rowptr[r + 1];
+      out[2] += e - s;
+      if (e - s > medium_max)
+        out[3] += e - s;
       if (e <= s)
         continue;
       const int line = col[s + ((e - s) >> 1)] >> 4;
@@ -256,7 +275,7 @@ int port_tiled_spmv(double alpha, double beta, const double *value, const int *r
       continue;
     const int r = tile_row[t] - 1;
     if (tile_row[t - 1] <= r) {
-      long long t1 = ((long long)rowptr[r + 1] - 1 - base) / T;
+      long long t1 = ((long long)rowptr[r + 1] - 1 - base + r) / T;
       if (t1 > ntiles - 1)
         t1 = ntiles - 1;
       double s = partials[2 * (t - 1) + 1];

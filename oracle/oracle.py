@@ -237,13 +237,13 @@ def port_analysis(rowptr, tile_nnz=2048, short_max=8, medium_max=128):
     }
 
 
-def port_gather_stat(rowptr, col):
-    """(active lanes, distinct 128-byte lines) of the sampled gather-coalescing statistic."""
+def port_gather_stat(rowptr, col, medium_max=128):
+    """(active lanes, distinct 128-byte lines, sampled nnz, sampled nnz in long rows) of the sampling pass."""
     rowptr, col = _c(rowptr, _i32), _c(col, _i32)
-    out = np.zeros(2, np.int64)
+    out = np.zeros(4, np.int64)
     _port_lib().port_gather_stat(_p(rowptr, C.c_int), _p(col, C.c_int), C.c_int(rowptr.size - 1),
-                                 _p(out, C.c_longlong))
-    return int(out[0]), int(out[1])
+                                 C.c_int(medium_max), _p(out, C.c_longlong))
+    return tuple(int(v) for v in out)
 
 
 def port_shard_bounds(rowptr, nshards):

@@ -9,18 +9,26 @@
 // and the 4-sample selector of adaptive (src/acc/hip-adaptive/adaptive.cpp:16-67).
 //
 // Specification (T = tile_nnz, L = medium_max, S = short_max, base = rowptr[0], end = rowptr[m]):
-//   ntiles      = max(1, ceil((end-base)/T)) if m > 0 else 0
-//   target(t)   = min(base + t*T, end)
-//   tile_row[t] = 0 if t == 0; m if t == ntiles; else min{ r in [0,m] : rowptr[r] >= target(t) }
-//   tile_part[t]= max{ r in [0,m] : rowptr[r] <= target(t) }            (the reference's merge-path partition S[t])
-//   a row "straddles" boundary t (0 < t < ntiles) when rowptr[tile_row[t]] > target(t); it is row tile_row[t]-1.
+//   Tiles balance nnz AND rows (merge-path coordinate): the items of row r are its non-zeros followed by one
+//   end-of-row marker, so the first item of row r sits at position f(r) = (rowptr[r] - base) + r of the merged list and
+//   element x of row r at position (x - base) + r. Tile t covers positions [t*T, (t+1)*T): at most T non-zeros and at
+//   most T rows, however many rows are empty.
+//   ntiles      = max(1, ceil((end - base + m) / T)) if m > 0 else 0
+//   tile_row[t] = 0 if t == 0; m if t == ntiles; else min{ r in [0,m] : f(r) >= t*T }      (rows are owned by the tile
+//                 that holds their first item)
+//   cut(t)      = base + t*T - (tile_row[t] - 1)   = number of non-zeros in front of position t*T, as an index
+//   a row "straddles" boundary t (0 < t < ntiles) when cut(t) < rowptr[tile_row[t]]; it is row tile_row[t]-1.
 //   tile_split[t] = 1 iff the straddling row is longer than L (its partial sums are combined by the fix-up kernel);
-//                   a straddling row of length <= L is streamed entirely by the tile that owns its first element.
-//   tile_elem[t]  = base if t == 0; end if t == ntiles; target(t) if tile_split[t]; else rowptr[tile_row[t]]
-//   row r is owned by tile min(floor((rowptr[r]-base)/T), ntiles-1); tile_maxlen[t] = max nnz of the rows it owns.
+//                   a straddling row of length <= L is streamed entirely by the tile that owns it.
+//   tile_elem[t]  = base if t == 0; end if t == ntiles; cut(t) if tile_split[t]; else rowptr[tile_row[t]]
+//   tile_part[t]  = max{ r in [0,m] : rowptr[r] <= min(base + t*T, end) }   (the reference's merge-path partition S[t],
+//                   benchmark/merge-path/merge_path_partition.h:7-17; exported for the cross-check only)
+//   row r is owned by tile min(floor(f(r)/T), ntiles-1); tile_maxlen[t] = max nnz of the rows it owns.
 //   tile_kind[t]  = MIXED if tile_split[t] or tile_split[t+1] or tile_maxlen[t] > L;
 //                   SHORT if tile_maxlen[t] <= S; else MEDIUM.
 //   bin(r) = SHORT if nnz_r <= S; MEDIUM if nnz_r <= L; LONG if nnz_r <= T; else VERYLONG.
+//   split row r (first split boundary t, i.e. tile_row[t-1] <= r = tile_row[t]-1): fragments live in tiles
+//   t-1 .. t1 with t1 = min(floor(((rowptr[r+1] - 1 - base) + r) / T), ntiles-1).
 #include <algorithm>
 #include <vector>
 
@@ -34,6 +42,20 @@ __device__ __forceinline__ int lower_bound_rowptr(const int *__restrict__ rowptr
   while (lo < hi) {
     const int mid = lo + ((hi - lo) >> 1);
     if ((long long)__ldg(rowptr + mid) < target)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+// first index in [0, m] with f(idx) = rowptr[idx] - base + idx >= target (f is strictly increasing, f(m) >= target)
+__device__ __forceinline__ int lower_bound_merge(const int *__restrict__ rowptr, int m, long long base,
+                                                 long long target) {
+  int lo = 0, hi = m;
+  while (lo < hi) {
+    const int mid = lo + ((hi - lo) >> 1);
+    if ((long long)__ldg(rowptr + mid) - base + mid < target)
       lo = mid + 1;
     else
       hi = mid;
@@ -63,7 +85,8 @@ __global__ void __launch_bounds__(256)
     return;
   const long long base = __ldg(rowptr);
   const long long end = __ldg(rowptr + m);
-  long long target = base + (long long)t * T;
+  const long long pos = (long long)t * T; // position in the merged (non-zeros + row ends) list
+  long long target = base + pos;          // nnz-only target of the reference's partition (cross-check array)
   if (target > end)
     target = end;
   int row, elem, aux = 0;
@@ -75,14 +98,15 @@ __global__ void __launch_bounds__(256)
     row = m;
     elem = (int)end;
   } else {
-    row = lower_bound_rowptr(rowptr, m, target);
+    row = lower_bound_merge(rowptr, m, base, pos); // >= 1 because f(0) = 0 < pos
     const int row_start = __ldg(rowptr + row);
+    const long long cut = base + pos - (row - 1); // non-zeros in front of the boundary (index into value/colindex)
     elem = row_start;
-    if ((long long)row_start > target) { // row-1 straddles this boundary
+    if (cut < (long long)row_start) { // row-1 straddles this boundary
       const int len = row_start - __ldg(rowptr + row - 1);
       if (len > medium_max) {
         split = 1;
-        elem = (int)target;
+        elem = (int)cut;
         aux = row_start; // end of the split row
       }
     }
@@ -114,7 +138,7 @@ __global__ void __launch_bounds__(256)
       cnt[b] += (bin == b) ? 1ull : 0ull;
       sum[b] += (bin == b) ? (unsigned long long)len : 0ull;
     }
-    long long t = ((long long)s - base) / T;
+    long long t = ((long long)s - base + r) / T;
     if (t > ntiles - 1)
       t = ntiles - 1;
     // most rows of a tile are no longer than the value already stored: test before paying for the atomic
@@ -158,6 +182,33 @@ __global__ void __launch_bounds__(256)
   else
     k = SPMV_B200_KIND_MEDIUM;
   tile_kind[t] = k;
+}
+
+__global__ void __launch_bounds__(256)
+    k_tile_desc(const int *__restrict__ rowptr, int ntiles, const int *__restrict__ tile_row,
+                const int *__restrict__ tile_elem, const unsigned char *__restrict__ tile_split,
+                TileDesc *__restrict__ desc) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles)
+    return;
+  TileDesc d;
+  d.r0 = tile_row[t];
+  d.r1 = tile_row[t + 1];
+  d.e0 = tile_elem[t];
+  d.e1 = tile_elem[t + 1];
+  d.flags = (tile_split[t] ? 1 : 0) | (tile_split[t + 1] ? 2 : 0);
+  const int first_row_start = __ldg(rowptr + d.r0); // r0 <= m
+  d.head_end = first_row_start < d.e1 ? first_row_start : d.e1;
+  d.tail_start = ((d.flags & 2) && d.r1 > d.r0) ? __ldg(rowptr + d.r1 - 1) : d.e1;
+  d.tile = t;
+  desc[t] = d;
+}
+
+__global__ void __launch_bounds__(256) k_gather_desc(const int *__restrict__ list, int n,
+                                                      const TileDesc *__restrict__ all, TileDesc *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = all[list[i]];
 }
 
 __global__ void __launch_bounds__(256) k_row_bins(const int *__restrict__ rowptr, int m, int T, int short_max,
@@ -204,16 +255,18 @@ __global__ void __launch_bounds__(256)
 // column patterns ~1.0. Integer counts of a fixed sample: deterministic, restated in oracle/analysis_port.c.
 constexpr int kGatherSamples = 4096;
 __global__ void __launch_bounds__(256)
-    k_gather_stat(const int *__restrict__ rowptr, const int *__restrict__ col, int m, unsigned long long *stat) {
+    k_gather_stat(const int *__restrict__ rowptr, const int *__restrict__ col, int m, int medium_max,
+                  unsigned long long *stat) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= kGatherSamples)
     return;
   const long long span = m > 32 ? (long long)(m - 32) : 0;
   const long long r = (span * warp) / kGatherSamples + lane;
-  int line = -1;
+  int line = -1, len = 0;
   if (r < m) {
     const int s = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+    len = e - s;
     if (e > s)
       line = __ldg(col + s + ((e - s) >> 1)) >> 4;
   }
@@ -221,9 +274,18 @@ __global__ void __launch_bounds__(256)
   const unsigned same = __match_any_sync(0xffffffffu, line);
   const bool leader = (line >= 0) && ((__ffs(same) - 1) == lane);
   const unsigned leaders = __ballot_sync(0xffffffffu, leader);
+  // stat[2] = non-zeros of the sampled rows, stat[3] = those in rows longer than medium_max (row-length skew)
+  unsigned long long nz = (unsigned long long)len, nzl = len > medium_max ? (unsigned long long)len : 0ull;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    nz += __shfl_xor_sync(0xffffffffu, nz, off);
+    nzl += __shfl_xor_sync(0xffffffffu, nzl, off);
+  }
   if (lane == 0) {
     atomicAdd(stat, (unsigned long long)__popc(active));
     atomicAdd(stat + 1, (unsigned long long)__popc(leaders));
+    atomicAdd(stat + 2, nz);
+    atomicAdd(stat + 3, nzl);
   }
 }
 
@@ -259,18 +321,20 @@ int analysis_prepare(spmv_b200_plan *p, cudaStream_t stream) {
   p->nnz = total;
   p->elem_base = h_be[0];
   p->elem_end = h_be[1];
-  p->gather_active = p->gather_lines = 0;
+  p->gather_active = p->gather_lines = p->sample_nnz = p->sample_nnz_long = 0;
   if (total > 0 && p->col) {
-    unsigned long long *d_stat = nullptr, h_stat[2];
+    unsigned long long *d_stat = nullptr, h_stat[4];
     B200_CUDA(cudaMalloc(&d_stat, sizeof(h_stat)));
     B200_CUDA(cudaMemsetAsync(d_stat, 0, sizeof(h_stat), stream));
-    k_gather_stat<<<kGatherSamples * 32 / 256, 256, 0, stream>>>(p->rowptr, p->col, p->m, d_stat);
+    k_gather_stat<<<kGatherSamples * 32 / 256, 256, 0, stream>>>(p->rowptr, p->col, p->m, p->medium_max, d_stat);
     B200_CUDA(cudaGetLastError());
     B200_CUDA(cudaMemcpyAsync(h_stat, d_stat, sizeof(h_stat), cudaMemcpyDeviceToHost, stream));
     B200_CUDA(cudaStreamSynchronize(stream));
     B200_CUDA(cudaFree(d_stat));
     p->gather_active = (long long)h_stat[0];
     p->gather_lines = (long long)h_stat[1];
+    p->sample_nnz = (long long)h_stat[2];
+    p->sample_nnz_long = (long long)h_stat[3];
   }
   return SPMV_B200_OK;
 }
@@ -283,7 +347,7 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
   }
   const long long total = p->nnz;
   const int h_be[2] = {(int)p->elem_base, (int)p->elem_end};
-  const long long nt = std::max<long long>(1, (total + p->T - 1) / p->T);
+  const long long nt = std::max<long long>(1, (total + m + p->T - 1) / p->T);
   if (nt > 0x7ffffff0LL) {
     set_error("too many tiles");
     return SPMV_B200_ERR_ARG;
@@ -313,6 +377,10 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
                                                                p->tile_maxlen, d_hist);
   k_tile_kind<<<grid_for(ntiles, 256, 1 << 30), 256, 0, stream>>>(ntiles, p->short_max, p->medium_max, p->tile_maxlen,
                                                                    p->tile_split, p->tile_kind);
+  B200_CUDA(cudaMalloc(&p->desc_all, sizeof(TileDesc) * (size_t)ntiles));
+  ws += sizeof(TileDesc) * (size_t)ntiles;
+  k_tile_desc<<<grid_for(ntiles, 256, 1 << 30), 256, 0, stream>>>(p->rowptr, ntiles, p->tile_row, p->tile_elem,
+                                                                   p->tile_split, p->desc_all);
   B200_CUDA(cudaGetLastError());
 
   // finalise on the host: compact per-kind tile lists (ascending tile id) and the split-row table
@@ -342,7 +410,13 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
       B200_CUDA(cudaMalloc(&p->list[k], sizeof(int) * lists[k].size()));
       B200_CUDA(cudaMemcpyAsync(p->list[k], lists[k].data(), sizeof(int) * lists[k].size(), cudaMemcpyHostToDevice,
                                 stream));
-      ws += sizeof(int) * lists[k].size();
+      B200_CUDA(cudaMalloc(&p->desc[k], sizeof(TileDesc) * lists[k].size()));
+      k_gather_desc<<<grid_for((long long)lists[k].size(), 256, 1 << 30), 256, 0, stream>>>(
+          p->list[k], (int)lists[k].size(), p->desc_all, p->desc[k]);
+      B200_CUDA(cudaGetLastError());
+      ws += (sizeof(int) + sizeof(TileDesc)) * lists[k].size();
+    } else if (p->count[k] == ntiles) {
+      p->desc[k] = p->desc_all; // one kind owns every tile: no compaction needed
     }
   }
   // split rows: boundary t is the first split boundary of its row iff the row is owned by tile t-1
@@ -355,7 +429,7 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
     if (h_row[t - 1] <= r) { // row r starts in tile t-1
       srow.push_back(r);
       st0.push_back(t - 1);
-      long long t1 = ((long long)h_aux[t] - 1 - base) / p->T;
+      long long t1 = ((long long)h_aux[t] - 1 - base + r) / p->T;
       if (t1 > ntiles - 1)
         t1 = ntiles - 1;
       st1.push_back((int)t1);

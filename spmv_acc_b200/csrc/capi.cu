@@ -25,8 +25,8 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
   return SPMV_B200_ERR_CUDA;
 }
 
-// Tile size when the caller does not fix it: one pass of the 256 threads over the rows of a tile. A tile of T nnz
-// holds T/avg rows; the row kernels give each row V = pow2ceil(avg / vec_div) lanes, so T = avg * 256 / V makes every
+// Tile size when the caller does not fix it: one pass of the 256 threads over the rows of a tile. A tile of T items
+// (non-zeros + rows) holds T/(avg+1) rows; the row kernels give each row V = pow2ceil(avg / vec_div) lanes, so T = avg * 256 / V makes every
 // lane group own exactly one row (fewest round trips to memory per CTA). Clamped to [1024, 4096], multiple of 256.
 static bool irregular_gathers(const spmv_b200_plan *p) {
   // more than half a cache line per gathered element (sampled): x gathers do not coalesce across rows
@@ -38,14 +38,16 @@ static int auto_tile(const spmv_b200_plan *p) {
     return 2048;
   // Irregular gathers are bound by the number of L1 misses in flight, which scales with the part of the unified
   // L1/shared array left to L1: small tiles keep the shared-memory carve-out at about half of it (ncu: profiles/).
+  // Measured (profiles/): uniform row lengths with random columns (x misses L2) are fastest at 1024; power-law
+  // matrices, whose long rows and hot columns go together, at 2048.
   if (irregular_gathers(p))
-    return 1024;
+    return (4 * p->sample_nnz_long > p->sample_nnz) ? 2048 : 1024;
   const double avg = (double)p->nnz / (double)p->m;
   int want = (int)((avg + p->vec_div - 1) / p->vec_div);
   int V = 1;
   while (V < want && V < 32)
     V <<= 1;
-  const double t = avg * (kThreads / V);
+  const double t = (avg + 1.0) * (kThreads / V); // tiles count non-zeros and rows: avg + 1 items per row
   // rounded down (one more row than lane groups would cost a second pass), with 5% slack so that an average just
   // below a whole number of nnz per row (matrix boundary effects, e.g. 4.999 for the 5-point stencil) still counts
   int T = (int)(t / 256.0 + 0.05) * 256;
@@ -57,8 +59,12 @@ static int auto_tile(const spmv_b200_plan *p) {
 }
 
 static int free_plan_arrays(spmv_b200_plan *p) {
-  void *ptrs[] = {p->tile_row, p->tile_elem, p->tile_split, p->tile_part, p->tile_maxlen, p->tile_kind,
-                  p->list[0],  p->list[1],   p->list[2],    p->split_rows, p->partials};
+  for (int k = 0; k < 3; ++k)
+    if (p->desc[k] == p->desc_all)
+      p->desc[k] = nullptr; // alias, freed once below
+  void *ptrs[] = {p->tile_row, p->tile_elem, p->tile_split, p->tile_part,  p->tile_maxlen, p->tile_kind, p->list[0],
+                  p->list[1],  p->list[2],   p->split_rows, p->partials,   p->desc_all,    p->desc[0],   p->desc[1],
+                  p->desc[2]};
   int rc = SPMV_B200_OK;
   for (void *q : ptrs)
     if (q && cudaFree(q) != cudaSuccess)

@@ -13,7 +13,8 @@ namespace b200 {
 
 constexpr int kThreads = 256;     // threads per CTA of every streaming kernel
 constexpr int kRowChunk = 512;    // row pointers staged in shared memory per pass (rows per pass = kRowChunk)
-constexpr int kSerialMax = 16;    // MIXED kernel: rows up to this length are reduced by one thread
+constexpr int kSerialMax = 8;     // MIXED kernel: rows up to this length are reduced by one thread
+constexpr int kGroupMax = 96;     // MIXED kernel: rows up to this length are reduced by 8 lanes, longer ones by a warp
 constexpr int kDefaultTile = 0; // 0 = chosen from the average row length (see auto_tile in capi.cu)
 constexpr int kDefaultShort = 8;
 constexpr int kDefaultMedium = 128;
@@ -29,6 +30,17 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
       return ::b200::cuda_fail(_e, #call, __FILE__, __LINE__);                                                         \
   } while (0)
 
+// Everything a CTA needs to know about its tile, packed into 32 bytes so that the prologue of a CTA is a single
+// round trip to memory (two 128-bit loads) before the TMA copies can be issued. Built per tile kind by the analysis.
+struct __align__(16) TileDesc {
+  int r0, r1;     // owned rows [r0, r1)
+  int e0, e1;     // streamed nnz [e0, e1)
+  int head_end;   // split leading boundary: the head fragment is [e0, head_end) (= min(rowptr[r0], e1))
+  int tail_start; // split trailing boundary: the tail fragment is [tail_start, e1) (= rowptr[r1-1])
+  int tile;       // global tile id (index of its partial sums)
+  int flags;      // bit 0: leading boundary split, bit 1: trailing boundary split
+};
+
 // Arguments of the streaming kernels (passed by value).
 struct SpmvArgs {
   const int *__restrict__ rowptr;
@@ -37,12 +49,10 @@ struct SpmvArgs {
   const double *__restrict__ x;
   double *__restrict__ y;
   double alpha, beta;
-  const int *__restrict__ tile_row;             // [ntiles+1]
-  const int *__restrict__ tile_elem;            // [ntiles+1]
-  const unsigned char *__restrict__ tile_split; // [ntiles+1]
-  const int *__restrict__ list;                 // tiles of this kind, or nullptr when every tile has this kind
+  const TileDesc *__restrict__ desc;            // descriptors of the tiles of this kind, in ascending tile order
   double *__restrict__ partials;                // [2*ntiles]: head fragment, tail fragment of each tile
   long long nnz; // absolute index one past the last element of the matrix (bounds the TMA size)
+  int ntiles;   // tiles of this kind (persistent kernels walk [0, ntiles) with stride gridDim.x)
   int cap;      // element capacity of the shared-memory tile
   int vec_div;  // MEDIUM: lanes per row = pow2ceil(avg / vec_div)
   int read_y;   // 0: beta == 0 and SPMV_B200_FLAG_BETA0_SKIP_Y
@@ -66,6 +76,7 @@ struct spmv_b200_plan {
   int m = 0, n = 0;
   long long nnz = 0;      // rowptr[m] - rowptr[0]
   long long gather_active = 0, gather_lines = 0; // sampled gather-coalescing statistic (analysis.cu)
+  long long sample_nnz = 0, sample_nnz_long = 0;  // non-zeros of the sampled rows / of those longer than medium_max
   long long elem_base = 0; // rowptr[0]
   long long elem_end = 0; // rowptr[m]
   const int *rowptr = nullptr;
@@ -79,6 +90,7 @@ struct spmv_b200_plan {
   int cap = 0;
   size_t smem_bytes = 0;
   size_t persist_bytes = 0, max_window_bytes = 0; // L2 persistence for x (SPMV_B200_FLAG_L2_PERSIST_X)
+  int persistent_grid[3] = {0, 0, 0}; // CTAs of the persistent kernels per tile kind
   int variant_short = 0, variant_medium = 0; // kernel variants (option flag bits 8-11 / 12-15)
   // device arrays owned by the plan
   int *tile_row = nullptr;
@@ -88,6 +100,8 @@ struct spmv_b200_plan {
   int *tile_maxlen = nullptr;
   unsigned char *tile_kind = nullptr;
   int *list[3] = {nullptr, nullptr, nullptr};
+  b200::TileDesc *desc_all = nullptr;                       // [ntiles] descriptors in tile order
+  b200::TileDesc *desc[3] = {nullptr, nullptr, nullptr};    // per kind (aliases desc_all when one kind owns all tiles)
   int count[3] = {0, 0, 0};
   int nsplit = 0;
   int *split_rows = nullptr; // [3*nsplit]: row, t0, t1 (struct of arrays: rows | t0 | t1)

@@ -86,9 +86,27 @@ __device__ __forceinline__ int ld_stream_s32(const int *p) {
 
 // x gather through the read-only path; `na` selects L1::no_allocate (the line is not kept in L1)
 __device__ __forceinline__ double gather_x(const double *__restrict__ x, int c, int na) {
+  if (na == 2) // experiment: no gather at all (wrong results; isolates the cost of the x traffic)
+    return 1.0;
   if (na)
     return ld_stream_f64(x + c);
   return __ldg(x + c);
+}
+
+// one round trip: the 32-byte descriptor of tile i of this kind as two 128-bit loads
+__device__ __forceinline__ TileDesc load_desc(const TileDesc *__restrict__ desc, int i) {
+  const int4 *p = reinterpret_cast<const int4 *>(desc + i);
+  const int4 lo = __ldg(p), hi = __ldg(p + 1);
+  TileDesc d;
+  d.r0 = lo.x;
+  d.r1 = lo.y;
+  d.e0 = lo.z;
+  d.e1 = lo.w;
+  d.head_end = hi.x;
+  d.tail_start = hi.y;
+  d.tile = hi.z;
+  d.flags = hi.w;
+  return d;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -130,6 +148,30 @@ __device__ __forceinline__ void tile_issue_loads(const SpmvArgs &a, int a0, int 
   }
 }
 
+// TMA part of tile_issue_loads for an already initialised barrier (persistent kernels)
+__device__ __forceinline__ void tile_issue_tma(const SpmvArgs &a, int a0, int e1, double *sval, int *scol,
+                                               unsigned long long *bar, int tid) {
+  const int span = e1 - a0;
+  const long long avail = a.nnz - (long long)a0;
+  int cnt = (span + 3) & ~3;
+  if ((long long)cnt > avail)
+    cnt = (int)(avail & ~3LL);
+  if (tid == 0) {
+    if (cnt > 0) {
+      const unsigned long long pol = policy_evict_first();
+      mbar_arrive_expect_tx(bar, (uint32_t)cnt * 12u);
+      tma_bulk_g2s(sval, a.val + a0, (uint32_t)cnt * 8u, bar, pol);
+      tma_bulk_g2s(scol, a.col + a0, (uint32_t)cnt * 4u, bar, pol);
+    } else {
+      mbar_arrive(bar);
+    }
+  }
+  for (int i = cnt + tid; i < span; i += kThreads) {
+    sval[i] = ld_stream_f64(a.val + a0 + i);
+    scol[i] = ld_stream_s32(a.col + a0 + i);
+  }
+}
+
 __device__ __forceinline__ void store_y(const SpmvArgs &a, int row, double sum) {
   // cli/verification.cpp:64  y[i] = alpha * y0 + beta * y[i]
   const double yv = a.read_y ? a.y[row] : 0.0;
@@ -142,23 +184,12 @@ __device__ __forceinline__ void store_y(const SpmvArgs &a, int row, double sum) 
 // W = x gathers issued back to back per row and round, R = rows handled by one lane group at a time. All W*R gathers
 // of a round are in flight before the first FMA, and y is fetched before the tile has landed, so that a CTA exposes
 // one round trip to memory per phase (tile, gathers) instead of one per batch of four elements.
+// Rows of one tile whose value / colindex are (being) staged in sval / scol; waits for the TMA phase `parity` of `bar`.
 template <bool TMA, bool VEC, int W, int R>
-__global__ void __launch_bounds__(kThreads) k_spmv_rows(const SpmvArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long bar;
-  double *sval = reinterpret_cast<double *>(smem_raw);
-  int *scol = reinterpret_cast<int *>(sval + a.cap);
-  int *srow = scol + a.cap;
-
-  const int tid = threadIdx.x;
-  const int t = a.list ? a.list[blockIdx.x] : (int)blockIdx.x;
-  const int r0 = a.tile_row[t], r1 = a.tile_row[t + 1];
-  const int e0 = a.tile_elem[t], e1 = a.tile_elem[t + 1];
-  const int a0 = e0 & ~3;
-  const int nrows = r1 - r0;
-
-  tile_issue_loads<TMA>(a, a0, e0, e1, sval, scol, &bar, tid);
-
+__device__ __forceinline__ void rows_tile(const SpmvArgs &a, const double *__restrict__ sval,
+                                          const int *__restrict__ scol, int *__restrict__ srow,
+                                          unsigned long long *bar, uint32_t parity, int r0, int nrows, int a0, int e0,
+                                          int e1, int tid) {
   int lv = 0; // log2(lanes per row)
   if (VEC) {
     const int avg = (e1 - e0) / (nrows > 0 ? nrows : 1);
@@ -189,7 +220,7 @@ __global__ void __launch_bounds__(kThreads) k_spmv_rows(const SpmvArgs a) {
       srow[i] = __ldg(a.rowptr + r0 + cb + i);
     __syncthreads();
     if (TMA && cb == 0)
-      mbar_wait(&bar, 0);
+      mbar_wait(bar, parity);
 
     for (int rb = 0; rb < nr; rb += R * G) {
       int k[R], e[R];
@@ -250,6 +281,72 @@ __global__ void __launch_bounds__(kThreads) k_spmv_rows(const SpmvArgs a) {
   }
 }
 
+template <bool TMA, bool VEC, int W, int R>
+__global__ void __launch_bounds__(kThreads) k_spmv_rows(const SpmvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bar;
+  double *sval = reinterpret_cast<double *>(smem_raw);
+  int *scol = reinterpret_cast<int *>(sval + a.cap);
+  int *srow = scol + a.cap;
+
+  const int tid = threadIdx.x;
+  const TileDesc d = load_desc(a.desc, blockIdx.x);
+  const int r0 = d.r0, r1 = d.r1, e0 = d.e0, e1 = d.e1;
+  const int a0 = e0 & ~3;
+
+  tile_issue_loads<TMA>(a, a0, e0, e1, sval, scol, &bar, tid);
+  rows_tile<TMA, VEC, W, R>(a, sval, scol, srow, &bar, 0u, r0, r1 - r0, a0, e0, e1, tid);
+}
+
+// Persistent form: gridDim.x CTAs walk the tile list with a two-stage ring of shared-memory tiles. The TMA copies
+// of tile i+1 are issued before tile i is processed, so the stream of value / colindex keeps flowing while the CTA
+// gathers x (the gather phase is bound by L1 wavefronts, the stream by HBM: the two overlap instead of alternating).
+template <bool VEC, int W, int R>
+__global__ void __launch_bounds__(kThreads) k_spmv_rows_persistent(const SpmvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bar[2];
+  double *sval0 = reinterpret_cast<double *>(smem_raw);
+  int *scol0 = reinterpret_cast<int *>(sval0 + a.cap);
+  double *sval1 = reinterpret_cast<double *>(scol0 + a.cap);
+  int *scol1 = reinterpret_cast<int *>(sval1 + a.cap);
+  int *srow = scol1 + a.cap;
+
+  const int tid = threadIdx.x;
+  int i = blockIdx.x;
+  if (i >= a.ntiles)
+    return;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+  }
+  __syncthreads();
+
+  TileDesc d = load_desc(a.desc, i);
+  int r0 = d.r0, r1 = d.r1, e0 = d.e0, e1 = d.e1;
+  tile_issue_tma(a, e0 & ~3, e1, sval0, scol0, &bar[0], tid);
+
+  for (int it = 0; i < a.ntiles; i += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const int inext = i + (int)gridDim.x;
+    int r0n = 0, r1n = 0, e0n = 0, e1n = 0;
+    if (inext < a.ntiles) { // refill the other stage: every thread left it at the barrier that ended the last iteration
+      d = load_desc(a.desc, inext);
+      r0n = d.r0;
+      r1n = d.r1;
+      e0n = d.e0;
+      e1n = d.e1;
+      tile_issue_tma(a, e0n & ~3, e1n, stage ? sval0 : sval1, stage ? scol0 : scol1, &bar[stage ^ 1], tid);
+    }
+    rows_tile<true, VEC, W, R>(a, stage ? sval1 : sval0, stage ? scol1 : scol0, srow, &bar[stage],
+                               (uint32_t)((it >> 1) & 1), r0, r1 - r0, e0 & ~3, e0, e1, tid);
+    __syncthreads(); // the stage and srow may be overwritten from here on
+    r0 = r0n;
+    r1 = r1n;
+    e0 = e0n;
+    e1 = e1n;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // MIXED tiles
 // ---------------------------------------------------------------------------------------------------------------
@@ -279,26 +376,27 @@ __global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
   __shared__ double swarp[kThreads / 32];
-  __shared__ int nlong;
+  __shared__ int nlong, nmid;
   double *sval = reinterpret_cast<double *>(smem_raw);
   int *scol = reinterpret_cast<int *>(sval + a.cap);
   int *srow = scol + a.cap;
-  int *slong = srow + (kRowChunk + 1); // rows longer than kSerialMax in the current chunk
+  const int qcap = a.cap / (kSerialMax + 1) + 8;
+  int *smid = srow + (kRowChunk + 1); // rows of kSerialMax+1 .. kGroupMax products in the current chunk
+  int *slong = smid + qcap;           // longer rows
 
   const int tid = threadIdx.x;
-  const int t = a.list ? a.list[blockIdx.x] : (int)blockIdx.x;
-  const int r0 = a.tile_row[t], r1 = a.tile_row[t + 1];
-  const int e0 = a.tile_elem[t], e1 = a.tile_elem[t + 1];
+  const TileDesc d = load_desc(a.desc, blockIdx.x);
+  const int t = d.tile;
+  const int r0 = d.r0, r1 = d.r1, e0 = d.e0, e1 = d.e1;
   const int a0 = e0 & ~3;
-  const bool split_begin = a.tile_split[t] != 0;
-  const bool split_end = a.tile_split[t + 1] != 0;
+  const bool split_begin = (d.flags & 1) != 0;
+  const bool split_end = (d.flags & 2) != 0;
   // the last owned row continues in the next tile: its part in this tile is the tail fragment
   const bool has_tail = split_end && (r1 > r0);
   const int nrows = (r1 - r0) - (has_tail ? 1 : 0);
 
   tile_issue_loads<TMA>(a, a0, e0, e1, sval, scol, &bar, tid);
-  const int first_row_start = __ldg(a.rowptr + r0);                   // r0 <= m
-  const int tail_start = has_tail ? __ldg(a.rowptr + r1 - 1) : e1;    // first element of the tail fragment
+  const int tail_start = d.tail_start; // first element of the tail fragment
   __syncthreads();
   if (TMA)
     mbar_wait(&bar, 0);
@@ -334,8 +432,7 @@ __global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
   __syncthreads();
 
   if (split_begin) { // leading elements belong to a row that started in an earlier tile
-    const int hend = first_row_start < e1 ? first_row_start : e1;
-    const double s = block_sum(sval, e0 - a0, hend - a0, swarp, tid);
+    const double s = block_sum(sval, e0 - a0, d.head_end - a0, swarp, tid);
     if (tid == 0)
       a.partials[2 * (size_t)t] = s;
   }
@@ -346,34 +443,60 @@ __global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
   }
 
   const int warp = tid >> 5, lane = tid & 31;
+  const int grp = tid >> 3, gl = tid & 7; // 8-lane groups for rows of medium length
   for (int cb = 0; cb < nrows; cb += kRowChunk) {
     int nr = nrows - cb;
     if (nr > kRowChunk)
       nr = kRowChunk;
-    __syncthreads(); // srow / slong / nlong reuse
+    __syncthreads(); // srow / queues reuse
     for (int i = tid; i <= nr; i += kThreads)
       srow[i] = __ldg(a.rowptr + r0 + cb + i);
-    if (tid == 0)
+    if (tid == 0) {
+      nmid = 0;
       nlong = 0;
+    }
     __syncthreads();
-    // pass 1: one thread per row; long rows are queued
+    // pass 1: one thread per row sums rows of <= kSerialMax products; longer rows are queued by length class
+    // (the value of a row does not depend on its queue position, only on its own fixed summation order)
     for (int r = tid; r < nr; r += kThreads) {
       const int s = srow[r] - a0, e = srow[r + 1] - a0;
-      if (e - s <= kSerialMax) {
+      const int len = e - s;
+      if (len <= kSerialMax) {
+        const double yv = a.read_y ? a.y[r0 + cb + r] : 0.0; // requested before the sum is formed
         double sum = 0.0;
         for (int k = s; k < e; ++k)
           sum += sval[k];
-        store_y(a, r0 + cb + r, sum);
+        a.y[r0 + cb + r] = a.alpha * sum + a.beta * yv;
+      } else if (len <= kGroupMax) {
+        smid[atomicAdd(&nmid, 1)] = r;
       } else {
         slong[atomicAdd(&nlong, 1)] = r;
       }
     }
     __syncthreads();
-    // pass 2: one warp per queued row (the value of a row does not depend on its queue position)
+    // pass 2a: eight lanes per queued row of medium length
+    const int nm = nmid;
+    for (int ib = 0; ib < nm; ib += kThreads / 8) {
+      const int i = ib + grp;
+      const bool act = i < nm;
+      const int r = act ? smid[i] : 0;
+      const int s = srow[r] - a0, e = act ? srow[r + 1] - a0 : s;
+      const double yv = (act && gl == 0 && a.read_y) ? a.y[r0 + cb + r] : 0.0;
+      double sum = 0.0;
+      for (int k = s + gl; k < e; k += 8)
+        sum += sval[k];
+      sum += __shfl_down_sync(0xffffffffu, sum, 4, 8);
+      sum += __shfl_down_sync(0xffffffffu, sum, 2, 8);
+      sum += __shfl_down_sync(0xffffffffu, sum, 1, 8);
+      if (act && gl == 0)
+        a.y[r0 + cb + r] = a.alpha * sum + a.beta * yv;
+    }
+    // pass 2b: one warp per queued long row
     const int nl = nlong;
     for (int i = warp; i < nl; i += kThreads / 32) {
       const int r = slong[i];
       const int s = srow[r] - a0, e = srow[r + 1] - a0;
+      const double yv = (lane == 0 && a.read_y) ? a.y[r0 + cb + r] : 0.0;
       double sum = 0.0;
       for (int k = s + lane; k < e; k += 32)
         sum += sval[k];
@@ -381,7 +504,7 @@ __global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
       for (int off = 16; off > 0; off >>= 1)
         sum += __shfl_xor_sync(0xffffffffu, sum, off);
       if (lane == 0)
-        store_y(a, r0 + cb + r, sum);
+        a.y[r0 + cb + r] = a.alpha * sum + a.beta * yv;
     }
   }
 }
@@ -417,32 +540,32 @@ static int cap_for(const spmv_b200_plan *p, int kind) {
   return p->T + (kind == SPMV_B200_KIND_SHORT ? ((p->short_max + 3) & ~3) : p->medium_max) + 8;
 }
 
-static size_t smem_for(const spmv_b200_plan *p, int kind) {
+static size_t smem_for(const spmv_b200_plan *p, int kind, bool persistent = false) {
   const int cap = cap_for(p, kind);
-  size_t b = (size_t)cap * 12 + sizeof(int) * (kRowChunk + 1);
+  size_t b = (size_t)cap * 12 * (persistent ? 2 : 1) + sizeof(int) * (kRowChunk + 1);
   if (kind == SPMV_B200_KIND_MIXED)
-    b += sizeof(int) * ((size_t)cap / (kSerialMax + 1) + 8);
+    b += 2 * sizeof(int) * ((size_t)cap / (kSerialMax + 1) + 8);
   return (b + 15) & ~(size_t)15;
 }
 
 typedef void (*RowsKernel)(const SpmvArgs);
 struct RowsVariant {
-  RowsKernel tma, plain;
+  RowsKernel tma, plain, persistent;
   const char *name;
 };
 // variant tables (index = option bits, 0 = default); every entry is a separate instantiation of k_spmv_rows
 static const RowsVariant kShortVariants[] = {
-    {k_spmv_rows<true, false, 6, 1>, k_spmv_rows<false, false, 6, 1>, "W6R1"},
-    {k_spmv_rows<true, false, 8, 1>, k_spmv_rows<false, false, 8, 1>, "W8R1"},
-    {k_spmv_rows<true, false, 4, 1>, k_spmv_rows<false, false, 4, 1>, "W4R1"},
-    {k_spmv_rows<true, false, 4, 2>, k_spmv_rows<false, false, 4, 2>, "W4R2"},
-    {k_spmv_rows<true, false, 8, 2>, k_spmv_rows<false, false, 8, 2>, "W8R2"},
+    {k_spmv_rows<true, false, 6, 1>, k_spmv_rows<false, false, 6, 1>, k_spmv_rows_persistent<false, 6, 1>, "W6R1"},
+    {k_spmv_rows<true, false, 8, 1>, k_spmv_rows<false, false, 8, 1>, k_spmv_rows_persistent<false, 8, 1>, "W8R1"},
+    {k_spmv_rows<true, false, 4, 1>, k_spmv_rows<false, false, 4, 1>, k_spmv_rows_persistent<false, 4, 1>, "W4R1"},
+    {k_spmv_rows<true, false, 4, 2>, k_spmv_rows<false, false, 4, 2>, k_spmv_rows_persistent<false, 4, 2>, "W4R2"},
+    {k_spmv_rows<true, false, 8, 2>, k_spmv_rows<false, false, 8, 2>, k_spmv_rows_persistent<false, 8, 2>, "W8R2"},
 };
 static const RowsVariant kMediumVariants[] = {
-    {k_spmv_rows<true, true, 8, 1>, k_spmv_rows<false, true, 8, 1>, "W8R1"},
-    {k_spmv_rows<true, true, 4, 1>, k_spmv_rows<false, true, 4, 1>, "W4R1"},
-    {k_spmv_rows<true, true, 4, 2>, k_spmv_rows<false, true, 4, 2>, "W4R2"},
-    {k_spmv_rows<true, true, 8, 2>, k_spmv_rows<false, true, 8, 2>, "W8R2"},
+    {k_spmv_rows<true, true, 8, 1>, k_spmv_rows<false, true, 8, 1>, k_spmv_rows_persistent<true, 8, 1>, "W8R1"},
+    {k_spmv_rows<true, true, 4, 1>, k_spmv_rows<false, true, 4, 1>, k_spmv_rows_persistent<true, 4, 1>, "W4R1"},
+    {k_spmv_rows<true, true, 4, 2>, k_spmv_rows<false, true, 4, 2>, k_spmv_rows_persistent<true, 4, 2>, "W4R2"},
+    {k_spmv_rows<true, true, 8, 2>, k_spmv_rows<false, true, 8, 2>, k_spmv_rows_persistent<true, 8, 2>, "W8R2"},
 };
 constexpr int kNumShortVariants = sizeof(kShortVariants) / sizeof(kShortVariants[0]);
 constexpr int kNumMediumVariants = sizeof(kMediumVariants) / sizeof(kMediumVariants[0]);
@@ -488,11 +611,30 @@ int kernels_configure(spmv_b200_plan *p) {
   const RowsVariant &vs = kShortVariants[p->variant_short], &vm = kMediumVariants[p->variant_medium];
   if ((rc = set_smem(vs.tma, smem_for(p, SPMV_B200_KIND_SHORT))) ||
       (rc = set_smem(vs.plain, smem_for(p, SPMV_B200_KIND_SHORT))) ||
+      (rc = set_smem(vs.persistent, smem_for(p, SPMV_B200_KIND_SHORT, true))) ||
+      (rc = set_smem(vm.persistent, smem_for(p, SPMV_B200_KIND_MEDIUM, true))) ||
       (rc = set_smem(vm.tma, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
       (rc = set_smem(vm.plain, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
       (rc = set_smem(k_spmv_mixed<true>, smem_for(p, SPMV_B200_KIND_MIXED))) ||
       (rc = set_smem(k_spmv_mixed<false>, smem_for(p, SPMV_B200_KIND_MIXED))))
     return rc;
+  // persistent kernels: one wave of CTAs, as many as fit on the device
+  int sms = 0;
+  B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int occ_s = 0, occ_m = 0;
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, vs.persistent, kThreads,
+                                                          smem_for(p, SPMV_B200_KIND_SHORT, true)));
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_m, vm.persistent, kThreads,
+                                                          smem_for(p, SPMV_B200_KIND_MEDIUM, true)));
+  p->persistent_grid[SPMV_B200_KIND_SHORT] = sms * (occ_s > 0 ? occ_s : 1);
+  p->persistent_grid[SPMV_B200_KIND_MEDIUM] = sms * (occ_m > 0 ? occ_m : 1);
+  if (const char *env = getenv("SPMV_B200_PERSIST_CTAS")) { // development knob: CTAs per SM of the persistent kernels
+    const int c = atoi(env);
+    if (c > 0) {
+      p->persistent_grid[SPMV_B200_KIND_SHORT] = sms * (c < occ_s ? c : occ_s);
+      p->persistent_grid[SPMV_B200_KIND_MEDIUM] = sms * (c < occ_m ? c : occ_m);
+    }
+  }
   return SPMV_B200_OK;
 }
 
@@ -537,34 +679,47 @@ int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const dou
   a.y = y;
   a.alpha = alpha;
   a.beta = beta;
-  a.tile_row = p->tile_row;
-  a.tile_elem = p->tile_elem;
-  a.tile_split = p->tile_split;
-  a.list = nullptr;
+  a.desc = nullptr;
   a.partials = p->partials;
   a.nnz = p->elem_end; // absolute index one past the last element (rowptr may be a view: rowptr[0] != 0)
   a.vec_div = p->vec_div;
-  a.gather_na = (p->flags & SPMV_B200_FLAG_GATHER_NO_L1) ? 1 : 0;
+  a.gather_na = (p->flags & (1u << 16)) ? 2 : ((p->flags & SPMV_B200_FLAG_GATHER_NO_L1) ? 1 : 0);
   a.read_y = (beta == 0.0 && (p->flags & SPMV_B200_FLAG_BETA0_SKIP_Y)) ? 0 : 1;
 
   const bool tma = p->uses_tma;
+  const bool persistent = (p->flags & SPMV_B200_FLAG_PERSISTENT) != 0;
+  a.ntiles = 0;
   if (p->count[SPMV_B200_KIND_SHORT] > 0) {
     const RowsVariant &v = kShortVariants[p->variant_short];
-    a.list = p->list[SPMV_B200_KIND_SHORT];
+    a.desc = p->desc[SPMV_B200_KIND_SHORT];
     a.cap = cap_for(p, SPMV_B200_KIND_SHORT);
-    B200_CUDA(launch_spmv(tma ? v.tma : v.plain, p->count[SPMV_B200_KIND_SHORT], smem_for(p, SPMV_B200_KIND_SHORT),
-                          stream, a, p));
+    a.ntiles = p->count[SPMV_B200_KIND_SHORT];
+    if (tma && persistent) {
+      const int grid = a.ntiles < p->persistent_grid[SPMV_B200_KIND_SHORT] ? a.ntiles
+                                                                           : p->persistent_grid[SPMV_B200_KIND_SHORT];
+      B200_CUDA(launch_spmv(v.persistent, grid, smem_for(p, SPMV_B200_KIND_SHORT, true), stream, a, p));
+    } else {
+      B200_CUDA(launch_spmv(tma ? v.tma : v.plain, a.ntiles, smem_for(p, SPMV_B200_KIND_SHORT), stream, a, p));
+    }
   }
   if (p->count[SPMV_B200_KIND_MEDIUM] > 0) {
     const RowsVariant &v = kMediumVariants[p->variant_medium];
-    a.list = p->list[SPMV_B200_KIND_MEDIUM];
+    a.desc = p->desc[SPMV_B200_KIND_MEDIUM];
     a.cap = cap_for(p, SPMV_B200_KIND_MEDIUM);
-    B200_CUDA(launch_spmv(tma ? v.tma : v.plain, p->count[SPMV_B200_KIND_MEDIUM], smem_for(p, SPMV_B200_KIND_MEDIUM),
-                          stream, a, p));
+    a.ntiles = p->count[SPMV_B200_KIND_MEDIUM];
+    if (tma && persistent) {
+      const int grid = a.ntiles < p->persistent_grid[SPMV_B200_KIND_MEDIUM]
+                           ? a.ntiles
+                           : p->persistent_grid[SPMV_B200_KIND_MEDIUM];
+      B200_CUDA(launch_spmv(v.persistent, grid, smem_for(p, SPMV_B200_KIND_MEDIUM, true), stream, a, p));
+    } else {
+      B200_CUDA(launch_spmv(tma ? v.tma : v.plain, a.ntiles, smem_for(p, SPMV_B200_KIND_MEDIUM), stream, a, p));
+    }
   }
   if (p->count[SPMV_B200_KIND_MIXED] > 0) {
-    a.list = p->list[SPMV_B200_KIND_MIXED];
+    a.desc = p->desc[SPMV_B200_KIND_MIXED];
     a.cap = cap_for(p, SPMV_B200_KIND_MIXED);
+    a.ntiles = p->count[SPMV_B200_KIND_MIXED];
     const size_t sm = smem_for(p, SPMV_B200_KIND_MIXED);
     B200_CUDA(launch_spmv(tma ? k_spmv_mixed<true> : k_spmv_mixed<false>, p->count[SPMV_B200_KIND_MIXED], sm, stream,
                           a, p));

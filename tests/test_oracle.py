@@ -92,13 +92,12 @@ def test_analysis_port_invariants_and_tiled_sum(T, S, L):
         x, y0 = rng.standard_normal(n), rng.standard_normal(m)
         ana = oracle.port_analysis(rp, T, S, L)
         nt = ana["ntiles"]
-        assert nt == max(1, -(-nnz // T))
+        assert nt == max(1, -(-(nnz + m) // T))                       # tiles balance nnz + rows
         tr, te = ana["tile_row"], ana["tile_elem"]
         assert tr[0] == 0 and tr[-1] == m and te[0] == 0 and te[-1] == nnz
         assert np.all(np.diff(tr) >= 0) and np.all(np.diff(te) >= 0)
         assert np.all(np.diff(te) <= T + L - 1)                       # nnz balance: the shared-memory tile bound
-        assert np.array_equal(ana["tile_part"], oracle.port_merge_path_partition(rp, nt + 1, T).clip(max=m)
-                              if nnz == nt * T else ana["tile_part"])
+        assert np.all(np.diff(tr) <= T)                               # row balance, however many rows are empty
         assert ana["bin_rows"].sum() == m and ana["bin_nnz"].sum() == nnz
         # every row is summed exactly once and the result matches the serial oracle within the fp64 bound
         yt = oracle.port_tiled_spmv(1.5, 0.25, rp, col, val, x, y0, ana, T, L)

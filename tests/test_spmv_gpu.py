@@ -20,6 +20,8 @@ OPTS = {
     "no_tma": make_options(flags=FLAG_NO_TMA),
     "small_tiles": make_options(256, 4, 16, 2),
     "big_tiles": make_options(8192, 16, 256, 16),
+    "persistent": make_options(flags=0x20000),
+    "persistent_small": make_options(256, 4, 16, 2, flags=0x20000),
 }
 
 
