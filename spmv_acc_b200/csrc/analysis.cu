@@ -24,7 +24,8 @@
 //   tile_part[t]  = max{ r in [0,m] : rowptr[r] <= min(base + t*T, end) }   (the reference's merge-path partition S[t],
 //                   benchmark/merge-path/merge_path_partition.h:7-17; exported for the cross-check only)
 //   row r is owned by tile min(floor(f(r)/T), ntiles-1); tile_maxlen[t] = max nnz of the rows it owns.
-//   tile_kind[t]  = MIXED if tile_split[t] or tile_split[t+1] or tile_maxlen[t] > L;
+//   tile_kind[t]  = MIXED if tile_split[t] or tile_split[t+1] or tile_maxlen[t] > L or the tile owns more than 512 rows
+//                   or (tile_maxlen[t] > S and tile_maxlen[t] * rows_t > 4 * nnz_t);
 //                   SHORT if tile_maxlen[t] <= S; else MEDIUM.
 //   bin(r) = SHORT if nnz_r <= S; MEDIUM if nnz_r <= L; LONG if nnz_r <= T; else VERYLONG.
 //   split row r (first split boundary t, i.e. tile_row[t-1] <= r = tile_row[t]-1): fragments live in tiles
@@ -169,13 +170,21 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     k_tile_kind(int ntiles, int short_max, int medium_max, const int *__restrict__ tile_maxlen,
-                const unsigned char *__restrict__ tile_split, unsigned char *__restrict__ tile_kind) {
+                const unsigned char *__restrict__ tile_split, const int *__restrict__ tile_row,
+                const int *__restrict__ tile_elem, unsigned char *__restrict__ tile_kind) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntiles)
     return;
   const int ml = tile_maxlen[t];
   unsigned char k;
-  if (tile_split[t] || tile_split[t + 1] || ml > medium_max)
+  // tiles with more than two passes' worth of rows (mostly empty / one-element rows) also go to the MIXED kernel,
+  // whose cost grows with the non-zeros and not with the number of rows
+  // ... and so do tiles whose longest row is more than four times the tile's average row (a lane group that owns
+  // such a row would keep the whole CTA waiting)
+  const long long rows = tile_row[t + 1] - tile_row[t];
+  const long long elems = tile_elem[t + 1] - tile_elem[t];
+  const bool skewed = ml > short_max && (long long)ml * rows > 4 * elems;
+  if (tile_split[t] || tile_split[t + 1] || ml > medium_max || rows > kSparseTileRows || skewed)
     k = SPMV_B200_KIND_MIXED;
   else if (ml <= short_max)
     k = SPMV_B200_KIND_SHORT;
@@ -376,7 +385,8 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
   k_row_stats<<<grid_for(m, 256, 148 * 16), 256, 0, stream>>>(p->rowptr, m, ntiles, p->T, p->short_max, p->medium_max,
                                                                p->tile_maxlen, d_hist);
   k_tile_kind<<<grid_for(ntiles, 256, 1 << 30), 256, 0, stream>>>(ntiles, p->short_max, p->medium_max, p->tile_maxlen,
-                                                                   p->tile_split, p->tile_kind);
+                                                                   p->tile_split, p->tile_row, p->tile_elem,
+                                                                   p->tile_kind);
   B200_CUDA(cudaMalloc(&p->desc_all, sizeof(TileDesc) * (size_t)ntiles));
   ws += sizeof(TileDesc) * (size_t)ntiles;
   k_tile_desc<<<grid_for(ntiles, 256, 1 << 30), 256, 0, stream>>>(p->rowptr, ntiles, p->tile_row, p->tile_elem,
@@ -403,7 +413,9 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
   std::vector<int> lists[3];
   for (int t = 0; t < ntiles; ++t)
     lists[h_kind[t]].push_back(t);
+  p->h_tile_row = h_row;
   for (int k = 0; k < 3; ++k) {
+    p->h_list[k] = lists[k];
     p->count[k] = (int)lists[k].size();
     // when every tile has the same kind the kernel indexes tiles by blockIdx directly (no list)
     if (p->count[k] > 0 && p->count[k] < ntiles) {

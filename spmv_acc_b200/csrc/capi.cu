@@ -4,6 +4,7 @@
 // (src/acc/hip-csr-adaptive-plus/csr_adaptive_plus_spmv.cpp:16-73); the stateless entry points mirror
 // sparse_csr_spmv (src/acc/api/spmv.h:20-21) and the deprecated sparse_spmv (src/acc/api/spmv_imp.cpp:10-18).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <list>
 #include <mutex>
@@ -376,8 +377,18 @@ struct spmv_b200_hostmat {
   double *d_x = nullptr;
   double *d_y = nullptr;
   spmv_b200_plan *plan = nullptr;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;                 // compute (and the non-pipelined path)
+  cudaStream_t s_in = nullptr, s_out = nullptr;  // host->device and device->host copy streams (pipelined path)
+  cudaEvent_t ev_x = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_done;       // per chunk: y0 chunk arrived / chunk computed
 };
+
+constexpr int kHostChunksMax = 64;
+static int host_chunks() { // row chunks of the pipelined host-buffer path (SPMV_B200_HOST_CHUNKS overrides)
+  const char *e = getenv("SPMV_B200_HOST_CHUNKS");
+  const int c = e ? atoi(e) : 8;
+  return c < 1 ? 1 : (c > kHostChunksMax ? kHostChunksMax : c);
+}
 
 int spmv_b200_hostmat_destroy(spmv_b200_hostmat *hm) {
   if (!hm)
@@ -390,8 +401,15 @@ int spmv_b200_hostmat_destroy(spmv_b200_hostmat *hm) {
   cudaFree(hm->d_val);
   cudaFree(hm->d_x);
   cudaFree(hm->d_y);
-  if (hm->stream)
-    cudaStreamDestroy(hm->stream);
+  for (cudaEvent_t e : hm->ev_in)
+    cudaEventDestroy(e);
+  for (cudaEvent_t e : hm->ev_done)
+    cudaEventDestroy(e);
+  if (hm->ev_x)
+    cudaEventDestroy(hm->ev_x);
+  for (cudaStream_t st : {hm->stream, hm->s_in, hm->s_out})
+    if (st)
+      cudaStreamDestroy(st);
   delete hm;
   return SPMV_B200_OK;
 }
@@ -400,6 +418,15 @@ static int hostmat_build(spmv_b200_hostmat *hm, const int32_t *h_rowptr, const i
                          const spmv_b200_options *opt) {
   const size_t m = (size_t)hm->m, n = (size_t)hm->n, nnz = (size_t)hm->nnz;
   B200_CUDA(cudaStreamCreateWithFlags(&hm->stream, cudaStreamNonBlocking));
+  B200_CUDA(cudaStreamCreateWithFlags(&hm->s_in, cudaStreamNonBlocking));
+  B200_CUDA(cudaStreamCreateWithFlags(&hm->s_out, cudaStreamNonBlocking));
+  B200_CUDA(cudaEventCreateWithFlags(&hm->ev_x, cudaEventDisableTiming));
+  hm->ev_in.resize(kHostChunksMax);
+  hm->ev_done.resize(kHostChunksMax);
+  for (int c = 0; c < kHostChunksMax; ++c) {
+    B200_CUDA(cudaEventCreateWithFlags(&hm->ev_in[c], cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&hm->ev_done[c], cudaEventDisableTiming));
+  }
   B200_CUDA(cudaMalloc(&hm->d_rowptr, sizeof(int) * (m + 1)));
   B200_CUDA(cudaMalloc(&hm->d_col, sizeof(int) * (nnz ? nnz : 1)));
   B200_CUDA(cudaMalloc(&hm->d_val, sizeof(double) * (nnz ? nnz : 1)));
@@ -443,6 +470,38 @@ int spmv_b200_hostmat_spmv(spmv_b200_hostmat *hm, double alpha, double beta, con
   if (!hm || (hm->n > 0 && !h_x) || (hm->m > 0 && !h_y)) {
     set_error("hostmat_spmv: invalid argument");
     return SPMV_B200_ERR_ARG;
+  }
+  const spmv_b200_plan *p = hm->plan;
+  // Pipelined path (no split rows, enough tiles): x goes up first; then the rows are walked in chunks of tiles, the y0
+  // chunk c+1 travels host->device while chunk c is multiplied and the y chunk c-1 travels device->host, so the two
+  // PCIe directions are busy at the same time. Rows of a chunk are final once its kernels have run.
+  const int kHostChunks = host_chunks();
+  if (p->nsplit == 0 && p->ntiles >= 4 * kHostChunks && hm->m > 0) {
+    if (hm->n > 0)
+      B200_CUDA(cudaMemcpyAsync(hm->d_x, h_x, sizeof(double) * (size_t)hm->n, cudaMemcpyHostToDevice, hm->s_in));
+    B200_CUDA(cudaEventRecord(hm->ev_x, hm->s_in));
+    B200_CUDA(cudaStreamWaitEvent(hm->stream, hm->ev_x, 0));
+    for (int c = 0; c < kHostChunks; ++c) {
+      const int tlo = (int)((long long)p->ntiles * c / kHostChunks);
+      const int thi = (int)((long long)p->ntiles * (c + 1) / kHostChunks);
+      const size_t rlo = (size_t)p->h_tile_row[tlo], rhi = (size_t)p->h_tile_row[thi];
+      if (rhi > rlo)
+        B200_CUDA(cudaMemcpyAsync(hm->d_y + rlo, h_y + rlo, sizeof(double) * (rhi - rlo), cudaMemcpyHostToDevice,
+                                  hm->s_in));
+      B200_CUDA(cudaEventRecord(hm->ev_in[c], hm->s_in));
+      B200_CUDA(cudaStreamWaitEvent(hm->stream, hm->ev_in[c], 0));
+      const int rc = kernels_launch_tiles(p, alpha, beta, hm->d_x, hm->d_y, tlo, thi, hm->stream);
+      if (rc != SPMV_B200_OK)
+        return rc;
+      B200_CUDA(cudaEventRecord(hm->ev_done[c], hm->stream));
+      B200_CUDA(cudaStreamWaitEvent(hm->s_out, hm->ev_done[c], 0));
+      if (rhi > rlo)
+        B200_CUDA(cudaMemcpyAsync(h_y + rlo, hm->d_y + rlo, sizeof(double) * (rhi - rlo), cudaMemcpyDeviceToHost,
+                                  hm->s_out));
+    }
+    B200_CUDA(cudaStreamSynchronize(hm->s_out));
+    B200_CUDA(cudaStreamSynchronize(hm->stream));
+    return SPMV_B200_OK;
   }
   if (hm->n > 0)
     B200_CUDA(cudaMemcpyAsync(hm->d_x, h_x, sizeof(double) * (size_t)hm->n, cudaMemcpyHostToDevice, hm->stream));

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "spmv_b200.h"
 
@@ -15,6 +16,7 @@ constexpr int kThreads = 256;     // threads per CTA of every streaming kernel
 constexpr int kRowChunk = 512;    // row pointers staged in shared memory per pass (rows per pass = kRowChunk)
 constexpr int kSerialMax = 8;     // MIXED kernel: rows up to this length are reduced by one thread
 constexpr int kGroupMax = 96;     // MIXED kernel: rows up to this length are reduced by 8 lanes, longer ones by a warp
+constexpr int kSparseTileRows = 512; // tiles owning more rows than this are streamed by the MIXED kernel
 constexpr int kDefaultTile = 0; // 0 = chosen from the average row length (see auto_tile in capi.cu)
 constexpr int kDefaultShort = 8;
 constexpr int kDefaultMedium = 128;
@@ -106,6 +108,9 @@ struct spmv_b200_plan {
   int nsplit = 0;
   int *split_rows = nullptr; // [3*nsplit]: row, t0, t1 (struct of arrays: rows | t0 | t1)
   double *partials = nullptr;
+  // host copies used to launch a sub-range of tiles (pipelined host-buffer path)
+  std::vector<int> h_list[3];   // tile ids per kind, ascending
+  std::vector<int> h_tile_row;  // [ntiles+1]
   long long bin_rows[4] = {0, 0, 0, 0};
   long long bin_nnz[4] = {0, 0, 0, 0};
   size_t workspace_bytes = 0;
@@ -125,5 +130,8 @@ int col_block_bitmap_run(long long nnz, const int *d_col, int n, int block_shift
 int kernels_configure(spmv_b200_plan *p);
 int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y,
                    cudaStream_t stream);
+// tiles [tile_lo, tile_hi) only; the plan must have no split rows (their partial sums cross tile ranges)
+int kernels_launch_tiles(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y, int tile_lo,
+                         int tile_hi, cudaStream_t stream);
 
 } // namespace b200

@@ -22,6 +22,7 @@
 // line_enhance_spmv_imp.inl:11-95), flat (src/acc/hip-flat/flat_imp_one_pass.hpp:15-77, which uses atomicAdd and
 // assumes beta == 1), merge-path reduction + update (benchmark/merge-path/merge_path_reduction.h:80-136,
 // merge_path_update.h:8-64). The epilogue y = alpha*sum + beta*y follows cli/verification.cpp:64.
+#include <algorithm>
 #include <cstdlib>
 
 #include "internal.cuh"
@@ -667,8 +668,15 @@ static cudaError_t launch_spmv(RowsKernel k, int grid, size_t smem, cudaStream_t
   return cudaLaunchKernelEx(&cfg, k, a);
 }
 
-int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y,
-                   cudaStream_t stream) {
+// index range [lo, hi) of the tiles of kind k whose tile id lies in [tile_lo, tile_hi)
+static void kind_range(const spmv_b200_plan *p, int k, int tile_lo, int tile_hi, int *lo, int *hi) {
+  const std::vector<int> &l = p->h_list[k];
+  *lo = (int)(std::lower_bound(l.begin(), l.end(), tile_lo) - l.begin());
+  *hi = (int)(std::lower_bound(l.begin(), l.end(), tile_hi) - l.begin());
+}
+
+static int launch_range(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y, int tile_lo,
+                        int tile_hi, bool with_fixup, cudaStream_t stream) {
   if (p->m == 0)
     return SPMV_B200_OK;
   SpmvArgs a;
@@ -685,46 +693,36 @@ int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const dou
   a.vec_div = p->vec_div;
   a.gather_na = (p->flags & (1u << 16)) ? 2 : ((p->flags & SPMV_B200_FLAG_GATHER_NO_L1) ? 1 : 0);
   a.read_y = (beta == 0.0 && (p->flags & SPMV_B200_FLAG_BETA0_SKIP_Y)) ? 0 : 1;
+  a.ntiles = 0;
 
   const bool tma = p->uses_tma;
   const bool persistent = (p->flags & SPMV_B200_FLAG_PERSISTENT) != 0;
-  a.ntiles = 0;
-  if (p->count[SPMV_B200_KIND_SHORT] > 0) {
-    const RowsVariant &v = kShortVariants[p->variant_short];
-    a.desc = p->desc[SPMV_B200_KIND_SHORT];
-    a.cap = cap_for(p, SPMV_B200_KIND_SHORT);
-    a.ntiles = p->count[SPMV_B200_KIND_SHORT];
+  const bool whole = tile_lo <= 0 && tile_hi >= p->ntiles;
+  for (int k = 0; k < 3; ++k) {
+    if (p->count[k] == 0)
+      continue;
+    int lo = 0, hi = p->count[k];
+    if (!whole)
+      kind_range(p, k, tile_lo, tile_hi, &lo, &hi);
+    if (hi <= lo)
+      continue;
+    a.desc = p->desc[k] + lo;
+    a.cap = cap_for(p, k);
+    a.ntiles = hi - lo;
+    if (k == SPMV_B200_KIND_MIXED) {
+      B200_CUDA(launch_spmv(tma ? k_spmv_mixed<true> : k_spmv_mixed<false>, a.ntiles, smem_for(p, k), stream, a, p));
+      continue;
+    }
+    const RowsVariant &v = k == SPMV_B200_KIND_SHORT ? kShortVariants[p->variant_short]
+                                                     : kMediumVariants[p->variant_medium];
     if (tma && persistent) {
-      const int grid = a.ntiles < p->persistent_grid[SPMV_B200_KIND_SHORT] ? a.ntiles
-                                                                           : p->persistent_grid[SPMV_B200_KIND_SHORT];
-      B200_CUDA(launch_spmv(v.persistent, grid, smem_for(p, SPMV_B200_KIND_SHORT, true), stream, a, p));
+      const int grid = a.ntiles < p->persistent_grid[k] ? a.ntiles : p->persistent_grid[k];
+      B200_CUDA(launch_spmv(v.persistent, grid, smem_for(p, k, true), stream, a, p));
     } else {
-      B200_CUDA(launch_spmv(tma ? v.tma : v.plain, a.ntiles, smem_for(p, SPMV_B200_KIND_SHORT), stream, a, p));
+      B200_CUDA(launch_spmv(tma ? v.tma : v.plain, a.ntiles, smem_for(p, k), stream, a, p));
     }
   }
-  if (p->count[SPMV_B200_KIND_MEDIUM] > 0) {
-    const RowsVariant &v = kMediumVariants[p->variant_medium];
-    a.desc = p->desc[SPMV_B200_KIND_MEDIUM];
-    a.cap = cap_for(p, SPMV_B200_KIND_MEDIUM);
-    a.ntiles = p->count[SPMV_B200_KIND_MEDIUM];
-    if (tma && persistent) {
-      const int grid = a.ntiles < p->persistent_grid[SPMV_B200_KIND_MEDIUM]
-                           ? a.ntiles
-                           : p->persistent_grid[SPMV_B200_KIND_MEDIUM];
-      B200_CUDA(launch_spmv(v.persistent, grid, smem_for(p, SPMV_B200_KIND_MEDIUM, true), stream, a, p));
-    } else {
-      B200_CUDA(launch_spmv(tma ? v.tma : v.plain, a.ntiles, smem_for(p, SPMV_B200_KIND_MEDIUM), stream, a, p));
-    }
-  }
-  if (p->count[SPMV_B200_KIND_MIXED] > 0) {
-    a.desc = p->desc[SPMV_B200_KIND_MIXED];
-    a.cap = cap_for(p, SPMV_B200_KIND_MIXED);
-    a.ntiles = p->count[SPMV_B200_KIND_MIXED];
-    const size_t sm = smem_for(p, SPMV_B200_KIND_MIXED);
-    B200_CUDA(launch_spmv(tma ? k_spmv_mixed<true> : k_spmv_mixed<false>, p->count[SPMV_B200_KIND_MIXED], sm, stream,
-                          a, p));
-  }
-  if (p->nsplit > 0) {
+  if (with_fixup && p->nsplit > 0) {
     FixupArgs f;
     f.split_row = p->split_rows;
     f.split_t0 = p->split_rows + p->nsplit;
@@ -740,6 +738,20 @@ int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const dou
   }
   B200_CUDA(cudaGetLastError());
   return SPMV_B200_OK;
+}
+
+int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y,
+                   cudaStream_t stream) {
+  return launch_range(p, alpha, beta, x, y, 0, p->ntiles, true, stream);
+}
+
+int kernels_launch_tiles(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y, int tile_lo,
+                         int tile_hi, cudaStream_t stream) {
+  if (p->nsplit > 0) {
+    set_error("kernels_launch_tiles: the plan has split rows");
+    return SPMV_B200_ERR_UNSUPPORTED;
+  }
+  return launch_range(p, alpha, beta, x, y, tile_lo, tile_hi, false, stream);
 }
 
 } // namespace b200

@@ -202,6 +202,22 @@ def test_host_buffer_path():
     assert_parity(h, g["x"], g["y0"], 1.0, 1.0, y, g["y"][0], what="host_spmv")
 
 
+def test_host_buffer_path_pipelined_chunks():
+    """Matrices without split rows and with enough tiles take the chunked, copy/compute-overlapped host path."""
+    for name, h in (("stencil2d_300", synth.stencil2d_numpy(300)), ("stencil3d_40", synth.stencil3d_numpy(40)),
+                    ("uniform", synth.uniform_numpy(4000, 6000, 32, seed=5))):
+        x, y0 = synth.vector_numpy(h.cols, 2), synth.vector_numpy(h.rows, 3)
+        hm = HostMatrix(h.rows, h.cols, h.rowptr, h.col, h.val)
+        for a, b in AB[:3]:
+            y = y0.copy()
+            hm.spmv(a, b, x, y)
+            assert_parity(h, x, y0, a, b, y, what=f"hostmat pipelined {name}")
+            y2 = y0.copy()
+            hm.spmv(a, b, x, y2)
+            assert np.array_equal(y, y2)
+        hm.destroy()
+
+
 def test_bad_options_are_rejected():
     d = synth.to_device(synth.stencil2d_numpy(8))
     for bad in (make_options(100), make_options(2048, 8, 4096), make_options(2048, 300, 128), make_options(2048, 8, 126)):
