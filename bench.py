@@ -333,7 +333,9 @@ def run_b200(args, rank, world, local_rank):
     if not args.no_iterated:
         try:
             from spmv_acc_b200.sharded import bench_power_loop
-            line["iterated"] = bench_power_loop(args.iter_grid, args.iters, exchange=args.exchange)
+            line["iterated"] = bench_power_loop(args.iter_grid, args.iters, exchange=args.exchange,
+                                                overlap=not args.no_overlap, graph=args.graph,
+                                                fused=not args.no_fused)
         except Exception as e:  # the headline number must survive a failure of the secondary measurement
             line["iterated"] = {"error": f"{type(e).__name__}: {e}"}
 
@@ -444,6 +446,9 @@ def main():
     ap.add_argument("--iter-grid", type=int, default=384)
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "halo"])
+    ap.add_argument("--no-fused", action="store_true", help="halo exchange with NCCL send/recv instead of the fused push")
+    ap.add_argument("--graph", action="store_true", help="replay the power loop from a CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true", help="do not overlap the halo exchange with interior rows")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -87,6 +87,16 @@ enum {
   SPMV_B200_EXPORT_TILE_MAXLEN = 7 /* int32 [ntiles]    longest row owned by each tile                               */
 };
 
+/* Fused halo push: rows [row_lo[j], row_hi[j]) of y are also stored to dst[j][row] (device pointers, typically
+ * peer memory of another GPU mapped through CUDA IPC, offset so that they are indexed by the local row). */
+#define SPMV_B200_MAX_PUSH 8
+typedef struct spmv_b200_push {
+  int32_t count;
+  int32_t row_lo[SPMV_B200_MAX_PUSH];
+  int32_t row_hi[SPMV_B200_MAX_PUSH];
+  double *dst[SPMV_B200_MAX_PUSH];
+} spmv_b200_push;
+
 typedef struct spmv_b200_plan spmv_b200_plan;
 typedef struct spmv_b200_hostmat spmv_b200_hostmat;
 
@@ -97,6 +107,26 @@ const char *spmv_b200_last_error(void);
 int spmv_b200_plan_create(spmv_b200_plan **out, int32_t m, int32_t n, int64_t nnz, const int32_t *d_rowptr,
                           const int32_t *d_colidx, const double *d_val, const spmv_b200_options *opt, void *stream);
 int spmv_b200_execute(spmv_b200_plan *plan, double alpha, double beta, const double *d_x, double *d_y, void *stream);
+/* tiles [tile_lo, tile_hi) only (row blocks in ascending row order, see SPMV_B200_EXPORT_TILE_ROW); lets a caller
+ * overlap the rows whose results other GPUs wait for with the rest. Refused for plans with split rows. */
+int spmv_b200_execute_tiles(spmv_b200_plan *plan, double alpha, double beta, const double *d_x, double *d_y,
+                            int32_t tile_lo, int32_t tile_hi, void *stream);
+/* execute + store the rows listed in `push` into other GPUs' memory from the same kernels (no separate exchange) */
+int spmv_b200_execute_push(spmv_b200_plan *plan, double alpha, double beta, const double *d_x, double *d_y,
+                           const spmv_b200_push *push, void *stream);
+/* stream-ordered 32-bit flags in (peer) device memory: write `value`, or block the stream until *flag >= value.
+ * Used to order the iterations of neighbouring GPUs without a collective. */
+int spmv_b200_stream_write_flag(void *stream, uint32_t *d_flag, uint32_t value);
+int spmv_b200_stream_wait_flag(void *stream, uint32_t *d_flag, uint32_t value);
+int spmv_b200_enable_peer_access(int32_t peer_device);
+/* exchange buffers other GPUs (other processes) store into: allocated with cudaMalloc on the current device and
+ * exported as a 64-byte CUDA IPC handle; the consumer opens the handle with ITS device current, which is what maps
+ * the memory for its kernels (cudaIpcMemLazyEnablePeerAccess). peer_free / peer_close release them. */
+#define SPMV_B200_IPC_HANDLE_BYTES 64
+int spmv_b200_peer_alloc(void **d_ptr, int64_t bytes, uint8_t handle_out[SPMV_B200_IPC_HANDLE_BYTES]);
+int spmv_b200_peer_open(const uint8_t handle[SPMV_B200_IPC_HANDLE_BYTES], void **d_ptr);
+int spmv_b200_peer_close(void *d_ptr);
+int spmv_b200_peer_free(void *d_ptr);
 int spmv_b200_plan_destroy(spmv_b200_plan *plan);
 int spmv_b200_plan_get_info(const spmv_b200_plan *plan, spmv_b200_plan_info *info);
 /* copies one analysis array to host memory; returns the number of bytes through *bytes_out. dst may be NULL to query */

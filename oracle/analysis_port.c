@@ -144,7 +144,7 @@ int port_analysis(const int *rowptr, int m, int T, int short_max, int medium_max
   for (int t = 0; t < ntiles; t++) {
     const long long rows = tile_row[t + 1] - tile_row[t];
     const long long elems = tile_elem[t + 1] - tile_elem[t];
-    const int skewed = tile_maxlen[t] > short_max && (long long)tile_maxlen[t] * rows > 4 * elems;
+    const int skewed = tile_maxlen[t] > short_max && (long long)tile_maxlen[t] * rows > 2 * elems;
     if (tile_split[t] || tile_split[t + 1] || tile_maxlen[t] > medium_max || rows > 512 || skewed)
       tile_kind[t] = 2;
     else if (tile_maxlen[t] <= short_max)

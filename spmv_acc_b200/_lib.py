@@ -14,6 +14,9 @@ LIB_DIR = PKG / "lib"
 # every symbol include/spmv_b200.h declares (tests/test_abi.py checks the header against this list)
 ABI_SYMBOLS = [
     "spmv_b200_abi_version", "spmv_b200_last_error", "spmv_b200_plan_create", "spmv_b200_execute",
+    "spmv_b200_execute_tiles", "spmv_b200_execute_push", "spmv_b200_stream_write_flag", "spmv_b200_stream_wait_flag",
+    "spmv_b200_enable_peer_access", "spmv_b200_peer_alloc", "spmv_b200_peer_open", "spmv_b200_peer_close",
+    "spmv_b200_peer_free",
     "spmv_b200_plan_destroy", "spmv_b200_plan_get_info", "spmv_b200_plan_export", "spmv_b200_csr_spmv",
     "spmv_b200_sparse_spmv", "spmv_b200_cache_invalidate", "spmv_b200_cache_size", "spmv_b200_hostmat_create",
     "spmv_b200_hostmat_spmv", "spmv_b200_hostmat_destroy", "spmv_b200_host_spmv", "spmv_b200_shard_bounds",
@@ -24,6 +27,15 @@ ABI_SYMBOLS = [
 class Options(C.Structure):
     _fields_ = [("tile_nnz", C.c_int32), ("short_max", C.c_int32), ("medium_max", C.c_int32),
                 ("vec_div", C.c_int32), ("flags", C.c_uint32)]
+
+
+MAX_PUSH = 8
+IPC_HANDLE_BYTES = 64
+
+
+class Push(C.Structure):
+    _fields_ = [("count", C.c_int32), ("row_lo", C.c_int32 * MAX_PUSH), ("row_hi", C.c_int32 * MAX_PUSH),
+                ("dst", C.c_void_p * MAX_PUSH)]
 
 
 class PlanInfo(C.Structure):
@@ -67,6 +79,15 @@ def lib() -> C.CDLL:
         L.spmv_b200_last_error.restype = C.c_char_p
         L.spmv_b200_plan_create.argtypes = [C.POINTER(vp), i32, i32, i64, vp, vp, vp, C.POINTER(Options), vp]
         L.spmv_b200_execute.argtypes = [vp, dbl, dbl, vp, vp, vp]
+        L.spmv_b200_execute_tiles.argtypes = [vp, dbl, dbl, vp, vp, i32, i32, vp]
+        L.spmv_b200_execute_push.argtypes = [vp, dbl, dbl, vp, vp, C.POINTER(Push), vp]
+        L.spmv_b200_stream_write_flag.argtypes = [vp, vp, C.c_uint32]
+        L.spmv_b200_stream_wait_flag.argtypes = [vp, vp, C.c_uint32]
+        L.spmv_b200_enable_peer_access.argtypes = [i32]
+        L.spmv_b200_peer_alloc.argtypes = [C.POINTER(vp), i64, C.c_char_p]
+        L.spmv_b200_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.spmv_b200_peer_close.argtypes = [vp]
+        L.spmv_b200_peer_free.argtypes = [vp]
         L.spmv_b200_plan_destroy.argtypes = [vp]
         L.spmv_b200_plan_get_info.argtypes = [vp, C.POINTER(PlanInfo)]
         L.spmv_b200_plan_export.argtypes = [vp, i32, vp, i64, C.POINTER(i64)]
@@ -111,6 +132,7 @@ def ctx() -> C.CDLL:
         X.spmv_b200_ctx_cusparse_create.argtypes = [C.POINTER(vp), i32, i32, i64, vp, vp, vp, vp, vp, i32]
         X.spmv_b200_ctx_cusparse_spmv.argtypes = [vp, dbl, dbl, vp]
         X.spmv_b200_ctx_cusparse_destroy.argtypes = [vp]
+        X.spmv_b200_ctx_gather_bound.argtypes = [i64, vp, vp, vp, vp, i32, i32, i32, vp]
         _ctx = X
     return _ctx
 

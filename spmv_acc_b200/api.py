@@ -137,6 +137,34 @@ class SpmvPlan:
                                           _current_stream() if stream is None else stream)
         check(rc, "execute")
 
+    def execute_tiles(self, alpha: float, beta: float, dx: Any, dy: Any, tile_lo: int, tile_hi: int,
+                      stream: Optional[int] = None) -> None:
+        """Row blocks [tile_lo, tile_hi) only (``export("tile_row")`` gives their row ranges); no split rows allowed."""
+        if not self._h:
+            raise SpmvB200Error("plan was destroyed")
+        _require_device(dx, "dx", "float64")
+        _require_device(dy, "dy", "float64")
+        rc = _lib.lib().spmv_b200_execute_tiles(self._h, float(alpha), float(beta), _ptr(dx), _ptr(dy), int(tile_lo),
+                                                int(tile_hi), _current_stream() if stream is None else stream)
+        check(rc, "execute_tiles")
+
+    def execute_push(self, alpha: float, beta: float, dx: Any, dy: Any, push: list, stream: Optional[int] = None) -> None:
+        """execute + fused halo push: ``push`` is a list of (row_lo, row_hi, dst_address); rows in [row_lo, row_hi) are
+        also stored to ``dst_address[row]`` (8-byte elements; typically another GPU's memory mapped through CUDA IPC)."""
+        if not self._h:
+            raise SpmvB200Error("plan was destroyed")
+        if len(push) > _lib.MAX_PUSH:
+            raise SpmvB200Error(f"at most {_lib.MAX_PUSH} push ranges are supported")
+        _require_device(dx, "dx", "float64")
+        _require_device(dy, "dy", "float64")
+        ps = _lib.Push()
+        ps.count = len(push)
+        for j, (lo, hi, dst) in enumerate(push):
+            ps.row_lo[j], ps.row_hi[j], ps.dst[j] = int(lo), int(hi), int(dst)
+        rc = _lib.lib().spmv_b200_execute_push(self._h, float(alpha), float(beta), _ptr(dx), _ptr(dy), C.byref(ps),
+                                               _current_stream() if stream is None else stream)
+        check(rc, "execute_push")
+
     def info(self) -> PlanInfo:
         out = PlanInfo()
         check(_lib.lib().spmv_b200_plan_get_info(self._h, C.byref(out)), "plan_get_info")
@@ -198,6 +226,64 @@ def host_spmv(alpha: float, beta: float, rows: int, cols: int, rowptr: np.ndarra
     rc = _lib.lib().spmv_b200_host_spmv(float(alpha), float(beta), int(rows), int(cols), int(len(value)),
                                         _ptr(rowptr), _ptr(colindex), _ptr(value), _ptr(x), _ptr(y))
     check(rc, "host_spmv")
+
+
+def stream_write_flag(address: int, value: int, stream: Optional[int] = None) -> None:
+    """Stream-ordered 32-bit store (with a system-scope memory barrier) to device memory, possibly another GPU's."""
+    check(_lib.lib().spmv_b200_stream_write_flag(_current_stream() if stream is None else stream, int(address),
+                                                 int(value)), "stream_write_flag")
+
+
+def stream_wait_flag(address: int, value: int, stream: Optional[int] = None) -> None:
+    """Blocks the stream (not the host) until the 32-bit word at ``address`` is >= value."""
+    check(_lib.lib().spmv_b200_stream_wait_flag(_current_stream() if stream is None else stream, int(address),
+                                                int(value)), "stream_wait_flag")
+
+
+def enable_peer_access(peer_device: int) -> None:
+    check(_lib.lib().spmv_b200_enable_peer_access(int(peer_device)), "enable_peer_access")
+
+
+class PeerBuffer:
+    """Device buffer other GPUs (other processes) can store into. ``PeerBuffer.alloc`` owns cudaMalloc'ed memory on the
+    current device and exposes its 64-byte CUDA IPC handle; ``PeerBuffer.open`` maps another process' buffer for the
+    kernels of the *current* device (cudaIpcOpenMemHandle with lazy peer access, NVLink on an NVSwitch box)."""
+
+    def __init__(self, address: int, nbytes: int, handle: bytes, owner: bool):
+        self.address, self.nbytes, self.handle, self.owner = address, nbytes, handle, owner
+
+    @classmethod
+    def alloc(cls, nbytes: int) -> "PeerBuffer":
+        out = C.c_void_p()
+        handle = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        check(_lib.lib().spmv_b200_peer_alloc(C.byref(out), int(nbytes), handle), "peer_alloc")
+        return cls(int(out.value), int(nbytes), handle.raw, True)
+
+    @classmethod
+    def open(cls, handle: bytes, nbytes: int) -> "PeerBuffer":
+        out = C.c_void_p()
+        check(_lib.lib().spmv_b200_peer_open(C.create_string_buffer(handle, _lib.IPC_HANDLE_BYTES), C.byref(out)),
+              "peer_open")
+        return cls(int(out.value), int(nbytes), handle, False)
+
+    def tensor(self, dtype: str, count: int, offset_bytes: int = 0):
+        """torch view of the buffer (no copy); only meaningful for buffers owned by this process."""
+        import torch
+        item = np.dtype(dtype).itemsize
+        assert offset_bytes + count * item <= self.nbytes
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (int(count),), "typestr": np.dtype(dtype).str,
+                                        "data": (self.address + offset_bytes, False), "version": 2}
+        t = torch.as_tensor(_View(), device="cuda")
+        t._spmv_b200_keepalive = self
+        return t
+
+    def release(self) -> None:
+        if self.address:
+            fn = _lib.lib().spmv_b200_peer_free if self.owner else _lib.lib().spmv_b200_peer_close
+            check(fn(self.address), "peer_free" if self.owner else "peer_close")
+            self.address = 0
 
 
 def shard_bounds(d_rowptr: Any, rows: int, nshards: int) -> np.ndarray:

@@ -25,7 +25,7 @@
 //                   benchmark/merge-path/merge_path_partition.h:7-17; exported for the cross-check only)
 //   row r is owned by tile min(floor(f(r)/T), ntiles-1); tile_maxlen[t] = max nnz of the rows it owns.
 //   tile_kind[t]  = MIXED if tile_split[t] or tile_split[t+1] or tile_maxlen[t] > L or the tile owns more than 512 rows
-//                   or (tile_maxlen[t] > S and tile_maxlen[t] * rows_t > 4 * nnz_t);
+//                   or (tile_maxlen[t] > S and tile_maxlen[t] * rows_t > 2 * nnz_t);
 //                   SHORT if tile_maxlen[t] <= S; else MEDIUM.
 //   bin(r) = SHORT if nnz_r <= S; MEDIUM if nnz_r <= L; LONG if nnz_r <= T; else VERYLONG.
 //   split row r (first split boundary t, i.e. tile_row[t-1] <= r = tile_row[t]-1): fragments live in tiles
@@ -179,11 +179,11 @@ __global__ void __launch_bounds__(256)
   unsigned char k;
   // tiles with more than two passes' worth of rows (mostly empty / one-element rows) also go to the MIXED kernel,
   // whose cost grows with the non-zeros and not with the number of rows
-  // ... and so do tiles whose longest row is more than four times the tile's average row (a lane group that owns
+  // ... and so do tiles whose longest row is more than twice the tile's average row (a lane group that owns
   // such a row would keep the whole CTA waiting)
   const long long rows = tile_row[t + 1] - tile_row[t];
   const long long elems = tile_elem[t + 1] - tile_elem[t];
-  const bool skewed = ml > short_max && (long long)ml * rows > 4 * elems;
+  const bool skewed = ml > short_max && (long long)ml * rows > 2 * elems;
   if (tile_split[t] || tile_split[t + 1] || ml > medium_max || rows > kSparseTileRows || skewed)
     k = SPMV_B200_KIND_MIXED;
   else if (ml <= short_max)

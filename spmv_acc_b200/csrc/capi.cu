@@ -164,6 +164,162 @@ int spmv_b200_execute(spmv_b200_plan *plan, double alpha, double beta, const dou
   return kernels_launch(plan, alpha, beta, d_x, d_y, static_cast<cudaStream_t>(stream));
 }
 
+int spmv_b200_execute_tiles(spmv_b200_plan *plan, double alpha, double beta, const double *d_x, double *d_y,
+                            int32_t tile_lo, int32_t tile_hi, void *stream) {
+  if (!plan) {
+    set_error("execute_tiles: plan is NULL");
+    return SPMV_B200_ERR_ARG;
+  }
+  if (tile_lo < 0 || tile_hi > plan->ntiles || tile_lo > tile_hi) {
+    set_error("execute_tiles: tile range out of bounds");
+    return SPMV_B200_ERR_ARG;
+  }
+  if ((plan->m > 0 && !d_y) || (plan->nnz > 0 && !d_x)) {
+    set_error("execute_tiles: x or y is NULL");
+    return SPMV_B200_ERR_ARG;
+  }
+  if (tile_lo == tile_hi)
+    return SPMV_B200_OK;
+  return kernels_launch_tiles(plan, alpha, beta, d_x, d_y, tile_lo, tile_hi, static_cast<cudaStream_t>(stream));
+}
+
+int spmv_b200_execute_push(spmv_b200_plan *plan, double alpha, double beta, const double *d_x, double *d_y,
+                           const spmv_b200_push *push, void *stream) {
+  if (!plan || !push) {
+    set_error("execute_push: NULL argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  if (push->count < 0 || push->count > SPMV_B200_MAX_PUSH) {
+    set_error("execute_push: push.count out of range");
+    return SPMV_B200_ERR_ARG;
+  }
+  if ((plan->m > 0 && !d_y) || (plan->nnz > 0 && !d_x)) {
+    set_error("execute_push: x or y is NULL");
+    return SPMV_B200_ERR_ARG;
+  }
+  PushArgs pa;
+  pa.count = push->count;
+  for (int j = 0; j < kMaxPush; ++j) {
+    pa.row_lo[j] = j < push->count ? push->row_lo[j] : 0;
+    pa.row_hi[j] = j < push->count ? push->row_hi[j] : 0;
+    pa.dst[j] = j < push->count ? push->dst[j] : nullptr;
+    if (j < push->count && (!pa.dst[j] || pa.row_lo[j] < 0 || pa.row_hi[j] > plan->m || pa.row_lo[j] > pa.row_hi[j])) {
+      set_error("execute_push: bad push range");
+      return SPMV_B200_ERR_ARG;
+    }
+  }
+  return kernels_launch(plan, alpha, beta, d_x, d_y, static_cast<cudaStream_t>(stream), &pa);
+}
+
+// stream memory operations of the driver API, fetched at run time (no link-time dependency on libcuda)
+namespace {
+typedef int (*StreamMemOp32)(void *stream, unsigned long long addr, unsigned int value, unsigned int flags);
+StreamMemOp32 driver_fn(const char *name) {
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return reinterpret_cast<StreamMemOp32>(fn);
+}
+} // namespace
+
+// The flag may live in another GPU's memory (IPC mapping): a one-thread kernel with a system-scope fence is the
+// portable way to publish it after the stores of the preceding kernels in the stream.
+__global__ void k_write_flag(uint32_t *flag, uint32_t value) {
+  __threadfence_system();
+  *reinterpret_cast<volatile uint32_t *>(flag) = value;
+}
+
+int spmv_b200_stream_write_flag(void *stream, uint32_t *d_flag, uint32_t value) {
+  if (!d_flag) {
+    set_error("stream_write_flag: flag is NULL");
+    return SPMV_B200_ERR_ARG;
+  }
+  k_write_flag<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(d_flag, value);
+  B200_CUDA(cudaGetLastError());
+  return SPMV_B200_OK;
+}
+
+int spmv_b200_stream_wait_flag(void *stream, uint32_t *d_flag, uint32_t value) {
+  static StreamMemOp32 fn = driver_fn("cuStreamWaitValue32");
+  if (!fn) {
+    set_error("cuStreamWaitValue32 is not available");
+    return SPMV_B200_ERR_UNSUPPORTED;
+  }
+  const int rc = fn(stream, (unsigned long long)(uintptr_t)d_flag, value, 0u /* CU_STREAM_WAIT_VALUE_GEQ */);
+  if (rc != 0) {
+    set_error("cuStreamWaitValue32 failed with CUresult " + std::to_string(rc));
+    return SPMV_B200_ERR_CUDA;
+  }
+  return SPMV_B200_OK;
+}
+
+int spmv_b200_enable_peer_access(int32_t peer_device) {
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (peer_device == dev)
+    return SPMV_B200_OK;
+  int can = 0;
+  B200_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+  if (!can) {
+    set_error("enable_peer_access: the devices have no peer path");
+    return SPMV_B200_ERR_UNSUPPORTED;
+  }
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return SPMV_B200_OK;
+  }
+  B200_CUDA(e);
+  return SPMV_B200_OK;
+}
+
+int spmv_b200_peer_alloc(void **d_ptr, int64_t bytes, uint8_t handle_out[SPMV_B200_IPC_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == SPMV_B200_IPC_HANDLE_BYTES, "IPC handle size");
+  if (!d_ptr || !handle_out || bytes <= 0) {
+    set_error("peer_alloc: bad argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  void *p = nullptr;
+  B200_CUDA(cudaMalloc(&p, static_cast<size_t>(bytes)));
+  cudaError_t e = cudaMemset(p, 0, static_cast<size_t>(bytes));
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess)
+    e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    B200_CUDA(e);
+  }
+  std::memcpy(handle_out, &h, sizeof(h));
+  *d_ptr = p;
+  return SPMV_B200_OK;
+}
+
+int spmv_b200_peer_open(const uint8_t handle[SPMV_B200_IPC_HANDLE_BYTES], void **d_ptr) {
+  if (!d_ptr || !handle) {
+    set_error("peer_open: bad argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  void *p = nullptr;
+  B200_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *d_ptr = p;
+  return SPMV_B200_OK;
+}
+
+int spmv_b200_peer_close(void *d_ptr) {
+  if (d_ptr)
+    B200_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return SPMV_B200_OK;
+}
+
+int spmv_b200_peer_free(void *d_ptr) {
+  if (d_ptr)
+    B200_CUDA(cudaFree(d_ptr));
+  return SPMV_B200_OK;
+}
+
 int spmv_b200_plan_destroy(spmv_b200_plan *plan) {
   if (!plan)
     return SPMV_B200_OK;

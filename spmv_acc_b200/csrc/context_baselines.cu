@@ -73,3 +73,82 @@ CTX_API int spmv_b200_ctx_cusparse_spmv(ctx_cusparse *c, double alpha, double be
   return (int)cusparseSpMV(c->handle, CUSPARSE_OPERATION_NON_TRANSPOSE, &alpha, c->mat, c->vx, &beta, c->vy,
                            CUDA_R_64F, c->alg, c->buffer);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gather bound (context, not product): streams colindex (and value) exactly like SpMV and gathers x[colindex[k]],
+// but with NO row structure: every thread keeps private sums, nothing is reduced per row, one store per thread.
+// Its time is a lower bound for any CSR kernel that gathers x element-wise for the same column stream: it pays the
+// same HBM streams, the same L1TEX wavefronts (one per distinct 128-byte line per warp gather) and the same L2 / DRAM
+// sector traffic for x, and nothing else.
+//   mode bit 0: also stream `value` and multiply;  bits 1-3: flavour of the gather load
+//   (0 ld.global.nc, 1 L1::no_allocate, 2 ld.global.cg (L2 only), 3 L1::evict_first, 4 L1::evict_last)
+// `smem_bytes` of dynamic shared memory are requested per CTA only to shrink L1 (the unified array is 256 KB per SM):
+// it measures how the gather rate depends on the L1 capacity left next to staged tiles.
+template <int FL> __device__ __forceinline__ double gb_load(const double *p) {
+  double g;
+  if (FL == 1)
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(g) : "l"(p));
+  else if (FL == 2)
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(g) : "l"(p));
+  else if (FL == 3)
+    asm volatile("ld.global.nc.L1::evict_first.f64 %0, [%1];" : "=d"(g) : "l"(p));
+  else if (FL == 4)
+    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(g) : "l"(p));
+  else
+    g = __ldg(p);
+  return g;
+}
+
+template <int U, bool VAL, int FL>
+__global__ void __launch_bounds__(256) k_gather_bound(const int *__restrict__ col, const double *__restrict__ val,
+                                                      const double *__restrict__ x, long long nnz,
+                                                      double *__restrict__ out) {
+  const long long chunk = 256LL * U;
+  double acc = 0.0;
+  for (long long base = blockIdx.x * chunk; base < nnz; base += (long long)gridDim.x * chunk) {
+    int c[U];
+    double v[U], g[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long k = base + u * 256 + threadIdx.x;
+      c[u] = k < nnz ? __ldcs(col + k) : -1;
+      if (VAL)
+        v[u] = k < nnz ? __ldcs(val + k) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      g[u] = c[u] >= 0 ? gb_load<FL>(x + c[u]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      acc += VAL ? v[u] * g[u] : g[u];
+  }
+  out[blockIdx.x * 256 + threadIdx.x] = acc;
+}
+
+typedef void (*GatherKernel)(const int *, const double *, const double *, long long, double *);
+
+// out must hold grid*256 doubles; returns the grid size when out == nullptr
+CTX_API int spmv_b200_ctx_gather_bound(long long nnz, const int *d_col, const double *d_val, const double *d_x,
+                                       double *d_out, int mode, int ctas_per_sm, int smem_bytes, void *stream) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = sms * (ctas_per_sm > 0 ? ctas_per_sm : 8);
+  if (!d_out)
+    return grid;
+  static const GatherKernel table[2][5] = {
+      {k_gather_bound<8, false, 0>, k_gather_bound<8, false, 1>, k_gather_bound<8, false, 2>,
+       k_gather_bound<8, false, 3>, k_gather_bound<8, false, 4>},
+      {k_gather_bound<8, true, 0>, k_gather_bound<8, true, 1>, k_gather_bound<8, true, 2>, k_gather_bound<8, true, 3>,
+       k_gather_bound<8, true, 4>}};
+  const int fl = (mode >> 1) & 7;
+  if (fl > 4)
+    return -2;
+  GatherKernel k = table[mode & 1][fl];
+  if (smem_bytes > 0) {
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess)
+      return -3;
+  }
+  k<<<grid, 256, smem_bytes > 0 ? smem_bytes : 0, static_cast<cudaStream_t>(stream)>>>(d_col, d_val, d_x, nnz, d_out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

@@ -43,6 +43,16 @@ struct __align__(16) TileDesc {
   int flags;      // bit 0: leading boundary split, bit 1: trailing boundary split
 };
 
+// Rows whose result is also stored into other GPUs' memory (fused halo push of the iterated multi-GPU loop):
+// for row in [row_lo[j], row_hi[j]) the epilogue stores y to dst[j][row] as well (dst is a peer-mapped pointer,
+// already offset so that it is indexed by the shard-local row).
+constexpr int kMaxPush = SPMV_B200_MAX_PUSH;
+struct PushArgs {
+  int count;
+  int row_lo[kMaxPush], row_hi[kMaxPush];
+  double *dst[kMaxPush];
+};
+
 // Arguments of the streaming kernels (passed by value).
 struct SpmvArgs {
   const int *__restrict__ rowptr;
@@ -59,6 +69,7 @@ struct SpmvArgs {
   int vec_div;  // MEDIUM: lanes per row = pow2ceil(avg / vec_div)
   int read_y;   // 0: beta == 0 and SPMV_B200_FLAG_BETA0_SKIP_Y
   int gather_na; // 1: x gathers use L1::no_allocate
+  PushArgs push;
 };
 
 struct FixupArgs {
@@ -70,6 +81,7 @@ struct FixupArgs {
   double alpha, beta;
   int nsplit;
   int read_y;
+  PushArgs push;
 };
 
 } // namespace b200
@@ -94,6 +106,8 @@ struct spmv_b200_plan {
   size_t persist_bytes = 0, max_window_bytes = 0; // L2 persistence for x (SPMV_B200_FLAG_L2_PERSIST_X)
   int persistent_grid[3] = {0, 0, 0}; // CTAs of the persistent kernels per tile kind
   int variant_short = 0, variant_medium = 0; // kernel variants (option flag bits 8-11 / 12-15)
+  bool mixed_queue_form = true;              // option flag bit 22 selects the segmented-sum form instead (A-B runs)
+  int mixed_threads = 256;                   // CTA size of the MIXED kernel (option flag bits 20-21 override)
   // device arrays owned by the plan
   int *tile_row = nullptr;
   int *tile_elem = nullptr;
@@ -129,7 +143,7 @@ int col_block_bitmap_run(long long nnz, const int *d_col, int n, int block_shift
 // kernels.cu
 int kernels_configure(spmv_b200_plan *p);
 int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y,
-                   cudaStream_t stream);
+                   cudaStream_t stream, const PushArgs *push = nullptr);
 // tiles [tile_lo, tile_hi) only; the plan must have no split rows (their partial sums cross tile ranges)
 int kernels_launch_tiles(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y, int tile_lo,
                          int tile_hi, cudaStream_t stream);

@@ -113,7 +113,7 @@ __device__ __forceinline__ TileDesc load_desc(const TileDesc *__restrict__ desc,
 // ---------------------------------------------------------------------------------------------------------------
 // tile streaming: global -> shared. Element i of the tile lives at smem index (i - a0), a0 = elem_begin & ~3.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool TMA>
+template <bool TMA, int NT = kThreads>
 __device__ __forceinline__ void tile_issue_loads(const SpmvArgs &a, int a0, int e0, int e1, double *sval, int *scol,
                                                  unsigned long long *bar, int tid) {
   const int span = e1 - a0;
@@ -137,12 +137,12 @@ __device__ __forceinline__ void tile_issue_loads(const SpmvArgs &a, int a0, int 
         mbar_arrive(bar);
       }
     }
-    for (int i = cnt + tid; i < span; i += kThreads) {
+    for (int i = cnt + tid; i < span; i += NT) {
       sval[i] = ld_stream_f64(a.val + a0 + i);
       scol[i] = ld_stream_s32(a.col + a0 + i);
     }
   } else {
-    for (int i = (e0 - a0) + tid; i < span; i += kThreads) {
+    for (int i = (e0 - a0) + tid; i < span; i += NT) {
       sval[i] = ld_stream_f64(a.val + a0 + i);
       scol[i] = ld_stream_s32(a.col + a0 + i);
     }
@@ -173,10 +173,15 @@ __device__ __forceinline__ void tile_issue_tma(const SpmvArgs &a, int a0, int e1
   }
 }
 
-__device__ __forceinline__ void store_y(const SpmvArgs &a, int row, double sum) {
-  // cli/verification.cpp:64  y[i] = alpha * y0 + beta * y[i]
-  const double yv = a.read_y ? a.y[row] : 0.0;
-  a.y[row] = a.alpha * sum + a.beta * yv;
+// the y store of every kernel: local store plus, for rows another GPU waits for, a store into that GPU's memory
+__device__ __forceinline__ void emit_y(double *__restrict__ y, const PushArgs &push, int row, double v) {
+  y[row] = v;
+  if (push.count) {
+#pragma unroll 1
+    for (int j = 0; j < push.count; ++j)
+      if (row >= push.row_lo[j] && row < push.row_hi[j])
+        push.dst[j][row] = v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -274,7 +279,7 @@ __device__ __forceinline__ void rows_tile(const SpmvArgs &a, const double *__res
         }
         const int r = rb + q * G + g;
         if (r < nr && l == 0) // cli/verification.cpp:64  y[i] = alpha * y0 + beta * y[i]
-          a.y[r0 + cb + r] = a.alpha * sum[q] + a.beta * yv[q];
+          emit_y(a.y, a.push, r0 + cb + r, a.alpha * sum[q] + a.beta * yv[q]);
       }
     }
     if (cb + kRowChunk >= nrows)
@@ -352,9 +357,10 @@ __global__ void __launch_bounds__(kThreads) k_spmv_rows_persistent(const SpmvArg
 // MIXED tiles
 // ---------------------------------------------------------------------------------------------------------------
 // deterministic CTA-wide sum of sval[lo, hi): strided per-thread partials, xor-shuffle tree, warp partials in order
+template <int NT>
 __device__ __forceinline__ double block_sum(const double *__restrict__ sval, int lo, int hi, double *swarp, int tid) {
   double s = 0.0;
-  for (int k = lo + tid; k < hi; k += kThreads)
+  for (int k = lo + tid; k < hi; k += NT)
     s += sval[k];
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1)
@@ -365,18 +371,21 @@ __device__ __forceinline__ double block_sum(const double *__restrict__ sval, int
   double total = 0.0;
   if (tid == 0) {
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w)
+    for (int w = 0; w < NT / 32; ++w)
       total += swarp[w];
   }
   __syncthreads();
   return total; // valid in thread 0
 }
 
-template <bool TMA>
-__global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
+// NT threads per CTA (64 / 128 / 256): small tiles run with small CTAs so that more independent CTAs are resident per
+// SM; the phases of one CTA (descriptor, tile, gathers, row sums) are dependent round trips to memory, and the number of
+// CTAs in different phases is what hides them.
+template <bool TMA, int NT>
+__global__ void __launch_bounds__(NT) k_spmv_mixed(const SpmvArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
-  __shared__ double swarp[kThreads / 32];
+  __shared__ double swarp[NT / 32];
   __shared__ int nlong, nmid;
   double *sval = reinterpret_cast<double *>(smem_raw);
   int *scol = reinterpret_cast<int *>(sval + a.cap);
@@ -396,8 +405,21 @@ __global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
   const bool has_tail = split_end && (r1 > r0);
   const int nrows = (r1 - r0) - (has_tail ? 1 : 0);
 
-  tile_issue_loads<TMA>(a, a0, e0, e1, sval, scol, &bar, tid);
+  tile_issue_loads<TMA, NT>(a, a0, e0, e1, sval, scol, &bar, tid);
   const int tail_start = d.tail_start; // first element of the tail fragment
+  // while the tile is in flight: row pointers of the first chunk of rows and the y values pass 1 will need
+  constexpr int kPre = kRowChunk / NT; // pass-1 iterations of a full chunk
+  double ypre[kPre];
+  {
+    const int nr0 = nrows < kRowChunk ? nrows : kRowChunk;
+    for (int i = tid; i <= nr0; i += NT)
+      srow[i] = __ldg(a.rowptr + r0 + i);
+#pragma unroll
+    for (int j = 0; j < kPre; ++j) {
+      const int r = tid + j * NT;
+      ypre[j] = (a.read_y && r < nr0) ? a.y[r0 + r] : 0.0;
+    }
+  }
   __syncthreads();
   if (TMA)
     mbar_wait(&bar, 0);
@@ -406,12 +428,12 @@ __global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
   // and indices are read into registers first because the compiler cannot prove that sval and scol do not alias.
   {
     const int end = e1 - a0;
-    for (int base = (e0 - a0) + tid; base < end; base += 8 * kThreads) {
+    for (int base = (e0 - a0) + tid; base < end; base += 8 * NT) {
       int c[8];
       double xv[8], v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int i = base + j * kThreads;
+        const int i = base + j * NT;
         c[j] = (i < end) ? scol[i] : -1;
       }
 #pragma unroll
@@ -419,12 +441,12 @@ __global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
         xv[j] = (c[j] >= 0) ? gather_x(a.x, c[j], a.gather_na) : 0.0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int i = base + j * kThreads;
+        const int i = base + j * NT;
         v[j] = (i < end) ? sval[i] : 0.0;
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int i = base + j * kThreads;
+        const int i = base + j * NT;
         if (i < end)
           sval[i] = v[j] * xv[j];
       }
@@ -433,12 +455,12 @@ __global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
   __syncthreads();
 
   if (split_begin) { // leading elements belong to a row that started in an earlier tile
-    const double s = block_sum(sval, e0 - a0, d.head_end - a0, swarp, tid);
+    const double s = block_sum<NT>(sval, e0 - a0, d.head_end - a0, swarp, tid);
     if (tid == 0)
       a.partials[2 * (size_t)t] = s;
   }
   if (has_tail) {
-    const double s = block_sum(sval, tail_start - a0, e1 - a0, swarp, tid);
+    const double s = block_sum<NT>(sval, tail_start - a0, e1 - a0, swarp, tid);
     if (tid == 0)
       a.partials[2 * (size_t)t + 1] = s;
   }
@@ -450,8 +472,10 @@ __global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
     if (nr > kRowChunk)
       nr = kRowChunk;
     __syncthreads(); // srow / queues reuse
-    for (int i = tid; i <= nr; i += kThreads)
-      srow[i] = __ldg(a.rowptr + r0 + cb + i);
+    if (cb > 0) {
+      for (int i = tid; i <= nr; i += NT)
+        srow[i] = __ldg(a.rowptr + r0 + cb + i);
+    }
     if (tid == 0) {
       nmid = 0;
       nlong = 0;
@@ -459,15 +483,19 @@ __global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
     __syncthreads();
     // pass 1: one thread per row sums rows of <= kSerialMax products; longer rows are queued by length class
     // (the value of a row does not depend on its queue position, only on its own fixed summation order)
-    for (int r = tid; r < nr; r += kThreads) {
+#pragma unroll
+    for (int j = 0; j < kPre; ++j) {
+      const int r = tid + j * NT;
+      if (r >= nr)
+        break;
       const int s = srow[r] - a0, e = srow[r + 1] - a0;
       const int len = e - s;
       if (len <= kSerialMax) {
-        const double yv = a.read_y ? a.y[r0 + cb + r] : 0.0; // requested before the sum is formed
+        const double yv = cb == 0 ? ypre[j] : (a.read_y ? a.y[r0 + cb + r] : 0.0);
         double sum = 0.0;
         for (int k = s; k < e; ++k)
           sum += sval[k];
-        a.y[r0 + cb + r] = a.alpha * sum + a.beta * yv;
+        emit_y(a.y, a.push, r0 + cb + r, a.alpha * sum + a.beta * yv);
       } else if (len <= kGroupMax) {
         smid[atomicAdd(&nmid, 1)] = r;
       } else {
@@ -477,7 +505,7 @@ __global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
     __syncthreads();
     // pass 2a: eight lanes per queued row of medium length
     const int nm = nmid;
-    for (int ib = 0; ib < nm; ib += kThreads / 8) {
+    for (int ib = 0; ib < nm; ib += NT / 8) {
       const int i = ib + grp;
       const bool act = i < nm;
       const int r = act ? smid[i] : 0;
@@ -490,11 +518,11 @@ __global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
       sum += __shfl_down_sync(0xffffffffu, sum, 2, 8);
       sum += __shfl_down_sync(0xffffffffu, sum, 1, 8);
       if (act && gl == 0)
-        a.y[r0 + cb + r] = a.alpha * sum + a.beta * yv;
+        emit_y(a.y, a.push, r0 + cb + r, a.alpha * sum + a.beta * yv);
     }
     // pass 2b: one warp per queued long row
     const int nl = nlong;
-    for (int i = warp; i < nl; i += kThreads / 32) {
+    for (int i = warp; i < nl; i += NT / 32) {
       const int r = slong[i];
       const int s = srow[r] - a0, e = srow[r + 1] - a0;
       const double yv = (lane == 0 && a.read_y) ? a.y[r0 + cb + r] : 0.0;
@@ -505,8 +533,228 @@ __global__ void __launch_bounds__(kThreads) k_spmv_mixed(const SpmvArgs a) {
       for (int off = 16; off > 0; off >>= 1)
         sum += __shfl_xor_sync(0xffffffffu, sum, off);
       if (lane == 0)
-        a.y[r0 + cb + r] = a.alpha * sum + a.beta * yv;
+        emit_y(a.y, a.push, r0 + cb + r, a.alpha * sum + a.beta * yv);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// MIXED tiles, segmented-sum form (option bit 22): cost per non-zero independent of the row-length distribution
+// ---------------------------------------------------------------------------------------------------------------
+// 1. products: thread `tid` forms the products of elements tid, tid + NT, ... (consecutive lanes gather for consecutive
+//    elements, all 8 gathers of a thread in flight before the first multiply) and writes them back in place with an
+//    XOR swizzle inside groups of 8, so that phase 2 reads 8 consecutive products per thread without bank conflicts.
+//    Elements of row fragments (rows split across tiles) are accumulated in registers instead and reduced CTA-wide
+//    into `partials` for the fix-up kernel.
+// 2. segmented sum: thread g owns the 8 consecutive products of group g. Rows that begin and end inside the group are
+//    finished by the thread alone; the piece in front of the first row end ("head") needs the sum of the open pieces
+//    of the preceding threads, which is a segmented scan (warp shuffles, then the 8 warp aggregates in order). The
+//    order of every addition is fixed by the tile geometry: results are bitwise reproducible.
+// 3. y: beta*y0 of the owned rows is staged in shared memory while the tile is in flight, each row's alpha*sum is
+//    added by the unique thread that finishes it, and the chunk is stored with coalesced writes.
+// Analogue of the reference's merge-path reduction (benchmark/merge-path/merge_path_reduction.h:80-136, block-wide
+// reduce-by-key) without its per-element binary search: one search per 8 elements.
+__device__ __forceinline__ int swz8(int i) { return i ^ ((i >> 4) & 7); }
+
+template <bool TMA, int NT>
+__global__ void __launch_bounds__(NT, 1536 / NT) k_spmv_seg(const SpmvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ double sfrag[2][NT / 32];
+  __shared__ double swv[NT / 32];
+  __shared__ int swf[NT / 32];
+  double *sval = reinterpret_cast<double *>(smem_raw);
+  double *sy = sval + a.cap;
+  int *scol = reinterpret_cast<int *>(sy + kRowChunk);
+  int *srow = scol + a.cap;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const TileDesc d = load_desc(a.desc, blockIdx.x);
+  const int t = d.tile;
+  const int r0 = d.r0, r1 = d.r1, e0 = d.e0, e1 = d.e1;
+  const int a0 = e0 & ~3;
+  const bool split_begin = (d.flags & 1) != 0;
+  const bool split_end = (d.flags & 2) != 0;
+  const bool has_tail = split_end && (r1 > r0); // the last owned row continues in the next tile
+  const int nrows = (r1 - r0) - (has_tail ? 1 : 0);
+
+  tile_issue_loads<TMA, NT>(a, a0, e0, e1, sval, scol, &bar, tid);
+  // while the tile is in flight: row pointers (as shared-memory indices) and beta*y0 of the first chunk of rows
+  {
+    const int nr0 = nrows < kRowChunk ? nrows : kRowChunk;
+    for (int i = tid; i <= nr0; i += NT)
+      srow[i] = __ldg(a.rowptr + r0 + i) - a0;
+    for (int i = tid; i < nr0; i += NT)
+      sy[i] = a.read_y ? a.beta * a.y[r0 + i] : 0.0; // cli/verification.cpp:64: y is read even when beta == 0
+  }
+  __syncthreads();
+  if (TMA)
+    mbar_wait(&bar, 0);
+
+  const int beg = e0 - a0, end = e1 - a0;
+  const int hend = split_begin ? d.head_end - a0 : beg; // head fragment [beg, hend): row r0-1 began in an earlier tile
+  const int tbeg = has_tail ? d.tail_start - a0 : end;  // tail fragment [tbeg, end): row r1-1 continues
+  double hacc = 0.0, tacc = 0.0;
+  for (int base = tid; base - lane < end; base += 8 * NT) { // warp-uniform trip count (there is a __syncwarp inside)
+    int c[8];
+    double xv[8], v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = base + j * NT;
+      c[j] = (i >= beg && i < end) ? scol[i] : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      xv[j] = (c[j] >= 0) ? gather_x(a.x, c[j], a.gather_na) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = (c[j] >= 0) ? sval[base + j * NT] : 0.0;
+    __syncwarp(); // every lane has read its values before any lane overwrites a slot of the same group
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = base + j * NT;
+      if (c[j] >= 0) {
+        const double pr = v[j] * xv[j];
+        if (i < hend)
+          hacc += pr;
+        else if (i >= tbeg)
+          tacc += pr;
+        else
+          sval[swz8(i)] = pr; // the 8 slots of a group are read and written by the same warp instruction
+      }
+    }
+  }
+  if (split_begin || has_tail) { // CTA-uniform
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      hacc += __shfl_xor_sync(0xffffffffu, hacc, off);
+      tacc += __shfl_xor_sync(0xffffffffu, tacc, off);
+    }
+    if (lane == 0) {
+      sfrag[0][warp] = hacc;
+      sfrag[1][warp] = tacc;
+    }
+  }
+  __syncthreads();
+  if ((split_begin || has_tail) && tid == 0) {
+    double h = 0.0, tl = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) {
+      h += sfrag[0][w];
+      tl += sfrag[1][w];
+    }
+    if (split_begin)
+      a.partials[2 * (size_t)t] = h;
+    if (has_tail)
+      a.partials[2 * (size_t)t + 1] = tl;
+  }
+
+  for (int cb = 0; cb < nrows; cb += kRowChunk) {
+    int nr = nrows - cb;
+    if (nr > kRowChunk)
+      nr = kRowChunk;
+    if (cb > 0) {
+      __syncthreads(); // the stores of the previous chunk have read sy
+      for (int i = tid; i <= nr; i += NT)
+        srow[i] = __ldg(a.rowptr + r0 + cb + i) - a0;
+      for (int i = tid; i < nr; i += NT)
+        sy[i] = a.read_y ? a.beta * a.y[r0 + cb + i] : 0.0;
+      __syncthreads();
+    }
+    const int lo = srow[0], hi = srow[nr]; // products of the complete rows of this chunk
+    const int g0 = lo >> 3;
+    const int ngroups = hi > lo ? ((hi + 7) >> 3) - g0 : 0;
+    double cv = 0.0; // open piece carried over from the previous round of groups
+    for (int gb = 0; gb < ngroups; gb += NT) {
+      const int g = g0 + gb + tid;
+      const int b = 8 * g > lo ? 8 * g : lo, e = 8 * g + 8 < hi ? 8 * g + 8 : hi;
+      bool f = false; // this group contains a row end
+      double head = 0.0, acc = 0.0;
+      int hrow = 0;
+      if (b < e) {
+        int r = 0, rh = nr; // row that owns element b: the last r with srow[r] <= b (empty rows in front are skipped)
+        while (rh - r > 1) {
+          const int mid = (r + rh) >> 1;
+          if (srow[mid] <= b)
+            r = mid;
+          else
+            rh = mid;
+        }
+        int rend = srow[r + 1];
+        const int sw = (g >> 1) & 7;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int idx = 8 * g + k;
+          if (idx >= b && idx < e) {
+            acc += sval[8 * g + (k ^ sw)];
+            if (idx + 1 == rend) {
+              if (!f) {
+                f = true;
+                head = acc;
+                hrow = r;
+              } else {
+                sy[r] = fma(a.alpha, acc, sy[r]); // the row began and ended inside this group
+              }
+              acc = 0.0;
+              if (++r < nr) {
+                rend = srow[r + 1];
+                if (rend == idx + 1) { // empty rows follow: continue with the last row that starts at idx + 1
+                  rh = nr;
+                  while (rh - r > 1) {
+                    const int mid = (r + rh) >> 1;
+                    if (srow[mid] <= idx + 1)
+                      r = mid;
+                    else
+                      rh = mid;
+                  }
+                  rend = srow[r + 1];
+                }
+              }
+            }
+          }
+        }
+      }
+      // segmented inclusive scan of (f, open piece) over the lanes; the piece of a lane with a row end restarts the sum
+      double v = acc;
+      int ff = f ? 1 : 0;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const double vv = __shfl_up_sync(0xffffffffu, v, off);
+        const int fo = __shfl_up_sync(0xffffffffu, ff, off);
+        if (lane >= off) {
+          if (!ff)
+            v = vv + v;
+          ff |= fo;
+        }
+      }
+      double ev = __shfl_up_sync(0xffffffffu, v, 1);
+      int ef = __shfl_up_sync(0xffffffffu, ff, 1);
+      if (lane == 0) {
+        ev = 0.0;
+        ef = 0;
+      }
+      if (lane == 31) {
+        swv[warp] = v;
+        swf[warp] = ff;
+      }
+      __syncthreads();
+      double wv = cv; // open piece in front of this warp: earlier rounds, then the aggregates of the warps before it
+      for (int w = 0; w < warp; ++w)
+        wv = swf[w] ? swv[w] : wv + swv[w];
+      if (f)
+        sy[hrow] = fma(a.alpha, (ef ? ev : wv + ev) + head, sy[hrow]);
+      if (gb + NT < ngroups) { // another round follows: carry the open piece of the whole CTA
+        double nv = cv;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w)
+          nv = swf[w] ? swv[w] : nv + swv[w];
+        __syncthreads(); // swv / swf are rewritten by the next round
+        cv = nv;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < nr; i += NT)
+      emit_y(a.y, a.push, r0 + cb + i, sy[i]);
   }
 }
 
@@ -529,7 +777,7 @@ __global__ void __launch_bounds__(kThreads) k_fixup(const FixupArgs f) {
     sum += __shfl_xor_sync(0xffffffffu, sum, off);
   if (lane == 0) {
     const double yv = f.read_y ? f.y[row] : 0.0;
-    f.y[row] = f.alpha * sum + f.beta * yv;
+    emit_y(f.y, f.push, row, f.alpha * sum + f.beta * yv);
   }
 }
 
@@ -544,8 +792,10 @@ static int cap_for(const spmv_b200_plan *p, int kind) {
 static size_t smem_for(const spmv_b200_plan *p, int kind, bool persistent = false) {
   const int cap = cap_for(p, kind);
   size_t b = (size_t)cap * 12 * (persistent ? 2 : 1) + sizeof(int) * (kRowChunk + 1);
-  if (kind == SPMV_B200_KIND_MIXED)
-    b += 2 * sizeof(int) * ((size_t)cap / (kSerialMax + 1) + 8);
+  if (kind == SPMV_B200_KIND_MIXED) { // segmented form: beta*y0 of a row chunk; queue form (tuning bit 22): two row queues
+    const size_t seg = sizeof(double) * kRowChunk, queues = 2 * sizeof(int) * ((size_t)cap / (kSerialMax + 1) + 8);
+    b += seg > queues ? seg : queues;
+  }
   return (b + 15) & ~(size_t)15;
 }
 
@@ -570,6 +820,21 @@ static const RowsVariant kMediumVariants[] = {
 };
 constexpr int kNumShortVariants = sizeof(kShortVariants) / sizeof(kShortVariants[0]);
 constexpr int kNumMediumVariants = sizeof(kMediumVariants) / sizeof(kMediumVariants[0]);
+
+static RowsKernel mixed_kernel(bool tma, int threads, bool queue_form = false) {
+  if (!queue_form) {
+    switch (threads) {
+    case 64: return tma ? k_spmv_seg<true, 64> : k_spmv_seg<false, 64>;
+    case 128: return tma ? k_spmv_seg<true, 128> : k_spmv_seg<false, 128>;
+    default: return tma ? k_spmv_seg<true, 256> : k_spmv_seg<false, 256>;
+    }
+  }
+  switch (threads) {
+  case 64: return tma ? k_spmv_mixed<true, 64> : k_spmv_mixed<false, 64>;
+  case 128: return tma ? k_spmv_mixed<true, 128> : k_spmv_mixed<false, 128>;
+  default: return tma ? k_spmv_mixed<true, 256> : k_spmv_mixed<false, 256>;
+  }
+}
 
 template <typename K> static int set_smem(K kernel, size_t bytes) {
   B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -602,6 +867,17 @@ int kernels_configure(spmv_b200_plan *p) {
     p->persist_bytes = (size_t)persist_max;
     p->max_window_bytes = (size_t)window_max;
   }
+  // CTA size of the MIXED kernel: 8 items per thread (one batch of gathers), option bits 20-21 override (tuning)
+  p->mixed_threads = p->T <= 512 ? 64 : (p->T <= 1024 ? 128 : 256);
+  switch ((p->flags >> 20) & 3u) {
+  case 1: p->mixed_threads = 64; break;
+  case 2: p->mixed_threads = 128; break;
+  case 3: p->mixed_threads = 256; break;
+  default: break;
+  }
+  // tuning bit 22 selects the segmented-sum form of the MIXED kernel; the length-class-queue form is the default: the
+  // segmented form needs 6 resident CTAs, whose shared memory leaves too little L1 for the gathers (profiles/)
+  p->mixed_queue_form = ((p->flags >> 22) & 1u) == 0;
   p->variant_short = (int)((p->flags >> 8) & 0xf);
   p->variant_medium = (int)((p->flags >> 12) & 0xf);
   if (p->variant_short >= kNumShortVariants || p->variant_medium >= kNumMediumVariants) {
@@ -616,8 +892,8 @@ int kernels_configure(spmv_b200_plan *p) {
       (rc = set_smem(vm.persistent, smem_for(p, SPMV_B200_KIND_MEDIUM, true))) ||
       (rc = set_smem(vm.tma, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
       (rc = set_smem(vm.plain, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
-      (rc = set_smem(k_spmv_mixed<true>, smem_for(p, SPMV_B200_KIND_MIXED))) ||
-      (rc = set_smem(k_spmv_mixed<false>, smem_for(p, SPMV_B200_KIND_MIXED))))
+      (rc = set_smem(mixed_kernel(true, p->mixed_threads, p->mixed_queue_form), smem_for(p, SPMV_B200_KIND_MIXED))) ||
+      (rc = set_smem(mixed_kernel(false, p->mixed_threads, p->mixed_queue_form), smem_for(p, SPMV_B200_KIND_MIXED))))
     return rc;
   // persistent kernels: one wave of CTAs, as many as fit on the device
   int sms = 0;
@@ -643,10 +919,10 @@ int kernels_configure(spmv_b200_plan *p) {
 // data of an SpMV; value / colindex are streamed with evict-first). The window is a per-launch attribute, so the
 // caller's stream state is not modified.
 static cudaError_t launch_spmv(RowsKernel k, int grid, size_t smem, cudaStream_t stream, const SpmvArgs &a,
-                               const spmv_b200_plan *p) {
+                               const spmv_b200_plan *p, int threads = kThreads) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3((unsigned)threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -676,7 +952,7 @@ static void kind_range(const spmv_b200_plan *p, int k, int tile_lo, int tile_hi,
 }
 
 static int launch_range(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y, int tile_lo,
-                        int tile_hi, bool with_fixup, cudaStream_t stream) {
+                        int tile_hi, bool with_fixup, cudaStream_t stream, const PushArgs *push = nullptr) {
   if (p->m == 0)
     return SPMV_B200_OK;
   SpmvArgs a;
@@ -694,6 +970,10 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
   a.gather_na = (p->flags & (1u << 16)) ? 2 : ((p->flags & SPMV_B200_FLAG_GATHER_NO_L1) ? 1 : 0);
   a.read_y = (beta == 0.0 && (p->flags & SPMV_B200_FLAG_BETA0_SKIP_Y)) ? 0 : 1;
   a.ntiles = 0;
+  if (push)
+    a.push = *push;
+  else
+    a.push.count = 0;
 
   const bool tma = p->uses_tma;
   const bool persistent = (p->flags & SPMV_B200_FLAG_PERSISTENT) != 0;
@@ -710,7 +990,8 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
     a.cap = cap_for(p, k);
     a.ntiles = hi - lo;
     if (k == SPMV_B200_KIND_MIXED) {
-      B200_CUDA(launch_spmv(tma ? k_spmv_mixed<true> : k_spmv_mixed<false>, a.ntiles, smem_for(p, k), stream, a, p));
+      B200_CUDA(launch_spmv(mixed_kernel(tma, p->mixed_threads, p->mixed_queue_form), a.ntiles, smem_for(p, k), stream, a, p,
+                            p->mixed_threads));
       continue;
     }
     const RowsVariant &v = k == SPMV_B200_KIND_SHORT ? kShortVariants[p->variant_short]
@@ -733,6 +1014,7 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
     f.beta = beta;
     f.nsplit = p->nsplit;
     f.read_y = a.read_y;
+    f.push = a.push;
     const int warps_per_cta = kThreads / 32;
     k_fixup<<<(p->nsplit + warps_per_cta - 1) / warps_per_cta, kThreads, 0, stream>>>(f);
   }
@@ -741,8 +1023,8 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
 }
 
 int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y,
-                   cudaStream_t stream) {
-  return launch_range(p, alpha, beta, x, y, 0, p->ntiles, true, stream);
+                   cudaStream_t stream, const PushArgs *push) {
+  return launch_range(p, alpha, beta, x, y, 0, p->ntiles, true, stream, push);
 }
 
 int kernels_launch_tiles(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y, int tile_lo,

@@ -87,6 +87,12 @@ class PowerLoop:
     need_local: np.ndarray  # uint8 [nblocks]: blocks of x this rank references
     exchange: str = "auto"
     block_shift: int = BLOCK_SHIFT
+    # optional overlap of the halo exchange with the rows nobody waits for:
+    spmv_tiles: Optional[Callable] = None   # spmv_tiles(x_full, y_slice, tile_lo, tile_hi): row blocks of the shard
+    tile_row: Optional[np.ndarray] = None   # [ntiles+1] first local row of each row block
+    overlap: bool = True
+    boundary: list = field(default_factory=list)   # tile ranges whose rows are sent to other ranks
+    interior: list = field(default_factory=list)   # the remaining tile ranges
     sends: list = field(default_factory=list)
     recvs: list = field(default_factory=list)
     mode: str = ""
@@ -99,11 +105,10 @@ class PowerLoop:
         if self.world == 1:
             self.mode = "none"
             return
-        mine = torch.from_numpy(np.ascontiguousarray(self.need_local)).to(self.x.device)
-        allneed = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=self.x.device)
-        dist.all_gather_into_tensor(allneed, mine) if self.x.is_cuda else dist.all_gather(
-            list(allneed.view(self.world, -1).unbind(0)), mine)
-        need = allneed.view(self.world, -1).cpu().numpy()
+        # set-up only: the bitmaps travel as host objects, so any backend (nccl, gloo) works
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, np.ascontiguousarray(self.need_local, dtype=np.uint8))
+        need = np.stack(gathered)
         self.sends, self.recvs = exchange_schedule(need, self.bounds, self.rank, self.block_shift)
         halo_in = sum(e - a for _, a, e in self.recvs) * 8
         full_in = (self.n - int(self.bounds[self.rank + 1] - self.bounds[self.rank])) * 8
@@ -113,6 +118,33 @@ class PowerLoop:
         else:
             self.mode = self.exchange
         self.bytes_in_per_iter = halo_in if self.mode == "halo" else full_in
+        self._plan_overlap()
+
+    def _plan_overlap(self):
+        """Row blocks that produce rows another rank needs are computed first; their exchange then runs on a second
+        stream while the rest of the shard is multiplied."""
+        self.overlapped = False
+        if not (self.overlap and self.mode == "halo" and self.spmv_tiles is not None and self.tile_row is not None):
+            return
+        tr = np.asarray(self.tile_row, dtype=np.int64)
+        nt = tr.size - 1
+        lo = int(self.bounds[self.rank])
+        marks = np.zeros(nt, dtype=bool)
+        for _, a, e in self.sends:
+            t0 = int(np.searchsorted(tr, a - lo, side="right")) - 1
+            t1 = int(np.searchsorted(tr, e - lo, side="left"))
+            marks[max(t0, 0):min(t1, nt)] = True
+        if nt == 0 or marks.sum() * 2 > nt:
+            return  # most of the shard is boundary: nothing to hide the exchange behind
+        edges = np.flatnonzero(np.diff(np.concatenate(([False], marks, [False])).astype(np.int8)))
+        self.boundary = [(int(edges[i]), int(edges[i + 1])) for i in range(0, edges.size, 2)]
+        inv = ~marks
+        edges = np.flatnonzero(np.diff(np.concatenate(([False], inv, [False])).astype(np.int8)))
+        self.interior = [(int(edges[i]), int(edges[i + 1])) for i in range(0, edges.size, 2)]
+        self.overlapped = True
+        if self.x.is_cuda:
+            import torch
+            self.comm_stream = torch.cuda.Stream()
 
     def _exchange(self, v):
         dist = _dist()
@@ -130,15 +162,135 @@ class PowerLoop:
 
     def step(self):
         lo, hi = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
-        self.spmv(self.x, self.x_next[lo:hi])
-        if self.world > 1:
-            self._exchange(self.x_next)
+        if self.world > 1 and getattr(self, "overlapped", False):
+            ys = self.x_next[lo:hi]
+            for t0, t1 in self.boundary:
+                self.spmv_tiles(self.x, ys, t0, t1)
+            if self.x.is_cuda:
+                import torch
+                cur = torch.cuda.current_stream()
+                self.comm_stream.wait_event(cur.record_event())
+                with torch.cuda.stream(self.comm_stream):
+                    self._exchange(self.x_next)
+                    done = self.comm_stream.record_event()
+                for t0, t1 in self.interior:
+                    self.spmv_tiles(self.x, ys, t0, t1)
+                cur.wait_event(done)
+            else:
+                self._exchange(self.x_next)
+                for t0, t1 in self.interior:
+                    self.spmv_tiles(self.x, ys, t0, t1)
+        else:
+            self.spmv(self.x, self.x_next[lo:hi])
+            if self.world > 1:
+                self._exchange(self.x_next)
         self.x, self.x_next = self.x_next, self.x
 
     def run(self, iters: int):
         for _ in range(iters):
             self.step()
         return self.x
+
+    def capture(self):
+        """Captures two iterations (one ping-pong period of the x buffers) into a CUDA graph: the kernels, the grouped
+        NCCL send/recv and the stream fork/join are then replayed without any host work in the loop."""
+        import torch
+        assert self.x.is_cuda
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up outside the capture (NCCL connections, lazy module loading)
+            self.step()
+            self.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.step()
+            self.step()
+        return self.graph
+
+    def run_graph(self, iters: int):
+        """Replays the captured pair of iterations iters/2 times (iters must be even)."""
+        assert iters % 2 == 0 and getattr(self, "graph", None) is not None
+        for _ in range(iters // 2):
+            self.graph.replay()
+        return self.x
+
+
+class FusedHaloLoop:
+    """x <- A*x with the halo exchange fused into the SpMV kernels: the epilogue of the kernels stores the rows a
+    neighbour references straight into that neighbour's copy of the next x (peer memory mapped through CUDA IPC,
+    NVLink stores), and iterations of neighbouring GPUs are ordered with stream-ordered flags
+    (cuStreamWriteValue32 / cuStreamWaitValue32) instead of a collective: one kernel launch per iteration, no NCCL
+    kernel, no host synchronisation. Double buffering: iteration k reads buf[k % 2] and writes buf[(k+1) % 2] here
+    and in the neighbours; a rank starts iteration k only after every neighbour has raised its flag to k, which means
+    the neighbour's rows for x_k have arrived and the neighbour no longer reads the buffer about to be overwritten."""
+
+    def __init__(self, base: PowerLoop, plan):
+        import torch
+        from . import PeerBuffer
+        dist = _dist()
+        assert base.world > 1 and base.x.is_cuda
+        self.base, self.plan = base, plan
+        self.rank, self.world = base.rank, base.world
+        self.lo, self.hi = int(base.bounds[self.rank]), int(base.bounds[self.rank + 1])
+        self.neigh = sorted({p for p, _, _ in base.sends} | {p for p, _, _ in base.recvs})
+        if len(base.sends) > _lib_max_push():
+            raise RuntimeError("too many push ranges for the fused halo exchange")
+        # one exported allocation per rank: [x buffer 0 | x buffer 1 | flags], opened by the neighbours with THEIR
+        # device current (that is what maps it for their kernels; a torch-IPC tensor is mapped for the owner's device)
+        n = base.n
+        self.xbytes = (8 * n + 255) // 256 * 256
+        self.own = PeerBuffer.alloc(2 * self.xbytes + 4 * self.world)
+        self.bufs = [self.own.tensor("float64", n, 0), self.own.tensor("float64", n, self.xbytes)]
+        self.flags = self.own.tensor("int32", self.world, 2 * self.xbytes)
+        self.bufs[0].copy_(base.x)
+        torch.cuda.synchronize()
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, (self.own.handle, self.own.nbytes))
+        self.peer = {p: PeerBuffer.open(*everyone[p]) for p in self.neigh}
+        # push descriptors for both buffer parities: destination = neighbour's buffer, indexed by my local row
+        self.push = [[(a - self.lo, e - self.lo, self.peer[p].address + b * self.xbytes + 8 * self.lo)
+                      for p, a, e in base.sends] for b in (0, 1)]
+        self.k = 0
+        dist.barrier()
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        _dist().barrier()
+        for pb in self.peer.values():
+            pb.release()
+        self.peer = {}
+        _dist().barrier()
+        self.bufs, self.flags = [], None
+        self.own.release()
+
+    def step(self):
+        from . import stream_wait_flag, stream_write_flag
+        k = self.k
+        if k > 0:
+            for p in self.neigh:  # neighbour p has finished iteration k-1
+                stream_wait_flag(self.flags.data_ptr() + 4 * p, k)
+        src, dst = self.bufs[k % 2], self.bufs[(k + 1) % 2]
+        self.plan.execute_push(1.0, 0.0, src, dst[self.lo:self.hi], self.push[(k + 1) % 2])
+        for p in self.neigh:
+            stream_write_flag(self.peer[p].address + 2 * self.xbytes + 4 * self.rank, k + 1)
+        self.k = k + 1
+
+    def run(self, iters: int):
+        for _ in range(iters):
+            self.step()
+        return self.x
+
+    @property
+    def x(self):
+        return self.bufs[self.k % 2]
+
+
+def _lib_max_push() -> int:
+    from . import _lib
+    return _lib.MAX_PUSH
 
 
 def bits_checksum(t) -> int:
@@ -147,7 +299,7 @@ def bits_checksum(t) -> int:
     return int(t.view(torch.int64).sum().item())
 
 
-def build_stencil3d_power_loop(N: int, exchange: str = "auto", options=None):
+def build_stencil3d_power_loop(N: int, exchange: str = "auto", options=None, overlap: bool = True):
     """Rank-local pieces of the C5 configuration: 27-point averaging stencil on an N^3 grid, rows sharded by nnz."""
     import torch
     from . import CsrDesc, SpmvPlan, col_block_bitmap, make_options, shard_bounds, synth, FLAG_BETA0_SKIP_Y
@@ -173,16 +325,24 @@ def build_stencil3d_power_loop(N: int, exchange: str = "auto", options=None):
     def spmv(xf, ys):
         plan.execute(1.0, 0.0, xf, ys)
 
-    loop = PowerLoop(n=n, bounds=bounds, spmv=spmv, x=x, x_next=x_next, need_local=need, exchange=exchange)
+    def spmv_tiles(xf, ys, t0, t1):
+        plan.execute_tiles(1.0, 0.0, xf, ys, t0, t1)
+
+    info = plan.info()
+    can_split = info.nsplit_rows == 0 and world > 1
+    loop = PowerLoop(n=n, bounds=bounds, spmv=spmv, x=x, x_next=x_next, need_local=need, exchange=exchange,
+                     spmv_tiles=spmv_tiles if can_split else None,
+                     tile_row=plan.export("tile_row") if can_split else None, overlap=overlap)
     return loop, plan, csr
 
 
-def bench_power_loop(N: int = 384, iters: int = 100, exchange: str = "auto", warmup: int = 3) -> dict:
+def bench_power_loop(N: int = 384, iters: int = 100, exchange: str = "auto", warmup: int = 4,
+                     overlap: bool = True, graph: bool = False, fused: bool = True) -> dict:
     """Times `iters` iterations of x <- A*x for the 27-point N^3 stencil on all ranks (device events, max over ranks)."""
     import torch
     dist = _dist()
     rank, world = world_info()
-    loop, plan, csr = build_stencil3d_power_loop(N, exchange)
+    loop, plan, csr = build_stencil3d_power_loop(N, exchange, overlap=overlap)
     nnz_local = csr.nnz
 
     def sync():
@@ -191,11 +351,34 @@ def bench_power_loop(N: int = 384, iters: int = 100, exchange: str = "auto", war
             dist.barrier()
         torch.cuda.synchronize()
 
-    loop.run(warmup)
+    # the same number of iterations runs in every mode, so the checksums of x stay comparable
+    warmup = max(4, warmup + warmup % 2)
+    iters += iters % 2
+    fused = bool(fused and world > 1 and loop.mode == "halo" and not graph)
+    runner = loop
+    fused_error = ""
+    if fused:
+        try:
+            runner = FusedHaloLoop(loop, plan)
+        except Exception as e:  # no peer path / IPC unavailable: keep the NCCL send/recv exchange
+            fused = False
+            fused_error = f"{type(e).__name__}: {e}"
+    if fused:
+        runner.run(warmup)
+    elif graph:
+        loop.capture()            # two eager iterations, then the capture of two more (not executed)
+        loop.run_graph(warmup - 2)
+    else:
+        loop.run(warmup)
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    loop.run(iters)
+    if fused:
+        runner.run(iters)
+    elif graph:
+        loop.run_graph(iters)
+    else:
+        loop.run(iters)
     e1.record()
     e1.synchronize()
     sync()
@@ -217,11 +400,20 @@ def bench_power_loop(N: int = 384, iters: int = 100, exchange: str = "auto", war
         "scaling": "strong", "n_gpus": world, "iters": iters, "ms_per_iter": sec_iter * 1e3,
         "value": 2.0 * nnz_total / sec_iter / 1e9, "unit": "GFLOP/s",
         "effective_gbs": (12 * nnz_total + 4 * (n + 1) + 8 * n + 16 * n) / sec_iter / 1e9,
-        "exchange": loop.mode, "exchange_bytes_in_per_iter_rank0": loop.bytes_in_per_iter,
+        "exchange": ("halo, pushed by the SpMV kernels into peer memory (NVLink stores) + stream-ordered flags"
+                     if fused else loop.mode), "exchange_bytes_in_per_iter_rank0": loop.bytes_in_per_iter,
+        "cuda_graph": bool(graph),
+        "exchange_overlapped_with_interior_rows": bool(getattr(loop, "overlapped", False)),
+        "boundary_row_blocks_rank0": int(sum(b - a for a, b in loop.boundary)),
         # bit pattern checksum of x[0 : n/16] after the last iteration: that range belongs to rank 0 for every
         # world size <= 8, so equal values across runs with 1/2/4/8 GPUs prove bitwise-identical results
-        "x_checksum_first_16th": bits_checksum(loop.x[0:n // 16]),
+        "x_checksum_first_16th": bits_checksum(runner.x[0:n // 16]),
+        "halo_fused_into_kernel": bool(fused),
         "total_timed_ms": ms,
     }
+    if fused:
+        runner.close()
+    elif fused_error:
+        out["halo_fused_error"] = fused_error
     plan.destroy()
     return out

@@ -59,9 +59,21 @@ def _worker(rank, world, port, mode, N, iters, out_dir):
         y = oracle.port_host_spmv(1.0, 0.0, shard.rowptr, shard.col, shard.val, xf.numpy(), np.zeros(hi - lo))
         ys.copy_(torch.from_numpy(y))
 
+    # row blocks of ~97 rows: lets the halo mode compute the rows other ranks wait for first (overlap path)
+    tile_row = np.unique(np.concatenate([np.arange(0, hi - lo, 97), [hi - lo]])).astype(np.int64)
+
+    def spmv_tiles(xf, ys, t0, t1):
+        a, b = int(tile_row[t0]), int(tile_row[t1])
+        sub_rp = shard.rowptr[a:b + 1] - shard.rowptr[a]
+        sl = slice(int(shard.rowptr[a]), int(shard.rowptr[b]))
+        y = oracle.port_host_spmv(1.0, 0.0, sub_rp, shard.col[sl], shard.val[sl], xf.numpy(), np.zeros(b - a))
+        ys[a:b].copy_(torch.from_numpy(y))
+
     x = torch.from_numpy(synth.vector_numpy(n, 2).copy())
     loop = sharded.PowerLoop(n=n, bounds=bounds, spmv=spmv, x=x, x_next=torch.zeros_like(x), need_local=need,
-                             exchange=mode, block_shift=shift)
+                             exchange=mode, block_shift=shift, spmv_tiles=spmv_tiles, tile_row=tile_row)
+    if mode == "halo":
+        assert loop.overlapped and loop.boundary and loop.interior
     xf = loop.run(iters)
     np.save(Path(out_dir) / f"x_{mode}_{rank}.npy", xf[lo:hi].numpy())
     np.save(Path(out_dir) / f"meta_{mode}_{rank}.npy", np.array([lo, hi, loop.bytes_in_per_iter]))
