@@ -43,6 +43,10 @@ extern "C" {
                                        /* that NaN/Inf in y propagate exactly like cli/verification.cpp:64  */
 #define SPMV_B200_FLAG_GATHER_NO_L1 8u /* gather x with L1::no_allocate                                             */
 #define SPMV_B200_FLAG_PERSISTENT 0x20000u /* row kernels as persistent CTAs with a two-stage TMA ring              */
+#define SPMV_B200_FLAG_DIRECT 0x40u    /* force the direct form: one warp per row block, value / colindex              */
+                                       /* streamed straight into registers, no shared memory (all of the unified      */
+                                       /* L1/shared array stays L1 for the x gathers); automatic for irregular gathers */
+#define SPMV_B200_FLAG_NO_DIRECT 0x80u /* never use the direct form                                                   */
 #define SPMV_B200_FLAG_L2_PERSIST_X 4u /* mark x as persisting in L2 for the SpMV launches (irregular gathers)      */
 
 /* row bins (by nnz per row) and tile kinds (which per-bin kernel streams a row block) */
@@ -67,6 +71,7 @@ typedef struct spmv_b200_plan_info {
   int32_t tiles_per_kind[3]; /* SHORT / MEDIUM / MIXED                                           */
   int32_t nsplit_rows;       /* rows whose partial sums are combined by the fix-up kernel       */
   int32_t launches_per_execute;
+  int32_t direct;            /* 1 if the direct (warp-per-row-block, no shared memory) form is used */
   int64_t bin_rows[4];       /* rows per bin: short / medium / long / very long                 */
   int64_t bin_nnz[4];        /* nnz per bin                                                      */
   int64_t gather_active;     /* sampled gathers (lanes) of the gather-coalescing statistic      */
@@ -84,7 +89,11 @@ enum {
   SPMV_B200_EXPORT_TILE_PART = 4,  /* int32 [ntiles+1]  largest r with rowptr[r] <= t*T (merge-path partition)       */
   SPMV_B200_EXPORT_ROW_BIN = 5,    /* uint8 [m]         SPMV_B200_BIN_* per row                                      */
   SPMV_B200_EXPORT_SPLIT_ROWS = 6, /* int32 [3*nsplit]  (row, first tile, last tile) per split row                   */
-  SPMV_B200_EXPORT_TILE_MAXLEN = 7 /* int32 [ntiles]    longest row owned by each tile                               */
+  SPMV_B200_EXPORT_TILE_MAXLEN = 7, /* int32 [ntiles]    longest row owned by each tile                               */
+  /* direct form only (empty otherwise): */
+  SPMV_B200_EXPORT_ROW_START_BITS = 8, /* uint32 [ceil(rowptr[m]/32)] bit k set iff element k is the first of its row */
+  SPMV_B200_EXPORT_NZ_ROWS = 9,        /* int32 [non-empty rows]      their ids, ascending                           */
+  SPMV_B200_EXPORT_TILE_NZBASE = 10    /* int32 [ntiles]              number of non-empty rows in front of each tile  */
 };
 
 /* Fused halo push: rows [row_lo[j], row_hi[j]) of y are also stored to dst[j][row] (device pointers, typically

@@ -17,7 +17,7 @@ REFERENCE = Path("/root/reference")
 __all__ = [
     "build", "have_ref", "port_host_spmv", "port_host_spmv_ax", "port_verify_y", "port_verify", "port_row_bound",
     "port_generate_vector", "port_merge_path_partition", "port_flat_break_points_v2", "port_analysis",
-    "port_shard_bounds", "port_gather_stat", "port_tiled_spmv", "ref_host_spmv", "ref_host_spmv_ax", "ref_verify_y",
+    "port_shard_bounds", "port_gather_stat", "port_tiled_spmv", "port_direct_arrays", "ref_host_spmv", "ref_host_spmv_ax", "ref_verify_y",
     "ref_adaptive_plus_analyze", "ref_read", "ref_generate_vector", "best_host_spmv", "check_rows",
 ]
 
@@ -235,6 +235,24 @@ def port_analysis(rowptr, tile_nnz=2048, short_max=8, medium_max=128):
         "tile_part": tile_part, "tile_maxlen": tile_maxlen, "tile_kind": tile_kind, "row_bin": row_bin,
         "bin_rows": bin_rows, "bin_nnz": bin_nnz, "nsplit": ns, "split_rows": split_rows,
     }
+
+
+def port_direct_arrays(rowptr, tile_row):
+    """CPU restatement (numpy, integer only) of the extra analysis arrays of the direct form
+    (spmv_acc_b200/csrc/analysis.cu: k_row_start_bits, k_nz_rows, k_desc_direct): row-start bit flags over the absolute
+    element index, the ascending list of non-empty rows, and the number of non-empty rows in front of every tile.
+    These play the role of the reference's per-block row bookkeeping (hip-flat break points, flat_imp.inl:107-152;
+    merge-path S[t], merge_path_partition.h:7-17) for a kernel that never searches row pointers per element."""
+    rowptr = _c(rowptr, _i32).astype(np.int64)
+    lens = np.diff(rowptr)
+    nz_rows = np.flatnonzero(lens > 0).astype(_i32)
+    end = int(rowptr[-1]) if rowptr.size else 0
+    bits = np.zeros((end + 31) // 32, np.uint32)
+    starts = rowptr[:-1][lens > 0]
+    np.bitwise_or.at(bits, starts >> 5, (np.uint32(1) << (starts & 31).astype(np.uint32)))
+    tile_row = np.asarray(tile_row, dtype=np.int64)
+    nzbase = np.searchsorted(nz_rows, tile_row[:-1], side="left").astype(_i32)
+    return {"row_start_bits": bits, "nz_rows": nz_rows, "tile_nzbase": nzbase}
 
 
 def port_gather_stat(rowptr, col, medium_max=128):

@@ -33,6 +33,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cub/device/device_scan.cuh>
+
 #include "internal.cuh"
 
 namespace b200 {
@@ -211,6 +213,42 @@ __global__ void __launch_bounds__(256)
   d.tail_start = ((d.flags & 2) && d.r1 > d.r0) ? __ldg(rowptr + d.r1 - 1) : d.e1;
   d.tile = t;
   desc[t] = d;
+}
+
+// ---- direct form (one warp per row block, no shared memory): row-start bit flags, non-empty row list ----
+// bits[k >> 5] bit (k & 31) is set iff element k (absolute index into value / colindex) is the first element of a row;
+// nzflag[r] = 1 iff row r is non-empty (nzflag[m] = 0 so that the exclusive scan yields the total at index m).
+__global__ void __launch_bounds__(256) k_row_start_bits(const int *__restrict__ rowptr, int m,
+                                                         unsigned int *__restrict__ bits, int *__restrict__ nzflag) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r <= m; r += (long long)gridDim.x * blockDim.x) {
+    int f = 0;
+    if (r < m) {
+      const int s = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+      if (e > s) {
+        f = 1;
+        atomicOr(bits + (s >> 5), 1u << (s & 31)); // integer OR: order independent
+      }
+    }
+    nzflag[r] = f;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_nz_rows(const int *__restrict__ nzflag, const int *__restrict__ nzprefix,
+                                                  int m, int *__restrict__ nz_rows) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += (long long)gridDim.x * blockDim.x)
+    if (nzflag[r])
+      nz_rows[nzprefix[r]] = (int)r;
+}
+
+__global__ void __launch_bounds__(256) k_desc_direct(int ntiles, const TileDesc *__restrict__ all,
+                                                      const int *__restrict__ nzprefix,
+                                                      TileDesc *__restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles)
+    return;
+  TileDesc d = all[t];
+  d.head_end = nzprefix[d.r0]; // number of non-empty rows in front of the tile (r0 <= m)
+  out[t] = d;
 }
 
 __global__ void __launch_bounds__(256) k_gather_desc(const int *__restrict__ list, int n,
@@ -392,6 +430,36 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
   k_tile_desc<<<grid_for(ntiles, 256, 1 << 30), 256, 0, stream>>>(p->rowptr, ntiles, p->tile_row, p->tile_elem,
                                                                    p->tile_split, p->desc_all);
   B200_CUDA(cudaGetLastError());
+  if (p->direct) {
+    const size_t words = (size_t)((p->elem_end + 31) / 32) + 16; // slack: a warp reads whole 128-element windows
+    int *nzflag = nullptr, *nzprefix = nullptr;
+    void *scan_tmp = nullptr;
+    size_t scan_bytes = 0;
+    B200_CUDA(cudaMalloc(&p->row_start_bits, sizeof(unsigned int) * words));
+    B200_CUDA(cudaMemsetAsync(p->row_start_bits, 0, sizeof(unsigned int) * words, stream));
+    B200_CUDA(cudaMalloc(&nzflag, sizeof(int) * ((size_t)m + 1)));
+    B200_CUDA(cudaMalloc(&nzprefix, sizeof(int) * ((size_t)m + 1)));
+    k_row_start_bits<<<grid_for((long long)m + 1, 256, 148 * 16), 256, 0, stream>>>(p->rowptr, m, p->row_start_bits,
+                                                                                    nzflag);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, nzflag, nzprefix, m + 1, stream));
+    B200_CUDA(cudaMalloc(&scan_tmp, scan_bytes ? scan_bytes : 16));
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, nzflag, nzprefix, m + 1, stream));
+    int h_nz = 0;
+    B200_CUDA(cudaMemcpyAsync(&h_nz, nzprefix + m, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    B200_CUDA(cudaStreamSynchronize(stream));
+    p->n_nz_rows = h_nz;
+    B200_CUDA(cudaMalloc(&p->nz_rows, sizeof(int) * ((size_t)h_nz + 1)));
+    k_nz_rows<<<grid_for(m, 256, 148 * 16), 256, 0, stream>>>(nzflag, nzprefix, m, p->nz_rows);
+    B200_CUDA(cudaMalloc(&p->desc_direct, sizeof(TileDesc) * (size_t)ntiles));
+    k_desc_direct<<<grid_for(ntiles, 256, 1 << 30), 256, 0, stream>>>(ntiles, p->desc_all, nzprefix, p->desc_direct);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaStreamSynchronize(stream));
+    B200_CUDA(cudaFree(scan_tmp));
+    B200_CUDA(cudaFree(nzflag));
+    B200_CUDA(cudaFree(nzprefix));
+    ws += sizeof(unsigned int) * words + sizeof(int) * ((size_t)h_nz + 1) + sizeof(TileDesc) * (size_t)ntiles;
+  }
 
   // finalise on the host: compact per-kind tile lists (ascending tile id) and the split-row table
   std::vector<unsigned char> h_kind(ntiles), h_split(ntiles + 1);

@@ -34,6 +34,17 @@ static bool irregular_gathers(const spmv_b200_plan *p) {
   return p->gather_active > 0 && 2 * p->gather_lines > p->gather_active;
 }
 
+// Direct form (one warp per 256-item row block, no shared memory) when the x gathers do not coalesce: then the kernel is
+// bound by the number of gathers in flight, every one of which holds a 128-byte line of L1, and shared memory for
+// staged tiles is taken from the same 256 KB array (profiles/: gather rate against the shared-memory carve-out).
+static bool auto_direct(const spmv_b200_plan *p) {
+  // Measured (profiles/r1_sweep_direct_*.jsonl): power-law matrices (irregular gathers AND a quarter or more of the
+  // sampled non-zeros in rows longer than medium_max) run 8 % faster in the direct form with 2048-item row blocks than
+  // in the tiled MIXED kernel (C4: 1.54 ms against 1.67 ms); matrices with uniform short rows and random columns
+  // (C3) are faster in the tiled MEDIUM kernel (1.84 ms against 2.2 ms) and stay there.
+  return irregular_gathers(p) && 4 * p->sample_nnz_long > p->sample_nnz;
+}
+
 static int auto_tile(const spmv_b200_plan *p) {
   if (p->m <= 0 || p->nnz <= 0)
     return 2048;
@@ -65,7 +76,7 @@ static int free_plan_arrays(spmv_b200_plan *p) {
       p->desc[k] = nullptr; // alias, freed once below
   void *ptrs[] = {p->tile_row, p->tile_elem, p->tile_split, p->tile_part,  p->tile_maxlen, p->tile_kind, p->list[0],
                   p->list[1],  p->list[2],   p->split_rows, p->partials,   p->desc_all,    p->desc[0],   p->desc[1],
-                  p->desc[2]};
+                  p->desc[2],  p->row_start_bits, p->nz_rows, p->desc_direct};
   int rc = SPMV_B200_OK;
   for (void *q : ptrs)
     if (q && cudaFree(q) != cudaSuccess)
@@ -127,8 +138,12 @@ int spmv_b200_plan_create(spmv_b200_plan **out, int32_t m, int32_t n, int64_t nn
   int rc = analysis_prepare(p, static_cast<cudaStream_t>(stream));
   if (rc == SPMV_B200_OK && !(opt && opt->vec_div) && irregular_gathers(p))
     p->vec_div = 8;
+  // direct form: forced by flag; automatic choice below (auto_direct)
+  if (rc == SPMV_B200_OK)
+    p->direct = !(p->flags & SPMV_B200_FLAG_NO_DIRECT) && p->nnz > 0 &&
+                ((p->flags & SPMV_B200_FLAG_DIRECT) || auto_direct(p));
   if (rc == SPMV_B200_OK && !(opt && opt->tile_nnz))
-    p->T = auto_tile(p);
+    p->T = p->direct ? 2048 : auto_tile(p);
   if (p->T < p->medium_max)
     p->T = (p->medium_max + 255) / 256 * 256;
   if (rc == SPMV_B200_OK && !((p->flags >> 8) & 0xf) && p->m > 0 && (double)p->nnz / p->m > 6.0)
@@ -353,7 +368,10 @@ int spmv_b200_plan_get_info(const spmv_b200_plan *p, spmv_b200_plan_info *info) 
   }
   launches += p->nsplit > 0 ? 1 : 0;
   info->nsplit_rows = p->nsplit;
+  if (p->direct)
+    launches = (p->ntiles > 0 ? 1 : 0) + (p->nsplit > 0 ? 1 : 0);
   info->launches_per_execute = launches;
+  info->direct = p->direct ? 1 : 0;
   for (int b = 0; b < 4; ++b) {
     info->bin_rows[b] = p->bin_rows[b];
     info->bin_nnz[b] = p->bin_nnz[b];
@@ -405,6 +423,17 @@ int spmv_b200_plan_export(spmv_b200_plan *p, int32_t what, void *h_dst, int64_t 
   case SPMV_B200_EXPORT_ROW_BIN:
     bytes = p->m;
     break;
+  case SPMV_B200_EXPORT_ROW_START_BITS:
+    src = p->row_start_bits;
+    bytes = p->direct ? 4 * ((p->elem_end + 31) / 32) : 0;
+    break;
+  case SPMV_B200_EXPORT_NZ_ROWS:
+    src = p->nz_rows;
+    bytes = p->direct ? 4 * (int64_t)p->n_nz_rows : 0;
+    break;
+  case SPMV_B200_EXPORT_TILE_NZBASE:
+    bytes = p->direct ? 4 * nt : 0;
+    break;
   default:
     set_error("plan_export: unknown array id");
     return SPMV_B200_ERR_ARG;
@@ -425,6 +454,13 @@ int spmv_b200_plan_export(spmv_b200_plan *p, int32_t what, void *h_dst, int64_t 
       rc = cuda_fail(cudaGetLastError(), "cudaMemcpy(row bins)", __FILE__, __LINE__);
     cudaFree(d_tmp);
     return rc;
+  }
+  if (what == SPMV_B200_EXPORT_TILE_NZBASE) { // field head_end of the direct descriptors
+    std::vector<TileDesc> h((size_t)nt);
+    B200_CUDA(cudaMemcpy(h.data(), p->desc_direct, sizeof(TileDesc) * (size_t)nt, cudaMemcpyDeviceToHost));
+    for (int64_t t = 0; t < nt; ++t)
+      static_cast<int32_t *>(h_dst)[t] = h[(size_t)t].head_end;
+    return SPMV_B200_OK;
   }
   B200_CUDA(cudaMemcpy(h_dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
   return SPMV_B200_OK;

@@ -67,6 +67,8 @@ struct SpmvArgs {
   int ntiles;   // tiles of this kind (persistent kernels walk [0, ntiles) with stride gridDim.x)
   int cap;      // element capacity of the shared-memory tile
   int vec_div;  // MEDIUM: lanes per row = pow2ceil(avg / vec_div)
+  const unsigned int *__restrict__ row_start_bits; // direct form only
+  const int *__restrict__ nz_rows;                 // direct form only
   int read_y;   // 0: beta == 0 and SPMV_B200_FLAG_BETA0_SKIP_Y
   int gather_na; // 1: x gathers use L1::no_allocate
   PushArgs push;
@@ -119,6 +121,12 @@ struct spmv_b200_plan {
   b200::TileDesc *desc_all = nullptr;                       // [ntiles] descriptors in tile order
   b200::TileDesc *desc[3] = {nullptr, nullptr, nullptr};    // per kind (aliases desc_all when one kind owns all tiles)
   int count[3] = {0, 0, 0};
+  // direct (warp-per-tile, no shared memory) form for matrices with irregular gathers (SPMV_B200_FLAG_DIRECT / auto)
+  bool direct = false;
+  unsigned int *row_start_bits = nullptr;  // bit k (absolute element index) set iff element k is the first of its row
+  int *nz_rows = nullptr;                  // ascending ids of the non-empty rows
+  int n_nz_rows = 0;
+  b200::TileDesc *desc_direct = nullptr;   // [ntiles] like desc_all, with head_end = number of non-empty rows < r0
   int nsplit = 0;
   int *split_rows = nullptr; // [3*nsplit]: row, t0, t1 (struct of arrays: rows | t0 | t1)
   double *partials = nullptr;

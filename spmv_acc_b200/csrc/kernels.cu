@@ -759,6 +759,188 @@ __global__ void __launch_bounds__(NT, 1536 / NT) k_spmv_seg(const SpmvArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Direct form: one warp per row block of 256 items, no shared memory (matrices whose x gathers do not coalesce)
+// ---------------------------------------------------------------------------------------------------------------
+// A gather in flight holds a 128-byte line of L1, and L1 is what the shared-memory carve-out leaves of the 256 KB
+// unified array: with tiles staged in shared memory the gather rate of an SM drops by 2-4x (profiles/, gather bound
+// against carve-out). Here value / colindex go straight into registers (each lane owns 4 consecutive elements: one
+// 128-bit load of colindex, two of value, fully used sectors), the products stay in registers, and rows are delimited
+// by the row-start bit flags of the analysis instead of row pointers:
+//   * a lane sums its 4 products up to the first row start ("head"), finishes the rows that begin and end inside its
+//     chunk on its own, and leaves the rest open;
+//   * a segmented warp scan (shuffles) gives every lane the open sum in front of it, which completes its head;
+//   * the row a finished sum belongs to is nz_rows[nzbase + ordinal of its row start]; the open sums at the two ends
+//     of a block are the fragments of rows split across blocks (partials -> k_fixup), or the block's last row.
+// No barrier, no atomics; the order of every addition is fixed by the block geometry (bitwise reproducible).
+// Analogue of the reference's flat / merge-path kernels (src/acc/hip-flat/flat_imp_one_pass.hpp:15-77,
+// benchmark/merge-path/merge_path_reduction.h:80-136) without atomicAdd and without the per-element row search.
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void finish_row(const SpmvArgs &a, int row, double sum) {
+  const double yv = a.read_y ? a.y[row] : 0.0; // cli/verification.cpp:64: y is read even when beta == 0
+  emit_y(a.y, a.push, row, a.alpha * sum + a.beta * yv);
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 5) k_spmv_warp(const SpmvArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int ti = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (ti >= a.ntiles)
+    return;
+  const TileDesc d = load_desc(a.desc, ti);
+  const int t = d.tile, r0 = d.r0, r1 = d.r1, e0 = d.e0, e1 = d.e1;
+  const int nzbase = d.head_end; // direct descriptors: non-empty rows in front of this block
+  const bool split_begin = (d.flags & 1) != 0, split_end = (d.flags & 2) != 0;
+  const long long arr_end = a.nnz;
+
+  // Everything a finished row needs later (its y, its id, the row pointers of the empty-row pass) is requested now,
+  // without a destination register, so that those dependent accesses hit L1 instead of adding round trips to the
+  // chain descriptor -> value/colindex/flags -> x gathers. One 128-byte line per lane and array (blocks own <= T rows).
+  {
+    const int nrows = r1 - r0;
+    for (int i = lane * 16; i < nrows; i += 32 * 16)
+      prefetch_l1(a.y + r0 + i);
+    for (int i = lane * 32; i <= nrows; i += 32 * 32) {
+      prefetch_l1(a.rowptr + r0 + i);
+      prefetch_l1(a.nz_rows + nzbase + i);
+    }
+  }
+
+  double cv = 0.0; // open sum (since the last row start) in front of the current 128-element window
+  int nstart = 0;  // row starts met so far
+  for (int rb = e0 & ~3; rb < e1; rb += 256) {
+    double p[2][4];
+    unsigned nib[2];
+    {
+      int c[2][4];
+      double v[2][4];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i0 = rb + 128 * q + 4 * lane;
+        nib[q] = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          c[q][k] = -1;
+          v[q][k] = 0.0;
+        }
+        if (i0 < e1 && i0 + 4 > e0) { // the chunk intersects the block
+          const unsigned w = __ldg(a.row_start_bits + (i0 >> 5));
+          nib[q] = (w >> (i0 & 31)) & 0xfu;
+          if (VEC && (long long)i0 + 4 <= arr_end) {
+            const int4 cc = __ldcs(reinterpret_cast<const int4 *>(a.col + i0));
+            const double2 v01 = __ldcs(reinterpret_cast<const double2 *>(a.val + i0));
+            const double2 v23 = __ldcs(reinterpret_cast<const double2 *>(a.val + i0) + 1);
+            c[q][0] = cc.x, c[q][1] = cc.y, c[q][2] = cc.z, c[q][3] = cc.w;
+            v[q][0] = v01.x, v[q][1] = v01.y, v[q][2] = v23.x, v[q][3] = v23.y;
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if ((long long)i0 + k < arr_end) {
+                c[q][k] = __ldcs(a.col + i0 + k);
+                v[q][k] = __ldcs(a.val + i0 + k);
+              }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (i0 + k < e0 || i0 + k >= e1) { // elements of the neighbouring blocks
+              c[q][k] = -1;
+              nib[q] &= ~(1u << k);
+            }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          p[q][k] = c[q][k] >= 0 ? gather_x(a.x, c[q][k], a.gather_na) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          p[q][k] *= v[q][k];
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (rb + 128 * q >= e1) // warp-uniform
+        break;
+      // ordinal of the first row start this lane meets = starts in earlier windows + starts in the lanes in front
+      int incl = __popc(nib[q]);
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off)
+          incl += o;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int s = nstart + incl - __popc(nib[q]);
+      const int sfirst = s;
+      bool f = false;
+      double head = 0.0, acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if ((nib[q] >> k) & 1u) { // a row starts here: the sum in front of it is complete
+          if (!f) {
+            f = true;
+            head = acc; // completed below, with the open sums of the lanes in front
+          } else {
+            finish_row(a, __ldg(a.nz_rows + nzbase + s - 1), acc);
+          }
+          acc = 0.0;
+          ++s;
+        }
+        acc += p[q][k];
+      }
+      // segmented inclusive scan of (f, open sum)
+      double v = acc;
+      int ff = f ? 1 : 0;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const double vv = __shfl_up_sync(0xffffffffu, v, off);
+        const int fo = __shfl_up_sync(0xffffffffu, ff, off);
+        if (lane >= off) {
+          if (!ff)
+            v = vv + v;
+          ff |= fo;
+        }
+      }
+      double ev = __shfl_up_sync(0xffffffffu, v, 1);
+      int ef = __shfl_up_sync(0xffffffffu, ff, 1);
+      if (lane == 0) {
+        ev = 0.0;
+        ef = 0;
+      }
+      if (f) {
+        const double tot = (ef ? ev : cv + ev) + head;
+        if (sfirst == 0) { // the sum in front of the block's first row start: fragment of a row that began earlier
+          if (split_begin)
+            a.partials[2 * (size_t)t] = tot;
+        } else {
+          finish_row(a, __ldg(a.nz_rows + nzbase + sfirst - 1), tot);
+        }
+      }
+      const double v31 = __shfl_sync(0xffffffffu, v, 31);
+      const int f31 = __shfl_sync(0xffffffffu, ff, 31);
+      cv = f31 ? v31 : cv + v31;
+      nstart += total;
+    }
+  }
+  // rows without elements only need the epilogue
+  for (int r = r0 + lane; r < r1; r += 32)
+    if (__ldg(a.rowptr + r) == __ldg(a.rowptr + r + 1))
+      finish_row(a, r, 0.0);
+  if (lane == 0) { // the open sum at the end of the block
+    if (nstart == 0) {
+      if (split_begin)
+        a.partials[2 * (size_t)t] = cv; // the whole block lies inside one row
+    } else if (split_end) {
+      a.partials[2 * (size_t)t + 1] = cv;
+    } else {
+      finish_row(a, __ldg(a.nz_rows + nzbase + nstart - 1), cv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // second pass: rows split across tiles
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_fixup(const FixupArgs f) {
@@ -975,10 +1157,23 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
   else
     a.push.count = 0;
 
+  a.row_start_bits = p->row_start_bits;
+  a.nz_rows = p->nz_rows;
   const bool tma = p->uses_tma;
   const bool persistent = (p->flags & SPMV_B200_FLAG_PERSISTENT) != 0;
   const bool whole = tile_lo <= 0 && tile_hi >= p->ntiles;
-  for (int k = 0; k < 3; ++k) {
+  if (p->direct) {
+    const int lo = tile_lo < 0 ? 0 : tile_lo, hi = tile_hi > p->ntiles ? p->ntiles : tile_hi;
+    if (hi > lo) {
+      a.desc = p->desc_direct + lo;
+      a.ntiles = hi - lo;
+      a.cap = 0;
+      const int wpc = kThreads / 32;
+      // uses_tma == value / colindex are 16-byte aligned (and vector loads were not disabled with NO_TMA)
+      B200_CUDA(launch_spmv(tma ? k_spmv_warp<true> : k_spmv_warp<false>, (a.ntiles + wpc - 1) / wpc, 0, stream, a, p));
+    }
+  }
+  for (int k = 0; k < 3 && !p->direct; ++k) {
     if (p->count[k] == 0)
       continue;
     int lo = 0, hi = p->count[k];

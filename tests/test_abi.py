@@ -30,8 +30,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Options) == 20
-    # int32 m,n | int64 nnz | 4 x int32 | uint32 | 2 x int32 | 3 x int32 | 2 x int32 | 8 x int64 | 2 x int64
-    assert ctypes.sizeof(_lib.PlanInfo) == 8 + 8 + 16 + 4 + 8 + 12 + 8 + 64 + 16 + 16
+    # int32 m,n | int64 nnz | 4 x int32 | uint32 | 2 x int32 | 3 x int32 | 3 x int32 (+4 pad) | 8 x int64 | 2 x int64
+    assert ctypes.sizeof(_lib.PlanInfo) == 8 + 8 + 16 + 4 + 8 + 12 + 16 + 64 + 16 + 16
 
 
 def test_product_package_never_imports_the_oracle():

@@ -58,6 +58,28 @@ def test_analysis_arrays_bit_exact(opts):
         plan.destroy()
 
 
+@pytest.mark.parametrize("opts", [(0, 0, 0), (256, 4, 16), (1024, 8, 64)])
+def test_direct_form_arrays_bit_exact(opts):
+    """Row-start bit flags, non-empty row list and per-tile base ordinal of the direct (warp-per-row-block) form."""
+    from spmv_acc_b200 import FLAG_DIRECT
+    T, S, L = opts
+    for name, h in _matrices():
+        d = synth.to_device(h)
+        plan = SpmvPlan(desc_of(d), make_options(T, S, L, flags=FLAG_DIRECT))
+        info = plan.info()
+        if h.nnz == 0:
+            assert info.direct == 0, name
+            plan.destroy()
+            continue
+        assert info.direct == 1 and (T or info.tile_nnz == 2048), name
+        ref = oracle.port_analysis(h.rowptr, info.tile_nnz, info.short_max, info.medium_max)
+        assert np.array_equal(plan.export("tile_row"), ref["tile_row"]), name
+        extra = oracle.port_direct_arrays(h.rowptr, ref["tile_row"])
+        for a in ("row_start_bits", "nz_rows", "tile_nzbase"):
+            assert np.array_equal(plan.export(a), extra[a]), f"{name}: {a} differs"
+        plan.destroy()
+
+
 def test_tile_partition_equals_reference_merge_path_partition_kernel():
     """TILE_PART (T = 2048) against the reference's `partition` kernel, compiled in place into oracle/_ref/libref_gpu.so
     (benchmark/merge-path/merge_path_partition.h:7-17; launch shape of merge_path_spmv.cu:44)."""

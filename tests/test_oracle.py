@@ -129,3 +129,16 @@ def test_reference_adaptive_plus_blocks_are_nnz_balanced_like_ours():
     our_nnz = np.diff(ours["tile_elem"])
     assert bp[0] == 0 and bp[-1] == c1.rows and ours["tile_row"][-1] == c1.rows
     assert our_nnz.max() <= 2048 + 127 and abs(len(our_nnz) - len(ref_nnz)) <= len(ref_nnz)
+
+
+def test_port_direct_arrays_small_known_answer():
+    """Hand-checked: rows of length 2, 0, 3, 0, 0, 1 -> starts at elements 0, 2, 5; non-empty rows 0, 2, 5."""
+    rowptr = np.array([0, 2, 2, 5, 5, 5, 6], np.int32)
+    out = oracle.port_direct_arrays(rowptr, np.array([0, 1, 3, 6]))
+    assert out["nz_rows"].tolist() == [0, 2, 5]
+    assert out["row_start_bits"].tolist() == [(1 << 0) | (1 << 2) | (1 << 5)]
+    assert out["tile_nzbase"].tolist() == [0, 1, 2]   # non-empty rows in front of rows 0, 1, 3
+    # starts beyond bit 31 land in the next word
+    rowptr = np.array([0, 40, 40, 70], np.int32)
+    out = oracle.port_direct_arrays(rowptr, np.array([0, 3]))
+    assert out["row_start_bits"].tolist() == [1, 1 << 8, 0]

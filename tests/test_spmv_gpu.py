@@ -9,7 +9,7 @@ import pytest
 import oracle
 from conftest import GOLDEN_CASES, load_golden
 from gpu_helpers import assert_parity, desc_of, gpu_spmv
-from spmv_acc_b200 import (FLAG_BETA0_SKIP_Y, FLAG_NO_TMA, CsrDesc, HostMatrix, SpmvB200Error, SpmvPlan,
+from spmv_acc_b200 import (FLAG_BETA0_SKIP_Y, FLAG_DIRECT, FLAG_NO_DIRECT, FLAG_NO_TMA, CsrDesc, HostMatrix, SpmvB200Error, SpmvPlan,
                            cache_invalidate, cache_size, host_spmv, make_options, sparse_csr_spmv, sparse_spmv, synth)
 
 pytestmark = pytest.mark.gpu
@@ -18,10 +18,16 @@ AB = [(1.0, 1.0), (0.75, -0.5), (1.0, 0.0), (0.0, 2.0), (-1.25, 1e-3)]
 OPTS = {
     "default": None,
     "no_tma": make_options(flags=FLAG_NO_TMA),
-    "small_tiles": make_options(256, 4, 16, 2),
-    "big_tiles": make_options(8192, 16, 256, 16),
-    "persistent": make_options(flags=0x20000),
-    "persistent_small": make_options(256, 4, 16, 2, flags=0x20000),
+    "small_tiles": make_options(256, 4, 16, 2, flags=FLAG_NO_DIRECT),
+    "big_tiles": make_options(8192, 16, 256, 16, flags=FLAG_NO_DIRECT),
+    "persistent": make_options(flags=0x20000 | FLAG_NO_DIRECT),
+    "persistent_small": make_options(256, 4, 16, 2, flags=0x20000 | FLAG_NO_DIRECT),
+    "tiled_only": make_options(flags=FLAG_NO_DIRECT),
+    "direct": make_options(flags=FLAG_DIRECT),
+    "direct_scalar_loads": make_options(flags=FLAG_DIRECT | FLAG_NO_TMA),
+    "direct_T512_L64": make_options(512, 8, 64, flags=FLAG_DIRECT),
+    "mixed_segmented": make_options(flags=(1 << 22) | FLAG_NO_DIRECT),
+    "mixed_segmented_small": make_options(256, 4, 16, 2, flags=(1 << 22) | FLAG_NO_DIRECT),
 }
 
 
