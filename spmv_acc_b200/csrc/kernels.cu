@@ -865,13 +865,24 @@ __global__ void __launch_bounds__(kThreads, 5) k_spmv_warp(const SpmvArgs a) {
         break;
       // ordinal of the first row start this lane meets = starts in earlier windows + starts in the lanes in front
       int incl = __popc(nib[q]);
+      const bool any_start = __any_sync(0xffffffffu, nib[q] != 0u);
+      if (any_start) {
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off)
-          incl += o;
+        for (int off = 1; off < 32; off <<= 1) {
+          const int o = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off)
+            incl += o;
+        }
       }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      const int total = any_start ? __shfl_sync(0xffffffffu, incl, 31) : 0;
+      if (total == 0) { // the whole window lies inside one row (long rows): one warp sum, nothing to finish
+        double w = (p[q][0] + p[q][1]) + (p[q][2] + p[q][3]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+          w += __shfl_xor_sync(0xffffffffu, w, off);
+        cv += w;
+        continue;
+      }
       int s = nstart + incl - __popc(nib[q]);
       const int sfirst = s;
       bool f = false;

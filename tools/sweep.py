@@ -21,6 +21,10 @@ def make(workload):
         return synth.stencil2d_device(4096)
     if workload == "c3":
         return synth.uniform_device(10_000_000, 10_000_000, 32, seed=1)
+    if workload == "c3half":  # one column half of C3 (what a 2-way column-blocked plan would multiply per pass)
+        return synth.uniform_device(10_000_000, 5_000_000, 16, seed=1)
+    if workload == "c3x40":   # C3 with x small enough for L2 (40 MB)
+        return synth.uniform_device(10_000_000, 5_000_000, 32, seed=1)
     if workload == "c4":
         return synth.rmat_device(24, 16, seed=1)
     if workload == "c5":
