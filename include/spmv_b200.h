@@ -123,9 +123,16 @@ int spmv_b200_execute_tiles(spmv_b200_plan *plan, double alpha, double beta, con
 /* execute + store the rows listed in `push` into other GPUs' memory from the same kernels (no separate exchange) */
 int spmv_b200_execute_push(spmv_b200_plan *plan, double alpha, double beta, const double *d_x, double *d_y,
                            const spmv_b200_push *push, void *stream);
+/* the same for tiles [tile_lo, tile_hi) only: lets the rows other GPUs wait for be multiplied and pushed first */
+int spmv_b200_execute_tiles_push(spmv_b200_plan *plan, double alpha, double beta, const double *d_x, double *d_y,
+                                 int32_t tile_lo, int32_t tile_hi, const spmv_b200_push *push, void *stream);
+/* smallest / largest column index referenced by each tile (h_min / h_max: int32 [ntiles]; INT32_MAX / -1 if empty):
+ * a sharded caller uses it to find the row blocks that read entries of x owned by other GPUs */
+int spmv_b200_plan_tile_col_range(spmv_b200_plan *plan, int32_t *h_min, int32_t *h_max, void *stream);
 /* stream-ordered 32-bit flags in (peer) device memory: write `value`, or block the stream until *flag >= value.
  * Used to order the iterations of neighbouring GPUs without a collective. */
 int spmv_b200_stream_write_flag(void *stream, uint32_t *d_flag, uint32_t value);
+int spmv_b200_stream_write_flags(void *stream, uint32_t *const *d_flags, int32_t count, uint32_t value); /* <= 8 flags, one launch */
 int spmv_b200_stream_wait_flag(void *stream, uint32_t *d_flag, uint32_t value);
 int spmv_b200_enable_peer_access(int32_t peer_device);
 /* exchange buffers other GPUs (other processes) store into: allocated with cudaMalloc on the current device and

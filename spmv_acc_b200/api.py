@@ -165,6 +165,33 @@ class SpmvPlan:
                                                _current_stream() if stream is None else stream)
         check(rc, "execute_push")
 
+    def execute_tiles_push(self, alpha: float, beta: float, dx: Any, dy: Any, tile_lo: int, tile_hi: int, push: list,
+                           stream: Optional[int] = None) -> None:
+        """Row blocks [tile_lo, tile_hi) with the fused halo push of ``execute_push``."""
+        if not self._h:
+            raise SpmvB200Error("plan was destroyed")
+        if len(push) > _lib.MAX_PUSH:
+            raise SpmvB200Error(f"at most {_lib.MAX_PUSH} push ranges are supported")
+        _require_device(dx, "dx", "float64")
+        _require_device(dy, "dy", "float64")
+        ps = _lib.Push()
+        ps.count = len(push)
+        for j, (lo, hi, dst) in enumerate(push):
+            ps.row_lo[j], ps.row_hi[j], ps.dst[j] = int(lo), int(hi), int(dst)
+        rc = _lib.lib().spmv_b200_execute_tiles_push(self._h, float(alpha), float(beta), _ptr(dx), _ptr(dy),
+                                                     int(tile_lo), int(tile_hi), C.byref(ps),
+                                                     _current_stream() if stream is None else stream)
+        check(rc, "execute_tiles_push")
+
+    def tile_col_range(self):
+        """(min, max) column index referenced by every row block (int32 arrays of length ntiles)."""
+        nt = self.info().ntiles
+        lo, hi = np.empty(nt, np.int32), np.empty(nt, np.int32)
+        if nt:
+            check(_lib.lib().spmv_b200_plan_tile_col_range(self._h, lo.ctypes.data, hi.ctypes.data, _current_stream()),
+                  "plan_tile_col_range")
+        return lo, hi
+
     def info(self) -> PlanInfo:
         out = PlanInfo()
         check(_lib.lib().spmv_b200_plan_get_info(self._h, C.byref(out)), "plan_get_info")
@@ -232,6 +259,13 @@ def stream_write_flag(address: int, value: int, stream: Optional[int] = None) ->
     """Stream-ordered 32-bit store (with a system-scope memory barrier) to device memory, possibly another GPU's."""
     check(_lib.lib().spmv_b200_stream_write_flag(_current_stream() if stream is None else stream, int(address),
                                                  int(value)), "stream_write_flag")
+
+
+def stream_write_flags(addresses: list, value: int, stream: Optional[int] = None) -> None:
+    """``stream_write_flag`` for up to 8 flags with a single launch."""
+    arr = (C.c_void_p * max(len(addresses), 1))(*[int(a) for a in addresses])
+    check(_lib.lib().spmv_b200_stream_write_flags(_current_stream() if stream is None else stream, arr,
+                                                  len(addresses), int(value)), "stream_write_flags")
 
 
 def stream_wait_flag(address: int, value: int, stream: Optional[int] = None) -> None:

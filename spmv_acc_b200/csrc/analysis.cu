@@ -534,6 +534,52 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
   return SPMV_B200_OK;
 }
 
+// smallest / largest column index referenced by every tile (one warp per tile): tells a sharded caller which row blocks
+// read entries of x owned by other GPUs. Integer min / max: order independent.
+__global__ void __launch_bounds__(256) k_tile_col_range(const int *__restrict__ col, int ntiles,
+                                                         const int *__restrict__ tile_elem, int *__restrict__ cmin,
+                                                         int *__restrict__ cmax) {
+  const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= ntiles)
+    return;
+  int lo = 0x7fffffff, hi = -1;
+  for (int k = tile_elem[t] + lane; k < tile_elem[t + 1]; k += 32) {
+    const int c = __ldg(col + k);
+    lo = c < lo ? c : lo;
+    hi = c > hi ? c : hi;
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    const int l2 = __shfl_xor_sync(0xffffffffu, lo, off), h2 = __shfl_xor_sync(0xffffffffu, hi, off);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+  }
+  if (lane == 0) {
+    cmin[t] = lo;
+    cmax[t] = hi;
+  }
+}
+
+int analysis_tile_col_range(const spmv_b200_plan *p, int *h_min, int *h_max, cudaStream_t stream) {
+  if (p->ntiles == 0)
+    return SPMV_B200_OK;
+  int *d = nullptr;
+  B200_CUDA(cudaMalloc(&d, sizeof(int) * 2 * (size_t)p->ntiles));
+  k_tile_col_range<<<grid_for((long long)p->ntiles * 32, 256, 1 << 30), 256, 0, stream>>>(p->col, p->ntiles,
+                                                                                           p->tile_elem, d,
+                                                                                           d + p->ntiles);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(h_min, d, sizeof(int) * (size_t)p->ntiles, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(h_max, d + p->ntiles, sizeof(int) * (size_t)p->ntiles, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(stream);
+  cudaFree(d);
+  B200_CUDA(e);
+  return SPMV_B200_OK;
+}
+
 int analysis_row_bins(const spmv_b200_plan *p, unsigned char *d_out, cudaStream_t stream) {
   if (p->m == 0)
     return SPMV_B200_OK;

@@ -198,14 +198,29 @@ int spmv_b200_execute_tiles(spmv_b200_plan *plan, double alpha, double beta, con
   return kernels_launch_tiles(plan, alpha, beta, d_x, d_y, tile_lo, tile_hi, static_cast<cudaStream_t>(stream));
 }
 
+static int convert_push(const spmv_b200_plan *plan, const spmv_b200_push *push, PushArgs *pa, const char *who) {
+  if (push->count < 0 || push->count > SPMV_B200_MAX_PUSH) {
+    set_error(std::string(who) + ": push.count out of range");
+    return SPMV_B200_ERR_ARG;
+  }
+  pa->count = push->count;
+  for (int j = 0; j < kMaxPush; ++j) {
+    pa->row_lo[j] = j < push->count ? push->row_lo[j] : 0;
+    pa->row_hi[j] = j < push->count ? push->row_hi[j] : 0;
+    pa->dst[j] = j < push->count ? push->dst[j] : nullptr;
+    if (j < push->count &&
+        (!pa->dst[j] || pa->row_lo[j] < 0 || pa->row_hi[j] > plan->m || pa->row_lo[j] > pa->row_hi[j])) {
+      set_error(std::string(who) + ": bad push range");
+      return SPMV_B200_ERR_ARG;
+    }
+  }
+  return SPMV_B200_OK;
+}
+
 int spmv_b200_execute_push(spmv_b200_plan *plan, double alpha, double beta, const double *d_x, double *d_y,
                            const spmv_b200_push *push, void *stream) {
   if (!plan || !push) {
     set_error("execute_push: NULL argument");
-    return SPMV_B200_ERR_ARG;
-  }
-  if (push->count < 0 || push->count > SPMV_B200_MAX_PUSH) {
-    set_error("execute_push: push.count out of range");
     return SPMV_B200_ERR_ARG;
   }
   if ((plan->m > 0 && !d_y) || (plan->nnz > 0 && !d_x)) {
@@ -213,17 +228,39 @@ int spmv_b200_execute_push(spmv_b200_plan *plan, double alpha, double beta, cons
     return SPMV_B200_ERR_ARG;
   }
   PushArgs pa;
-  pa.count = push->count;
-  for (int j = 0; j < kMaxPush; ++j) {
-    pa.row_lo[j] = j < push->count ? push->row_lo[j] : 0;
-    pa.row_hi[j] = j < push->count ? push->row_hi[j] : 0;
-    pa.dst[j] = j < push->count ? push->dst[j] : nullptr;
-    if (j < push->count && (!pa.dst[j] || pa.row_lo[j] < 0 || pa.row_hi[j] > plan->m || pa.row_lo[j] > pa.row_hi[j])) {
-      set_error("execute_push: bad push range");
-      return SPMV_B200_ERR_ARG;
-    }
-  }
+  if (int rc = convert_push(plan, push, &pa, "execute_push"))
+    return rc;
   return kernels_launch(plan, alpha, beta, d_x, d_y, static_cast<cudaStream_t>(stream), &pa);
+}
+
+int spmv_b200_execute_tiles_push(spmv_b200_plan *plan, double alpha, double beta, const double *d_x, double *d_y,
+                                 int32_t tile_lo, int32_t tile_hi, const spmv_b200_push *push, void *stream) {
+  if (!plan || !push) {
+    set_error("execute_tiles_push: NULL argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  if (tile_lo < 0 || tile_hi > plan->ntiles || tile_lo > tile_hi) {
+    set_error("execute_tiles_push: tile range out of bounds");
+    return SPMV_B200_ERR_ARG;
+  }
+  if ((plan->m > 0 && !d_y) || (plan->nnz > 0 && !d_x)) {
+    set_error("execute_tiles_push: x or y is NULL");
+    return SPMV_B200_ERR_ARG;
+  }
+  PushArgs pa;
+  if (int rc = convert_push(plan, push, &pa, "execute_tiles_push"))
+    return rc;
+  if (tile_lo == tile_hi)
+    return SPMV_B200_OK;
+  return kernels_launch_tiles(plan, alpha, beta, d_x, d_y, tile_lo, tile_hi, static_cast<cudaStream_t>(stream), &pa);
+}
+
+int spmv_b200_plan_tile_col_range(spmv_b200_plan *plan, int32_t *h_min, int32_t *h_max, void *stream) {
+  if (!plan || !h_min || !h_max) {
+    set_error("plan_tile_col_range: NULL argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  return analysis_tile_col_range(plan, h_min, h_max, static_cast<cudaStream_t>(stream));
 }
 
 // stream memory operations of the driver API, fetched at run time (no link-time dependency on libcuda)
@@ -251,6 +288,32 @@ int spmv_b200_stream_write_flag(void *stream, uint32_t *d_flag, uint32_t value) 
     return SPMV_B200_ERR_ARG;
   }
   k_write_flag<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(d_flag, value);
+  B200_CUDA(cudaGetLastError());
+  return SPMV_B200_OK;
+}
+
+struct FlagList {
+  uint32_t *p[SPMV_B200_MAX_PUSH];
+  int n;
+};
+__global__ void k_write_flags(FlagList f, uint32_t value) {
+  __threadfence_system();
+  if ((int)threadIdx.x < f.n)
+    *reinterpret_cast<volatile uint32_t *>(f.p[threadIdx.x]) = value;
+}
+
+int spmv_b200_stream_write_flags(void *stream, uint32_t *const *d_flags, int32_t count, uint32_t value) {
+  if (count < 0 || count > SPMV_B200_MAX_PUSH || (count > 0 && !d_flags)) {
+    set_error("stream_write_flags: bad argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  if (count == 0)
+    return SPMV_B200_OK;
+  FlagList f;
+  f.n = count;
+  for (int i = 0; i < SPMV_B200_MAX_PUSH; ++i)
+    f.p[i] = i < count ? d_flags[i] : nullptr;
+  k_write_flags<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(f, value);
   B200_CUDA(cudaGetLastError());
   return SPMV_B200_OK;
 }

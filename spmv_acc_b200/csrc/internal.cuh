@@ -144,6 +144,7 @@ namespace b200 {
 int analysis_prepare(spmv_b200_plan *p, cudaStream_t stream); // reads rowptr[0], rowptr[m]
 int analysis_run(spmv_b200_plan *p, cudaStream_t stream);
 int analysis_row_bins(const spmv_b200_plan *p, unsigned char *d_out, cudaStream_t stream);
+int analysis_tile_col_range(const spmv_b200_plan *p, int *h_min, int *h_max, cudaStream_t stream);
 int shard_bounds_run(int m, long long nnz, const int *d_rowptr, int nshards, int *h_bounds, cudaStream_t stream);
 int col_block_bitmap_run(long long nnz, const int *d_col, int n, int block_shift, unsigned char *h_bitmap,
                          cudaStream_t stream);
@@ -154,6 +155,6 @@ int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const dou
                    cudaStream_t stream, const PushArgs *push = nullptr);
 // tiles [tile_lo, tile_hi) only; the plan must have no split rows (their partial sums cross tile ranges)
 int kernels_launch_tiles(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y, int tile_lo,
-                         int tile_hi, cudaStream_t stream);
+                         int tile_hi, cudaStream_t stream, const PushArgs *push = nullptr);
 
 } // namespace b200

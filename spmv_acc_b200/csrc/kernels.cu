@@ -1234,12 +1234,12 @@ int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const dou
 }
 
 int kernels_launch_tiles(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y, int tile_lo,
-                         int tile_hi, cudaStream_t stream) {
+                         int tile_hi, cudaStream_t stream, const PushArgs *push) {
   if (p->nsplit > 0) {
     set_error("kernels_launch_tiles: the plan has split rows");
     return SPMV_B200_ERR_UNSUPPORTED;
   }
-  return launch_range(p, alpha, beta, x, y, tile_lo, tile_hi, false, stream);
+  return launch_range(p, alpha, beta, x, y, tile_lo, tile_hi, false, stream, push);
 }
 
 } // namespace b200

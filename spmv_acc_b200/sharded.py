@@ -90,6 +90,7 @@ class PowerLoop:
     # optional overlap of the halo exchange with the rows nobody waits for:
     spmv_tiles: Optional[Callable] = None   # spmv_tiles(x_full, y_slice, tile_lo, tile_hi): row blocks of the shard
     tile_row: Optional[np.ndarray] = None   # [ntiles+1] first local row of each row block
+    tile_reads_halo: Optional[np.ndarray] = None  # bool [ntiles]: the row block references x entries of other ranks
     overlap: bool = True
     boundary: list = field(default_factory=list)   # tile ranges whose rows are sent to other ranks
     interior: list = field(default_factory=list)   # the remaining tile ranges
@@ -134,6 +135,12 @@ class PowerLoop:
             t0 = int(np.searchsorted(tr, a - lo, side="right")) - 1
             t1 = int(np.searchsorted(tr, e - lo, side="left"))
             marks[max(t0, 0):min(t1, nt)] = True
+        # Row blocks that read entries owned by other ranks count as boundary too: once the boundary blocks of an
+        # iteration are done, this rank neither owes anybody a row of that iteration nor reads a halo entry of it, which is
+        # what lets a neighbour overwrite the halo early (fused push) while the interior is still being multiplied.
+        self.boundary_reads_all_halo = self.tile_reads_halo is not None
+        if self.tile_reads_halo is not None:
+            marks |= np.asarray(self.tile_reads_halo, dtype=bool)[:nt]
         if nt == 0 or marks.sum() * 2 > nt:
             return  # most of the shard is boundary: nothing to hide the exchange behind
         edges = np.flatnonzero(np.diff(np.concatenate(([False], marks, [False])).astype(np.int8)))
@@ -253,6 +260,8 @@ class FusedHaloLoop:
         self.push = [[(a - self.lo, e - self.lo, self.peer[p].address + b * self.xbytes + 8 * self.lo)
                       for p, a, e in base.sends] for b in (0, 1)]
         self.k = 0
+        # boundary-first schedule only if the boundary blocks are known to contain every reader of halo entries
+        self.split = bool(getattr(base, "overlapped", False) and getattr(base, "boundary_reads_all_halo", False))
         dist.barrier()
 
     def close(self):
@@ -267,15 +276,25 @@ class FusedHaloLoop:
         self.own.release()
 
     def step(self):
-        from . import stream_wait_flag, stream_write_flag
+        from . import stream_wait_flag, stream_write_flags
         k = self.k
         if k > 0:
-            for p in self.neigh:  # neighbour p has finished iteration k-1
+            for p in self.neigh:  # neighbour p has pushed its rows of x_k and no longer reads the halo of x_(k-1)
                 stream_wait_flag(self.flags.data_ptr() + 4 * p, k)
         src, dst = self.bufs[k % 2], self.bufs[(k + 1) % 2]
-        self.plan.execute_push(1.0, 0.0, src, dst[self.lo:self.hi], self.push[(k + 1) % 2])
-        for p in self.neigh:
-            stream_write_flag(self.peer[p].address + 2 * self.xbytes + 4 * self.rank, k + 1)
+        ys, push = dst[self.lo:self.hi], self.push[(k + 1) % 2]
+        flags = [self.peer[p].address + 2 * self.xbytes + 4 * self.rank for p in self.neigh]
+        if self.split:
+            # boundary row blocks first (they produce every pushed row and are the only readers of halo entries), then
+            # the flags, then the interior: the neighbours get their go-ahead a few percent into the iteration
+            for t0, t1 in self.base.boundary:
+                self.plan.execute_tiles_push(1.0, 0.0, src, ys, t0, t1, push)
+            stream_write_flags(flags, k + 1)
+            for t0, t1 in self.base.interior:
+                self.plan.execute_tiles(1.0, 0.0, src, ys, t0, t1)
+        else:
+            self.plan.execute_push(1.0, 0.0, src, ys, push)
+            stream_write_flags(flags, k + 1)
         self.k = k + 1
 
     def run(self, iters: int):
@@ -330,9 +349,14 @@ def build_stencil3d_power_loop(N: int, exchange: str = "auto", options=None, ove
 
     info = plan.info()
     can_split = info.nsplit_rows == 0 and world > 1
+    reads_halo = None
+    if can_split:
+        cmin, cmax = plan.tile_col_range()
+        reads_halo = (cmin < lo) | (cmax >= hi)
     loop = PowerLoop(n=n, bounds=bounds, spmv=spmv, x=x, x_next=x_next, need_local=need, exchange=exchange,
                      spmv_tiles=spmv_tiles if can_split else None,
-                     tile_row=plan.export("tile_row") if can_split else None, overlap=overlap)
+                     tile_row=plan.export("tile_row") if can_split else None, tile_reads_halo=reads_halo,
+                     overlap=overlap)
     return loop, plan, csr
 
 
@@ -409,6 +433,7 @@ def bench_power_loop(N: int = 384, iters: int = 100, exchange: str = "auto", war
         # world size <= 8, so equal values across runs with 1/2/4/8 GPUs prove bitwise-identical results
         "x_checksum_first_16th": bits_checksum(runner.x[0:n // 16]),
         "halo_fused_into_kernel": bool(fused),
+        "fused_boundary_first": bool(fused and getattr(runner, "split", False)),
         "total_timed_ms": ms,
     }
     if fused:
