@@ -135,6 +135,27 @@ int spmv_b200_stream_write_flag(void *stream, uint32_t *d_flag, uint32_t value);
 int spmv_b200_stream_write_flags(void *stream, uint32_t *const *d_flags, int32_t count, uint32_t value); /* <= 8 flags, one launch */
 int spmv_b200_stream_wait_flag(void *stream, uint32_t *d_flag, uint32_t value);
 int spmv_b200_enable_peer_access(int32_t peer_device);
+
+/* The iterated loop x <- A*x of one rank with the fused halo exchange, enqueued natively (no host work per iteration
+ * beyond the launches): iteration k waits until every neighbour's flag is >= k, multiplies buf[k%2] into rows
+ * [row_lo,row_hi) of buf[(k+1)%2] -- boundary row blocks first, pushing the rows other GPUs reference straight into
+ * their buffers (push[(k+1)%2]) --, raises its flag in the neighbours' memory to k+1 and multiplies the interior blocks.
+ * n_boundary == 0: the whole shard is one launch (push included) followed by the flags. */
+#define SPMV_B200_MAX_RANGES 16
+typedef struct spmv_b200_halo_loop_desc {
+  spmv_b200_plan *plan;
+  double *buf[2];
+  int32_t row_lo, row_hi;
+  int32_t n_neigh;
+  uint32_t *wait_flags[SPMV_B200_MAX_PUSH];   /* local words written by the neighbours             */
+  uint32_t *signal_flags[SPMV_B200_MAX_PUSH]; /* words in the neighbours' memory written by this rank */
+  spmv_b200_push push[2];                     /* by parity of the destination buffer                  */
+  int32_t n_boundary, n_interior;
+  int32_t boundary[2 * SPMV_B200_MAX_RANGES]; /* (tile_lo, tile_hi) pairs                             */
+  int32_t interior[2 * SPMV_B200_MAX_RANGES];
+} spmv_b200_halo_loop_desc;
+int spmv_b200_halo_loop_run(const spmv_b200_halo_loop_desc *desc, int32_t first_iteration, int32_t iterations,
+                            void *stream);
 /* exchange buffers other GPUs (other processes) store into: allocated with cudaMalloc on the current device and
  * exported as a 64-byte CUDA IPC handle; the consumer opens the handle with ITS device current, which is what maps
  * the memory for its kernels (cudaIpcMemLazyEnablePeerAccess). peer_free / peer_close release them. */

@@ -332,6 +332,49 @@ int spmv_b200_stream_wait_flag(void *stream, uint32_t *d_flag, uint32_t value) {
   return SPMV_B200_OK;
 }
 
+int spmv_b200_halo_loop_run(const spmv_b200_halo_loop_desc *d, int32_t first_iteration, int32_t iterations,
+                            void *stream) {
+  if (!d || !d->plan || !d->buf[0] || !d->buf[1] || first_iteration < 0 || iterations < 0) {
+    set_error("halo_loop_run: bad argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  if (d->n_neigh < 0 || d->n_neigh > SPMV_B200_MAX_PUSH || d->n_boundary < 0 || d->n_boundary > SPMV_B200_MAX_RANGES ||
+      d->n_interior < 0 || d->n_interior > SPMV_B200_MAX_RANGES || d->row_lo < 0 || d->row_hi < d->row_lo ||
+      d->row_hi - d->row_lo != d->plan->m) {
+    set_error("halo_loop_run: inconsistent descriptor");
+    return SPMV_B200_ERR_ARG;
+  }
+  for (int32_t i = 0; i < iterations; ++i) {
+    const int32_t k = first_iteration + i;
+    int rc;
+    if (k > 0)
+      for (int j = 0; j < d->n_neigh; ++j)
+        if ((rc = spmv_b200_stream_wait_flag(stream, d->wait_flags[j], (uint32_t)k)))
+          return rc;
+    const double *src = d->buf[k & 1];
+    double *ys = d->buf[(k + 1) & 1] + d->row_lo;
+    const spmv_b200_push *push = &d->push[(k + 1) & 1];
+    if (d->n_boundary > 0) {
+      for (int r = 0; r < d->n_boundary; ++r)
+        if ((rc = spmv_b200_execute_tiles_push(d->plan, 1.0, 0.0, src, ys, d->boundary[2 * r], d->boundary[2 * r + 1],
+                                               push, stream)))
+          return rc;
+      if ((rc = spmv_b200_stream_write_flags(stream, d->signal_flags, d->n_neigh, (uint32_t)(k + 1))))
+        return rc;
+      for (int r = 0; r < d->n_interior; ++r)
+        if ((rc = spmv_b200_execute_tiles(d->plan, 1.0, 0.0, src, ys, d->interior[2 * r], d->interior[2 * r + 1],
+                                          stream)))
+          return rc;
+    } else {
+      if ((rc = spmv_b200_execute_push(d->plan, 1.0, 0.0, src, ys, push, stream)))
+        return rc;
+      if ((rc = spmv_b200_stream_write_flags(stream, d->signal_flags, d->n_neigh, (uint32_t)(k + 1))))
+        return rc;
+    }
+  }
+  return SPMV_B200_OK;
+}
+
 int spmv_b200_enable_peer_access(int32_t peer_device) {
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));

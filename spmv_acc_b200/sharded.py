@@ -262,7 +262,35 @@ class FusedHaloLoop:
         self.k = 0
         # boundary-first schedule only if the boundary blocks are known to contain every reader of halo entries
         self.split = bool(getattr(base, "overlapped", False) and getattr(base, "boundary_reads_all_halo", False))
+        self.desc = self._native_desc()
         dist.barrier()
+
+    def _native_desc(self):
+        """Descriptor of spmv_b200_halo_loop_run: the whole loop is then enqueued by the C library, one call per run."""
+        from . import _lib
+        if len(self.neigh) > _lib.MAX_PUSH:
+            return None
+        if self.split and max(len(self.base.boundary), len(self.base.interior)) > _lib.MAX_RANGES:
+            return None
+        d = _lib.HaloLoopDesc()
+        d.plan = self.plan._h
+        d.buf[0], d.buf[1] = self.bufs[0].data_ptr(), self.bufs[1].data_ptr()
+        d.row_lo, d.row_hi = self.lo, self.hi
+        d.n_neigh = len(self.neigh)
+        for j, p in enumerate(self.neigh):
+            d.wait_flags[j] = self.flags.data_ptr() + 4 * p
+            d.signal_flags[j] = self.peer[p].address + 2 * self.xbytes + 4 * self.rank
+        for b in (0, 1):
+            d.push[b].count = len(self.push[b])
+            for j, (lo, hi, dst) in enumerate(self.push[b]):
+                d.push[b].row_lo[j], d.push[b].row_hi[j], d.push[b].dst[j] = int(lo), int(hi), int(dst)
+        if self.split:
+            d.n_boundary, d.n_interior = len(self.base.boundary), len(self.base.interior)
+            for j, (t0, t1) in enumerate(self.base.boundary):
+                d.boundary[2 * j], d.boundary[2 * j + 1] = t0, t1
+            for j, (t0, t1) in enumerate(self.base.interior):
+                d.interior[2 * j], d.interior[2 * j + 1] = t0, t1
+        return d
 
     def close(self):
         import torch
@@ -297,7 +325,16 @@ class FusedHaloLoop:
             stream_write_flags(flags, k + 1)
         self.k = k + 1
 
-    def run(self, iters: int):
+    def run(self, iters: int, native: bool = True):
+        if native and self.desc is not None:
+            import ctypes as C
+            import torch
+            from . import _lib
+            _lib.check(_lib.lib().spmv_b200_halo_loop_run(C.byref(self.desc), self.k, int(iters),
+                                                          int(torch.cuda.current_stream().cuda_stream)),
+                       "halo_loop_run")
+            self.k += int(iters)
+            return self.x
         for _ in range(iters):
             self.step()
         return self.x
@@ -434,6 +471,7 @@ def bench_power_loop(N: int = 384, iters: int = 100, exchange: str = "auto", war
         "x_checksum_first_16th": bits_checksum(runner.x[0:n // 16]),
         "halo_fused_into_kernel": bool(fused),
         "fused_boundary_first": bool(fused and getattr(runner, "split", False)),
+        "loop_enqueued_natively": bool(fused and getattr(runner, "desc", None) is not None),
         "total_timed_ms": ms,
     }
     if fused:
