@@ -15,7 +15,7 @@ LIB_DIR = PKG / "lib"
 ABI_SYMBOLS = [
     "spmv_b200_abi_version", "spmv_b200_last_error", "spmv_b200_plan_create", "spmv_b200_execute",
     "spmv_b200_execute_tiles", "spmv_b200_execute_push", "spmv_b200_stream_write_flag", "spmv_b200_stream_wait_flag",
-    "spmv_b200_execute_tiles_push", "spmv_b200_plan_tile_col_range", "spmv_b200_stream_write_flags",
+    "spmv_b200_execute_tiles_push", "spmv_b200_plan_tile_col_range", "spmv_b200_stream_write_flags", "spmv_b200_stream_wait_flags",
     "spmv_b200_halo_loop_run", "spmv_b200_enable_peer_access", "spmv_b200_peer_alloc", "spmv_b200_peer_open", "spmv_b200_peer_close",
     "spmv_b200_peer_free",
     "spmv_b200_plan_destroy", "spmv_b200_plan_get_info", "spmv_b200_plan_export", "spmv_b200_csr_spmv",
@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
         L.spmv_b200_execute_tiles_push.argtypes = [vp, dbl, dbl, vp, vp, i32, i32, C.POINTER(Push), vp]
         L.spmv_b200_plan_tile_col_range.argtypes = [vp, vp, vp, vp]
         L.spmv_b200_stream_write_flags.argtypes = [vp, C.POINTER(C.c_void_p), i32, C.c_uint32]
+        L.spmv_b200_stream_wait_flags.argtypes = [vp, C.POINTER(C.c_void_p), i32, C.c_uint32]
         L.spmv_b200_halo_loop_run.argtypes = [C.POINTER(HaloLoopDesc), i32, i32, vp]
         L.spmv_b200_stream_write_flag.argtypes = [vp, vp, C.c_uint32]
         L.spmv_b200_stream_wait_flag.argtypes = [vp, vp, C.c_uint32]
