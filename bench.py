@@ -286,7 +286,8 @@ def run_b200(args, rank, world, local_rank):
             traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    dominant = {0: "k_spmv_rows<TMA, SHORT>", 1: "k_spmv_rows<TMA, MEDIUM>", 2: "k_spmv_mixed<TMA>"}[
+    dominant = "k_spmv_warp (direct form)" if info.direct else {
+        0: "k_spmv_rows<TMA, SHORT>", 1: "k_spmv_rows<TMA, MEDIUM>", 2: "k_spmv_mixed<TMA>"}[
         int(np.argmax(list(info.tiles_per_kind)))]
 
     line = {
@@ -328,6 +329,10 @@ def run_b200(args, rank, world, local_rank):
     plan.destroy()
     del csr, x, y
     torch.cuda.empty_cache()
+
+    # ---- the other single-GPU configurations of BASELINE.json (C3 uniform-random, C4 R-MAT): same timing, rank 0 ----
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        line["other_configs"] = run_other_configs(torch, args, peak)
 
     # ---- iterated configuration C5 (power loop with exchange of x) ----
     if not args.no_iterated:
@@ -379,6 +384,51 @@ def run_cusparse(torch, csr, x, y, args):
             X.spmv_b200_ctx_cusparse_destroy(h)
     except Exception as e:
         out["error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
+def run_other_configs(torch, args, peak):
+    """C3 and C4 of BASELINE.json, device resident, default plan options: ms / GFLOP/s / fraction of the HBM roofline,
+    next to cuSPARSE on the same buffers. Not the headline; reported so that one run covers every single-GPU config."""
+    from spmv_acc_b200 import CsrDesc, SpmvPlan, synth
+    out = {}
+    makers = {
+        "C3 uniform-random 1e7 x 1e7, 32 nnz/row": lambda: synth.uniform_device(10_000_000, 10_000_000, 32, seed=1),
+        "C4 R-MAT 2^24 rows, 2^28 nnz": lambda: synth.rmat_device(24, 16, seed=1),
+    }
+    for name, make in makers.items():
+        try:
+            csr = make()
+            plan = SpmvPlan(CsrDesc(csr.rows, csr.cols, csr.nnz, csr.rowptr, csr.col, csr.val))
+            info = plan.info()
+            x = synth.vector_device(csr.cols, 2)
+            y = synth.vector_device(csr.rows, 3)
+            for _ in range(5):
+                plan.execute(1.0, 1.0, x, y)
+            torch.cuda.synchronize()
+            reps = 30
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                plan.execute(1.0, 1.0, x, y)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            b = alg_bytes(csr.rows, csr.cols, csr.nnz)
+            gbs = b / (ms * 1e-3) / 1e9
+            out[name] = {"ms": ms, "gflops": 2.0 * csr.nnz / (ms * 1e-3) / 1e9, "effective_gbs": gbs,
+                         "frac_of_measured_peak": gbs / peak, "frac_of_nominal_8TBs": gbs / NOMINAL_HBM_GBS,
+                         "form": "direct (warp per row block, no shared memory)" if info.direct else "tiled (TMA)",
+                         "tile_nnz": info.tile_nnz, "tiles_per_kind": list(info.tiles_per_kind),
+                         "split_rows": info.nsplit_rows, "launches_per_spmv": info.launches_per_execute,
+                         "bound": "x gathers (L1 lines in flight), see DESIGN.md §3.5"}
+            if not args.no_context:
+                out[name]["context"] = run_cusparse(torch, csr, x, y, args)
+            plan.destroy()
+            del csr, x, y
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
     return out
 
 
@@ -443,6 +493,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-context", action="store_true")
     ap.add_argument("--no-iterated", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the C3 / C4 lines (N = 1 only)")
     ap.add_argument("--iter-grid", type=int, default=384)
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "halo"])

@@ -173,8 +173,9 @@ int spmv_b200_plan_create(spmv_b200_plan **out, int32_t m, int32_t n, int64_t nn
     rc = analysis_run(p, static_cast<cudaStream_t>(stream));
   // Automatic tile size, second look: a tile that owns more rows than the row kernels have lane groups costs the CTA a
   // second pass over its rows. T was derived from the average row; if rows a little shorter than the average (domain
-  // boundaries of a stencil) push more than a quarter of the tiles over the limit, one step down is faster
-  // (measured on the interior z-slabs of the 27-point stencil: 0.89 ms with T = 3584, 0.81 ms with T = 3328).
+  // boundaries of a stencil) push more than 15 % of the tiles over the limit, one step down is faster (measured on an
+  // interior z-slab of the 27-point stencil, 1/8 of 384^3: 21.8 % of the tiles over, 0.447 ms with T = 3584, 0.407 ms
+  // with T = 3328).
   if (rc == SPMV_B200_OK && !(opt && opt->tile_nnz) && !p->direct && p->T > 1024 && p->ntiles > 0 &&
       p->count[SPMV_B200_KIND_MIXED] == 0) {
     const double avg = (double)p->nnz / (double)p->m;
@@ -186,7 +187,7 @@ int spmv_b200_plan_create(spmv_b200_plan **out, int32_t m, int32_t n, int64_t nn
     long long over = 0;
     for (int t = 0; t < p->ntiles; ++t)
       over += (p->h_tile_row[t + 1] - p->h_tile_row[t]) > G ? 1 : 0;
-    if (4 * over > p->ntiles) {
+    if (20 * over > 3 * (long long)p->ntiles) { // > 15 %: C2 (12.5 % at T = 1536, still the faster choice) stays
       free_plan_arrays(p);
       reset_plan_arrays(p);
       p->T -= 256;
