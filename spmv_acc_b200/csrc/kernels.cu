@@ -24,6 +24,9 @@
 // merge_path_update.h:8-64). The epilogue y = alpha*sum + beta*y follows cli/verification.cpp:64.
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "internal.cuh"
 
@@ -1029,7 +1032,21 @@ static RowsKernel mixed_kernel(bool tma, int threads, bool queue_form = false) {
   }
 }
 
+// The dynamic shared-memory limit is an attribute of the kernel function, not of a plan: several plans with different
+// tile sizes may be alive at once, so the limit is only ever raised (per device).
 template <typename K> static int set_smem(K kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void *, int>, size_t> limit;
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &cur = limit[std::make_pair(reinterpret_cast<const void *>(kernel), dev)];
+    if (bytes <= cur)
+      bytes = cur;
+    else
+      cur = bytes;
+  }
   B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   // development knob: SPMV_B200_CARVEOUT=<percent of the unified L1/shared array given to shared memory>
   if (const char *env = getenv("SPMV_B200_CARVEOUT")) {

@@ -297,3 +297,22 @@ def test_full_size_c4_rmat_row_sums():
     assert bool(((y - ref).abs() <= 2e-12 * absum + 1e-300).all())
     assert int((lens == 0).sum()) > 0 and float(y[lens == 0].abs().max()) == 0.0
     p.destroy()
+
+
+def test_plans_with_different_tile_sizes_coexist():
+    """The shared-memory limit is a property of the kernel function: creating a plan with small tiles must not break a
+    live plan with large tiles (regression: 'invalid argument' at launch)."""
+    import torch
+    h = synth.stencil3d_numpy(24)
+    d = synth.to_device(h)
+    x, y0 = synth.vector_numpy(h.cols, 2), synth.vector_numpy(h.rows, 3)
+    big = SpmvPlan(desc_of(d), make_options(8192))
+    small = SpmvPlan(desc_of(d), make_options(512))
+    dx = torch.from_numpy(x).cuda()
+    for plan in (big, small, big):
+        dy = torch.from_numpy(y0).cuda()
+        plan.execute(1.0, 1.0, dx, dy)
+        torch.cuda.synchronize()
+        assert_parity(h, x, y0, 1.0, 1.0, dy.cpu().numpy(), what="coexisting plans")
+    big.destroy()
+    small.destroy()
