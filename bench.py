@@ -457,9 +457,10 @@ def run_e2e(torch, dist, world, csr, x, n_global, nnz_total, args):
     torch.cuda.synchronize()
     sec = (time.perf_counter() - t0) / steps
     sec = max_over_ranks(torch, dist, world, sec)
+    x_lo, x_hi = hm.x_range()  # only the referenced part of x is copied (a row shard reads its rows' columns + halo)
     hm.destroy()
     return {"value": 2.0 * nnz_total / sec / 1e9, "unit": "GFLOP/s", "ms_per_step": sec * 1e3,
-            "h2d_bytes_per_step": int(8 * (n_global + h.rows)), "d2h_bytes_per_step": int(8 * h.rows),
+            "h2d_bytes_per_step": int(8 * ((x_hi - x_lo) + h.rows)), "d2h_bytes_per_step": int(8 * h.rows),
             "steps": steps, "api": "spmv_b200_hostmat_spmv (matrix resident, x and y0 copied in, y copied out "
                                    "from/to pinned host memory every step; cli/main.cpp:99-118 pattern)",
             "cold_upload_and_analyse_ms": cold_s * 1e3}

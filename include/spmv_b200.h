@@ -185,6 +185,8 @@ int spmv_b200_cache_size(void);
 int spmv_b200_hostmat_create(spmv_b200_hostmat **out, int32_t m, int32_t n, int64_t nnz, const int32_t *h_rowptr,
                              const int32_t *h_colidx, const double *h_val, const spmv_b200_options *opt);
 int spmv_b200_hostmat_spmv(spmv_b200_hostmat *hm, double alpha, double beta, const double *h_x, double *h_y);
+/* columns [col_lo, col_hi) the matrix references: the only part of h_x that hostmat_spmv reads and copies */
+int spmv_b200_hostmat_x_range(const spmv_b200_hostmat *hm, int32_t *col_lo, int32_t *col_hi);
 int spmv_b200_hostmat_destroy(spmv_b200_hostmat *hm);
 /* one-shot: upload, analyse, multiply, download, free */
 int spmv_b200_host_spmv(double alpha, double beta, int32_t m, int32_t n, int64_t nnz, const int32_t *h_rowptr,

@@ -235,6 +235,12 @@ class HostMatrix:
         check(_lib.lib().spmv_b200_hostmat_spmv(self._h, float(alpha), float(beta), _ptr(h_x), _ptr(h_y)),
               "hostmat_spmv")
 
+    def x_range(self):
+        """Columns [lo, hi) the matrix references: the only part of ``h_x`` that ``spmv`` reads and copies."""
+        lo, hi = C.c_int32(), C.c_int32()
+        check(_lib.lib().spmv_b200_hostmat_x_range(self._h, C.byref(lo), C.byref(hi)), "hostmat_x_range")
+        return int(lo.value), int(hi.value)
+
     def destroy(self) -> None:
         if self._h:
             h, self._h = self._h, C.c_void_p()

@@ -759,6 +759,9 @@ struct spmv_b200_hostmat {
   cudaStream_t s_in = nullptr, s_out = nullptr;  // host->device and device->host copy streams (pipelined path)
   cudaEvent_t ev_x = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;       // per chunk: y0 chunk arrived / chunk computed
+  // columns the matrix references: only x[col_lo, col_hi) is copied to the device; per tile for the pipelined path
+  int col_lo = 0, col_hi = 0;
+  std::vector<int> tile_cmax;
 };
 
 constexpr int kHostChunksMax = 64;
@@ -815,7 +818,37 @@ static int hostmat_build(spmv_b200_hostmat *hm, const int32_t *h_rowptr, const i
     B200_CUDA(cudaMemcpyAsync(hm->d_col, h_colidx, sizeof(int) * nnz, cudaMemcpyHostToDevice, hm->stream));
     B200_CUDA(cudaMemcpyAsync(hm->d_val, h_val, sizeof(double) * nnz, cudaMemcpyHostToDevice, hm->stream));
   }
-  return spmv_b200_plan_create(&hm->plan, hm->m, hm->n, hm->nnz, hm->d_rowptr, hm->d_col, hm->d_val, opt, hm->stream);
+  int rc = spmv_b200_plan_create(&hm->plan, hm->m, hm->n, hm->nnz, hm->d_rowptr, hm->d_col, hm->d_val, opt, hm->stream);
+  if (rc != SPMV_B200_OK)
+    return rc;
+  hm->col_lo = 0;
+  hm->col_hi = hm->n;
+  if (hm->plan->ntiles > 0 && nnz > 0) {
+    std::vector<int> cmin((size_t)hm->plan->ntiles);
+    hm->tile_cmax.resize((size_t)hm->plan->ntiles);
+    if ((rc = analysis_tile_col_range(hm->plan, cmin.data(), hm->tile_cmax.data(), hm->stream)))
+      return rc;
+    int lo = 0x7fffffff, hi = -1;
+    for (int t = 0; t < hm->plan->ntiles; ++t) {
+      lo = cmin[(size_t)t] < lo ? cmin[(size_t)t] : lo;
+      hi = hm->tile_cmax[(size_t)t] > hi ? hm->tile_cmax[(size_t)t] : hi;
+    }
+    if (hi >= lo && lo >= 0 && hi < hm->n) {
+      hm->col_lo = lo;
+      hm->col_hi = hi + 1;
+    }
+  }
+  return SPMV_B200_OK;
+}
+
+int spmv_b200_hostmat_x_range(const spmv_b200_hostmat *hm, int32_t *col_lo, int32_t *col_hi) {
+  if (!hm || !col_lo || !col_hi) {
+    set_error("hostmat_x_range: NULL argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  *col_lo = hm->col_lo;
+  *col_hi = hm->col_hi;
+  return SPMV_B200_OK;
 }
 
 int spmv_b200_hostmat_create(spmv_b200_hostmat **out, int32_t m, int32_t n, int64_t nnz, const int32_t *h_rowptr,
@@ -855,14 +888,25 @@ int spmv_b200_hostmat_spmv(spmv_b200_hostmat *hm, double alpha, double beta, con
   // PCIe directions are busy at the same time. Rows of a chunk are final once its kernels have run.
   const int kHostChunks = host_chunks();
   if (p->nsplit == 0 && p->ntiles >= 4 * kHostChunks && hm->m > 0) {
-    if (hm->n > 0)
-      B200_CUDA(cudaMemcpyAsync(hm->d_x, h_x, sizeof(double) * (size_t)hm->n, cudaMemcpyHostToDevice, hm->s_in));
-    B200_CUDA(cudaEventRecord(hm->ev_x, hm->s_in));
-    B200_CUDA(cudaStreamWaitEvent(hm->stream, hm->ev_x, 0));
+    // x travels in pieces as well: a chunk of row blocks needs x up to the largest column it references, so for banded
+    // matrices the first kernel starts after 1/chunks of the input has arrived; a matrix whose first rows reference the
+    // last columns simply gets the whole referenced range up front.
+    int x_sent = hm->col_lo;
     for (int c = 0; c < kHostChunks; ++c) {
       const int tlo = (int)((long long)p->ntiles * c / kHostChunks);
       const int thi = (int)((long long)p->ntiles * (c + 1) / kHostChunks);
       const size_t rlo = (size_t)p->h_tile_row[tlo], rhi = (size_t)p->h_tile_row[thi];
+      int need = x_sent;
+      if (hm->tile_cmax.empty())
+        need = hm->col_hi;
+      else
+        for (int t = tlo; t < thi; ++t)
+          need = hm->tile_cmax[(size_t)t] + 1 > need ? hm->tile_cmax[(size_t)t] + 1 : need;
+      if (need > x_sent) {
+        B200_CUDA(cudaMemcpyAsync(hm->d_x + x_sent, h_x + x_sent, sizeof(double) * (size_t)(need - x_sent),
+                                  cudaMemcpyHostToDevice, hm->s_in));
+        x_sent = need;
+      }
       if (rhi > rlo)
         B200_CUDA(cudaMemcpyAsync(hm->d_y + rlo, h_y + rlo, sizeof(double) * (rhi - rlo), cudaMemcpyHostToDevice,
                                   hm->s_in));
@@ -881,8 +925,9 @@ int spmv_b200_hostmat_spmv(spmv_b200_hostmat *hm, double alpha, double beta, con
     B200_CUDA(cudaStreamSynchronize(hm->stream));
     return SPMV_B200_OK;
   }
-  if (hm->n > 0)
-    B200_CUDA(cudaMemcpyAsync(hm->d_x, h_x, sizeof(double) * (size_t)hm->n, cudaMemcpyHostToDevice, hm->stream));
+  if (hm->col_hi > hm->col_lo)
+    B200_CUDA(cudaMemcpyAsync(hm->d_x + hm->col_lo, h_x + hm->col_lo, sizeof(double) * (size_t)(hm->col_hi - hm->col_lo),
+                              cudaMemcpyHostToDevice, hm->stream));
   if (hm->m > 0)
     B200_CUDA(cudaMemcpyAsync(hm->d_y, h_y, sizeof(double) * (size_t)hm->m, cudaMemcpyHostToDevice, hm->stream));
   const int rc = spmv_b200_execute(hm->plan, alpha, beta, hm->d_x, hm->d_y, hm->stream);

@@ -224,6 +224,26 @@ def test_host_buffer_path_pipelined_chunks():
         hm.destroy()
 
 
+def test_host_buffer_path_copies_only_the_referenced_part_of_x():
+    """A row shard references its own columns plus a halo: entries of h_x outside that range are neither copied nor
+    read (they are poisoned with NaN here), in the pipelined and in the single-shot host path."""
+    N = 40
+    full_rows = N ** 3
+    for lo, hi in ((full_rows // 3, 2 * full_rows // 3), (full_rows // 2, full_rows // 2 + 700)):
+        h = synth.stencil3d_numpy(N, lo, hi)
+        x, y0 = synth.vector_numpy(h.cols, 2), synth.vector_numpy(h.rows, 3)
+        hm = HostMatrix(h.rows, h.cols, h.rowptr, h.col, h.val)
+        c0, c1 = hm.x_range()
+        assert (c0, c1) == (int(h.col.min()), int(h.col.max()) + 1) and c1 - c0 < h.cols
+        xp = x.copy()
+        xp[:c0] = np.nan
+        xp[c1:] = np.nan
+        y = y0.copy()
+        hm.spmv(0.75, -0.5, xp, y)
+        assert_parity(h, x, y0, 0.75, -0.5, y, what=f"hostmat shard rows {lo}:{hi}")
+        hm.destroy()
+
+
 def test_bad_options_are_rejected():
     d = synth.to_device(synth.stencil2d_numpy(8))
     for bad in (make_options(100), make_options(2048, 8, 4096), make_options(2048, 300, 128), make_options(2048, 8, 126)):
