@@ -387,6 +387,32 @@ def run_cusparse(torch, csr, x, y, args):
             out[name] = {"ms": ms, "gflops": 2.0 * csr.nnz / (ms * 1e-3) / 1e9,
                          "effective_gbs": alg_bytes(csr.rows, csr.cols, csr.nnz) / (ms * 1e-3) / 1e9}
             X.spmv_b200_ctx_cusparse_destroy(h)
+        # cub::DeviceSpmv::CsrMV computes y = A*x (no alpha / beta), like the reference's adapter benchmark_cub.hpp:25
+        h = C.c_void_p()
+        rc = X.spmv_b200_ctx_cub_create(C.byref(h), csr.rows, csr.cols, csr.nnz, csr.rowptr.data_ptr(),
+                                        csr.col.data_ptr(), csr.val.data_ptr(), x.data_ptr(), yy.data_ptr())
+        if rc != 0:
+            out["cub_device_spmv"] = {"error": rc}
+        else:
+            stream = torch.cuda.current_stream().cuda_stream
+            call = lambda: X.spmv_b200_ctx_cub_spmv(h, csr.rows, csr.cols, csr.nnz, csr.rowptr.data_ptr(),  # noqa: E731
+                                                    csr.col.data_ptr(), csr.val.data_ptr(), x.data_ptr(),
+                                                    yy.data_ptr(), stream)
+            for _ in range(5):
+                call()
+            torch.cuda.synchronize()
+            reps = max(20, min(args.steps, 200))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                call()
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            out["cub_device_spmv"] = {"ms": ms, "gflops": 2.0 * csr.nnz / (ms * 1e-3) / 1e9,
+                                      "effective_gbs": alg_bytes(csr.rows, csr.cols, csr.nnz) / (ms * 1e-3) / 1e9,
+                                      "note": "y = A*x only (beta = 0, alpha = 1)"}
+            X.spmv_b200_ctx_cub_destroy(h)
     except Exception as e:
         out["error"] = f"{type(e).__name__}: {e}"
     return out

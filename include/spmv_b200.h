@@ -192,6 +192,12 @@ int spmv_b200_hostmat_destroy(spmv_b200_hostmat *hm);
 int spmv_b200_host_spmv(double alpha, double beta, int32_t m, int32_t n, int64_t nnz, const int32_t *h_rowptr,
                         const int32_t *h_colidx, const double *h_val, const double *h_x, double *h_y);
 
+/* ---- COO -> CSR on the device (0-based int32 row / col, fp64 values, any order, duplicates kept): entries sorted by
+ * (row, col), equal pairs in input order. Device-side form of matrix_market::to_csr, cli/sparse_format.h:100-128.
+ * Outputs are caller-allocated device arrays: rowptr[m+1], col[nnz], val[nnz]. ---- */
+int spmv_b200_coo_to_csr(int32_t m, int32_t n, int64_t nnz, const int32_t *d_row, const int32_t *d_col,
+                         const double *d_val, int32_t *d_rowptr_out, int32_t *d_col_out, double *d_val_out, void *stream);
+
 /* ---- row sharding for multi-GPU runs: bounds[g] = lower_bound(rowptr, g*nnz/nshards), bounds[nshards] = m ---- */
 int spmv_b200_shard_bounds(int32_t m, int64_t nnz, const int32_t *d_rowptr, int32_t nshards, int32_t *h_bounds,
                            void *stream);

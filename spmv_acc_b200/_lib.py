@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "spmv_b200_peer_free",
     "spmv_b200_plan_destroy", "spmv_b200_plan_get_info", "spmv_b200_plan_export", "spmv_b200_csr_spmv",
     "spmv_b200_sparse_spmv", "spmv_b200_cache_invalidate", "spmv_b200_cache_size", "spmv_b200_hostmat_create",
-    "spmv_b200_hostmat_spmv", "spmv_b200_hostmat_x_range", "spmv_b200_hostmat_destroy", "spmv_b200_host_spmv", "spmv_b200_shard_bounds",
+    "spmv_b200_hostmat_spmv", "spmv_b200_hostmat_x_range", "spmv_b200_hostmat_destroy", "spmv_b200_host_spmv", "spmv_b200_coo_to_csr", "spmv_b200_shard_bounds",
     "spmv_b200_col_block_bitmap",
 ]
 
@@ -117,6 +117,7 @@ def lib() -> C.CDLL:
         L.spmv_b200_hostmat_destroy.argtypes = [vp]
         L.spmv_b200_hostmat_x_range.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
         L.spmv_b200_host_spmv.argtypes = [dbl, dbl, i32, i32, i64, vp, vp, vp, vp, vp]
+        L.spmv_b200_coo_to_csr.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, vp, vp]
         L.spmv_b200_shard_bounds.argtypes = [i32, i64, vp, i32, vp, vp]
         L.spmv_b200_col_block_bitmap.argtypes = [i64, vp, i32, i32, vp, vp]
         for s in ABI_SYMBOLS:
@@ -152,6 +153,9 @@ def ctx() -> C.CDLL:
         X.spmv_b200_ctx_cusparse_create.argtypes = [C.POINTER(vp), i32, i32, i64, vp, vp, vp, vp, vp, i32]
         X.spmv_b200_ctx_cusparse_spmv.argtypes = [vp, dbl, dbl, vp]
         X.spmv_b200_ctx_cusparse_destroy.argtypes = [vp]
+        X.spmv_b200_ctx_cub_create.argtypes = [C.POINTER(vp), i32, i32, i32, vp, vp, vp, vp, vp]
+        X.spmv_b200_ctx_cub_spmv.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+        X.spmv_b200_ctx_cub_destroy.argtypes = [vp]
         X.spmv_b200_ctx_gather_bound.argtypes = [i64, vp, vp, vp, vp, i32, i32, i32, vp]
         _ctx = X
     return _ctx

@@ -326,6 +326,22 @@ class PeerBuffer:
             self.address = 0
 
 
+def coo_to_csr(rows: int, cols: int, d_row: Any, d_col: Any, d_val: Any) -> CsrDesc:
+    """COO on the device (int32 row / col, fp64 values, any order, duplicates kept) -> CsrDesc with new device arrays,
+    entries sorted by (row, col) like the reference's matrix_market::to_csr (cli/sparse_format.h:100-128)."""
+    import torch
+    _require_device(d_row, "row", "int32")
+    _require_device(d_col, "col", "int32")
+    _require_device(d_val, "val", "float64")
+    nnz = int(d_val.numel())
+    rowptr = torch.empty(rows + 1, dtype=torch.int32, device=d_val.device)
+    col = torch.empty(max(nnz, 1), dtype=torch.int32, device=d_val.device)
+    val = torch.empty(max(nnz, 1), dtype=torch.float64, device=d_val.device)
+    check(_lib.lib().spmv_b200_coo_to_csr(int(rows), int(cols), nnz, _ptr(d_row), _ptr(d_col), _ptr(d_val),
+                                          _ptr(rowptr), _ptr(col), _ptr(val), _current_stream()), "coo_to_csr")
+    return CsrDesc(int(rows), int(cols), nnz, rowptr, col[:nnz], val[:nnz])
+
+
 def shard_bounds(d_rowptr: Any, rows: int, nshards: int) -> np.ndarray:
     """nnz-balanced contiguous row shards: bounds[g] = lower_bound(rowptr, g*nnz/nshards) (int32, length nshards+1)."""
     _require_device(d_rowptr, "rowptr", "int32")

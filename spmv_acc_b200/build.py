@@ -24,7 +24,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-shared", f"
 
 TARGETS = {
     # library -> (sources, extra link flags)
-    "libspmv_b200.so": (["analysis.cu", "kernels.cu", "capi.cu"], []),
+    "libspmv_b200.so": (["analysis.cu", "kernels.cu", "convert.cu", "capi.cu"], []),
     "libspmv_b200_gen.so": (["gen.cu"], []),
     "libspmv_b200_ctx.so": (["context_baselines.cu"], ["-lcusparse"]),
 }

@@ -964,6 +964,17 @@ int spmv_b200_shard_bounds(int32_t m, int64_t nnz, const int32_t *d_rowptr, int3
   return shard_bounds_run(m, nnz, d_rowptr, nshards, h_bounds, static_cast<cudaStream_t>(stream));
 }
 
+int spmv_b200_coo_to_csr(int32_t m, int32_t n, int64_t nnz, const int32_t *d_row, const int32_t *d_col,
+                         const double *d_val, int32_t *d_rowptr_out, int32_t *d_col_out, double *d_val_out, void *stream) {
+  if (m < 0 || n < 0 || nnz < 0 || nnz > 0x7fffffffLL || !d_rowptr_out ||
+      (nnz > 0 && (!d_row || !d_col || !d_val || !d_col_out || !d_val_out))) {
+    set_error("coo_to_csr: invalid argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  return coo_to_csr_run(m, n, nnz, d_row, d_col, d_val, d_rowptr_out, d_col_out, d_val_out,
+                        static_cast<cudaStream_t>(stream));
+}
+
 int spmv_b200_col_block_bitmap(int64_t nnz, const int32_t *d_colidx, int32_t n, int32_t block_shift,
                                uint8_t *h_bitmap, void *stream) {
   if (!h_bitmap || (nnz > 0 && !d_colidx)) {

@@ -3,6 +3,7 @@
 // CUDA_R_64F), with the handle / descriptor / buffer creation hoisted out of the timed call.
 #include <cuda_runtime.h>
 #include <cusparse.h>
+#include <cub/device/device_spmv.cuh>
 #include <stdint.h>
 
 #define CTX_API extern "C" __attribute__((visibility("default")))
@@ -151,4 +152,38 @@ CTX_API int spmv_b200_ctx_gather_bound(long long nnz, const int *d_col, const do
   }
   k<<<grid, 256, smem_bytes > 0 ? smem_bytes : 0, static_cast<cudaStream_t>(stream)>>>(d_col, d_val, d_x, nnz, d_out);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cub::DeviceSpmv::CsrMV (merge-based, y = A*x), the second comparator of the reference harness
+// (benchmark/cub/spmv.cu:30-37: size query, cudaMalloc of the buffer, one call). Context only.
+// ---------------------------------------------------------------------------------------------------------------
+struct ctx_cub {
+  void *buffer = nullptr;
+  size_t bytes = 0;
+};
+
+CTX_API int spmv_b200_ctx_cub_destroy(ctx_cub *c) {
+  if (!c) return 0;
+  if (c->buffer) cudaFree(c->buffer);
+  delete c;
+  return 0;
+}
+
+CTX_API int spmv_b200_ctx_cub_create(ctx_cub **out, int m, int n, int nnz, const int *d_rowptr, const int *d_col,
+                                     const double *d_val, const double *d_x, double *d_y) {
+  ctx_cub *c = new ctx_cub();
+  if (cub::DeviceSpmv::CsrMV<double>(nullptr, c->bytes, d_val, d_rowptr, d_col, d_x, d_y, m, n, nnz) != cudaSuccess ||
+      cudaMalloc(&c->buffer, c->bytes ? c->bytes : 16) != cudaSuccess) {
+    spmv_b200_ctx_cub_destroy(c);
+    return 1;
+  }
+  *out = c;
+  return 0;
+}
+
+CTX_API int spmv_b200_ctx_cub_spmv(ctx_cub *c, int m, int n, int nnz, const int *d_rowptr, const int *d_col,
+                                   const double *d_val, const double *d_x, double *d_y, void *stream) {
+  return (int)cub::DeviceSpmv::CsrMV<double>(c->buffer, c->bytes, d_val, d_rowptr, d_col, d_x, d_y, m, n, nnz,
+                                             static_cast<cudaStream_t>(stream));
 }

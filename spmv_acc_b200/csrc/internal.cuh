@@ -149,6 +149,10 @@ int shard_bounds_run(int m, long long nnz, const int *d_rowptr, int nshards, int
 int col_block_bitmap_run(long long nnz, const int *d_col, int n, int block_shift, unsigned char *h_bitmap,
                          cudaStream_t stream);
 
+// convert.cu
+int coo_to_csr_run(int m, int n, long long nnz, const int *d_row, const int *d_col, const double *d_val,
+                   int *d_rowptr_out, int *d_col_out, double *d_val_out, cudaStream_t stream);
+
 // kernels.cu
 int kernels_configure(spmv_b200_plan *p);
 int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y,

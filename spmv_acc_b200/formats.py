@@ -109,7 +109,9 @@ def coo_to_csr(rows: int, cols: int, r: np.ndarray, c: np.ndarray, v: np.ndarray
     return Csr(rows, cols, rowptr, c.astype(np.int32), v.astype(np.float64))
 
 
-def read_mtx(path) -> Csr:
+def _read_mtx_coo(path):
+    """Header checks, 1-based -> 0-based, symmetric / Hermitian mirroring: the parsing half of
+    cli/matrix_market_reader.hpp:50-303. Returns (rows, cols, row, col, val) in file order."""
     with open(path, "r") as f:
         first = f.readline()
         if not first.startswith("%%MatrixMarket matrix coordinate"):
@@ -138,8 +140,21 @@ def read_mtx(path) -> Csr:
             rr.append(r - 1); cc.append(c - 1); vv.append(v)
             if mirrored and r != c:
                 rr.append(c - 1); cc.append(r - 1); vv.append(v)
-    return coo_to_csr(rows, cols, np.array(rr, dtype=np.int64), np.array(cc, dtype=np.int64),
-                      np.array(vv, dtype=np.float64))
+    return rows, cols, np.array(rr, dtype=np.int64), np.array(cc, dtype=np.int64), np.array(vv, dtype=np.float64)
+
+
+def read_mtx(path) -> Csr:
+    return coo_to_csr(*_read_mtx_coo(path))
+
+
+def read_mtx_device(path):
+    """MatrixMarket file -> CsrDesc with device arrays: the text is parsed on the host, the COO -> CSR conversion (sort by
+    (row, col), row offsets) runs on the GPU (spmv_b200_coo_to_csr)."""
+    import torch
+    from . import api
+    rows, cols, r, c, v = _read_mtx_coo(path)
+    return api.coo_to_csr(rows, cols, torch.from_numpy(r.astype(np.int32)).cuda(),
+                          torch.from_numpy(c.astype(np.int32)).cuda(), torch.from_numpy(v).cuda())
 
 
 def write_mtx(path, csr: Csr, symmetric_lower_only: bool = False) -> None:
