@@ -84,3 +84,15 @@ def test_reference_reader_reads_the_committed_c1_file():
     g = np.load(GOLDEN / "c1_circuit.npz")
     assert np.array_equal(rp, g["rowptr"]) and np.array_equal(col, g["col"]) and np.array_equal(val, g["val"])
     assert np.array_equal(x, g["x"]) and n == 7602
+
+
+def test_csr_tool_output_follows_the_reference_tool():
+    """Hand-checked against tools/main.cpp:125-181 on rows of length 2, 0, 3, 0, 0, 1, 4."""
+    from spmv_acc_b200 import csr_tool
+    rp = np.array([0, 2, 2, 5, 5, 5, 6, 10], np.int32)
+    assert csr_tool.dist_lines(rp) == ["0 = 3", "1 = 1", "2 = 1", "3 = 1", "4 = 1"]
+    # 3 parts -> ceil(7/3) = 3 rows per part: rows 0-2 (5 nnz), 3-5 (1 nnz), last part row 6 (4 nnz)
+    assert csr_tool.part_nnz_lines(rp, 3) == ["[part ID] [part nnz] [avg-nnz/row]", "0 5 1.66667", "1 1 0.333333", "2 4 4"]
+    # parts == 0: one part per row
+    assert csr_tool.part_nnz_lines(rp, 0)[1:4] == ["0 2 2", "1 0 0", "2 3 3"]
+    assert csr_tool.main(["dist", str(GOLDEN / "rajat03_standin.csr")]) == 0
