@@ -295,3 +295,34 @@ int port_tiled_spmv(double alpha, double beta, const double *value, const int *r
       return -7;
   return 0;
 }
+
+/* The reference's run-time strategy selector, restated (src/acc/hip-adaptive/adaptive.cpp:16-67): four samples of the
+ * host row pointers decide which of its kernels multiplies the matrix. Integer arithmetic throughout, including the
+ * average (bp_3 / m, :29) and the imbalance ratio of the two row halves (:34-35). Returns
+ *   0 vector-row with two data blocks (:34-40)   1 adaptive line (:43-49)          2 adaptive line-enhance (:52-55)
+ *   3 adaptive flat (:60-63)                     4 line-enhance (:66)
+ * An empty half (division by zero in the reference) is reported as the two-block case. Used by the selector study in
+ * DESIGN.md §7, which sets the reference's choice next to the tile kinds our analysis assigns. */
+int port_adaptive_choice(const int *rowptr, int m) {
+  if (m <= 0)
+    return 4;
+  const int bp_1 = rowptr[m / 2];
+  const int bp_3 = rowptr[m];
+  const int avg_nnz_per_row = bp_3 / m;
+  const int nnz_block_0 = bp_1 - 0;
+  const int nnz_block_1 = bp_3 - bp_1;
+  if (nnz_block_0 == 0 || nnz_block_1 == 0) {
+    if (nnz_block_0 != nnz_block_1)
+      return 0;
+  } else if ((nnz_block_1 > nnz_block_0 && nnz_block_1 / nnz_block_0 >= 4) ||
+             (nnz_block_0 > nnz_block_1 && nnz_block_0 / nnz_block_1 >= 4)) {
+    return 0;
+  }
+  if (avg_nnz_per_row <= 4)
+    return 1;
+  if (bp_3 <= 0xC00000)
+    return 2;
+  if (bp_3 > (1 << 23))
+    return 3;
+  return 4;
+}

@@ -17,7 +17,7 @@ REFERENCE = Path("/root/reference")
 __all__ = [
     "build", "have_ref", "port_host_spmv", "port_host_spmv_ax", "port_verify_y", "port_verify", "port_row_bound",
     "port_generate_vector", "port_merge_path_partition", "port_flat_break_points_v2", "port_analysis",
-    "port_shard_bounds", "port_gather_stat", "port_tiled_spmv", "port_direct_arrays", "ref_host_spmv", "ref_host_spmv_ax", "ref_verify_y",
+    "port_shard_bounds", "port_gather_stat", "port_tiled_spmv", "port_direct_arrays", "port_adaptive_choice", "ref_host_spmv", "ref_host_spmv_ax", "ref_verify_y",
     "ref_adaptive_plus_analyze", "ref_read", "ref_generate_vector", "best_host_spmv", "check_rows",
 ]
 
@@ -253,6 +253,18 @@ def port_direct_arrays(rowptr, tile_row):
     tile_row = np.asarray(tile_row, dtype=np.int64)
     nzbase = np.searchsorted(nz_rows, tile_row[:-1], side="left").astype(_i32)
     return {"row_start_bits": bits, "nz_rows": nz_rows, "tile_nzbase": nzbase}
+
+
+ADAPTIVE_CHOICES = ["vector-row, two data blocks", "adaptive line", "adaptive line-enhance", "adaptive flat",
+                    "line-enhance"]
+
+
+def port_adaptive_choice(rowptr) -> str:
+    """Which kernel the reference's run-time selector would pick (src/acc/hip-adaptive/adaptive.cpp:16-67)."""
+    rowptr = _c(rowptr, _i32)
+    lib = _port_lib()
+    lib.port_adaptive_choice.restype = C.c_int
+    return ADAPTIVE_CHOICES[int(lib.port_adaptive_choice(_p(rowptr, C.c_int), C.c_int(rowptr.size - 1)))]
 
 
 def port_gather_stat(rowptr, col, medium_max=128):

@@ -142,3 +142,22 @@ def test_port_direct_arrays_small_known_answer():
     rowptr = np.array([0, 40, 40, 70], np.int32)
     out = oracle.port_direct_arrays(rowptr, np.array([0, 3]))
     assert out["row_start_bits"].tolist() == [1, 1 << 8, 0]
+
+
+def test_port_adaptive_choice_on_the_baseline_shapes():
+    """The reference's 4-sample selector (src/acc/hip-adaptive/adaptive.cpp:16-67) on the row pointers of the
+    BASELINE.json configs; SURVEY.md §8a lists the same picks."""
+    g = load_golden("c1_circuit")
+    assert oracle.port_adaptive_choice(g["rowptr"]) == "adaptive line"            # 32653 / 7602 = 4 (integer) <= 4
+    N = 4096                                                                       # C2: 5-point stencil, avg 4.999 -> 4
+    counts = np.full((N, N), 5, np.int32)
+    counts[0, :] -= 1; counts[-1, :] -= 1; counts[:, 0] -= 1; counts[:, -1] -= 1
+    rp = np.zeros(N * N + 1, np.int32)
+    np.cumsum(counts.ravel(), out=rp[1:])
+    assert int(rp[-1]) == 83869696 and oracle.port_adaptive_choice(rp) == "adaptive line"
+    rp = (np.arange(10_000_001, dtype=np.int64) * 32).astype(np.int32)            # C3: avg 32, nnz 3.2e8 > 2^23
+    assert oracle.port_adaptive_choice(rp) == "adaptive flat"
+    rp = np.array([0, 0, 0, 1000, 9000], np.int32)                                 # halves 0 : 9000 -> two data blocks
+    assert oracle.port_adaptive_choice(rp) == "vector-row, two data blocks"
+    rp = (np.arange(1001, dtype=np.int32) * 9)                                     # small, avg 9 -> line-enhance (adaptive)
+    assert oracle.port_adaptive_choice(rp) == "adaptive line-enhance"
