@@ -71,6 +71,7 @@ struct SpmvArgs {
   const int *__restrict__ nz_rows;                 // direct form only
   int read_y;   // 0: beta == 0 and SPMV_B200_FLAG_BETA0_SKIP_Y
   int gather_na; // 1: x gathers use L1::no_allocate
+  int stream_prefetch; // direct form: keep value / colindex a few windows ahead in L2 (prefetch.global.L2)
   PushArgs push;
 };
 

@@ -778,14 +778,29 @@ __global__ void __launch_bounds__(NT, 1536 / NT) k_spmv_seg(const SpmvArgs a) {
 // Analogue of the reference's flat / merge-path kernels (src/acc/hip-flat/flat_imp_one_pass.hpp:15-77,
 // benchmark/merge-path/merge_path_reduction.h:80-136) without atomicAdd and without the per-element row search.
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// one 128-element window of colindex (4 lines) and value (8 lines) requested into L2 by lanes 0-11: no destination
+// register, so a warp can keep its streams several windows ahead of the window it is summing
+constexpr int kDirectPrefetchWindows = 4;
+__device__ __forceinline__ void prefetch_window(const SpmvArgs &a, int w0, int e1, int lane) {
+  if (w0 < e1) {
+    if (lane < 4)
+      prefetch_l2(a.col + w0 + 32 * lane);
+    else if (lane < 12)
+      prefetch_l2(a.val + w0 + 16 * (lane - 4));
+  }
+}
 
 __device__ __forceinline__ void finish_row(const SpmvArgs &a, int row, double sum) {
   const double yv = a.read_y ? a.y[row] : 0.0; // cli/verification.cpp:64: y is read even when beta == 0
   emit_y(a.y, a.push, row, a.alpha * sum + a.beta * yv);
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(kThreads, 5) k_spmv_warp(const SpmvArgs a) {
+// Q = 128-element windows a warp has in flight at a time: 2 (8 gathers per lane, 48 registers, 5 CTAs/SM) or 1 (4 gathers
+// per lane, fewer registers, more resident warps).
+template <bool VEC, int Q>
+__global__ void __launch_bounds__(kThreads, Q == 1 ? 8 : 5) k_spmv_warp(const SpmvArgs a) {
   const int lane = threadIdx.x & 31;
   const int ti = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (ti >= a.ntiles)
@@ -811,14 +826,20 @@ __global__ void __launch_bounds__(kThreads, 5) k_spmv_warp(const SpmvArgs a) {
 
   double cv = 0.0; // open sum (since the last row start) in front of the current 128-element window
   int nstart = 0;  // row starts met so far
-  for (int rb = e0 & ~3; rb < e1; rb += 256) {
-    double p[2][4];
-    unsigned nib[2];
+  if (a.stream_prefetch) // tuning bit 24 (off by default, see launch_range)
+    for (int w = 0; w < kDirectPrefetchWindows; ++w)
+      prefetch_window(a, (e0 & ~3) + 128 * w, e1, lane);
+  for (int rb = e0 & ~3; rb < e1; rb += 128 * Q) {
+    if (a.stream_prefetch)
+      for (int q = 0; q < Q; ++q)
+        prefetch_window(a, rb + 128 * (kDirectPrefetchWindows + q), e1, lane);
+    double p[Q][4];
+    unsigned nib[Q];
     {
-      int c[2][4];
-      double v[2][4];
+      int c[Q][4];
+      double v[Q][4];
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < Q; ++q) {
         const int i0 = rb + 128 * q + 4 * lane;
         nib[q] = 0u;
 #pragma unroll
@@ -852,18 +873,18 @@ __global__ void __launch_bounds__(kThreads, 5) k_spmv_warp(const SpmvArgs a) {
         }
       }
 #pragma unroll
-      for (int q = 0; q < 2; ++q)
+      for (int q = 0; q < Q; ++q)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           p[q][k] = c[q][k] >= 0 ? gather_x(a.x, c[q][k], a.gather_na) : 0.0;
 #pragma unroll
-      for (int q = 0; q < 2; ++q)
+      for (int q = 0; q < Q; ++q)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           p[q][k] *= v[q][k];
     }
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < Q; ++q) {
       if (rb + 128 * q >= e1) // warp-uniform
         break;
       // ordinal of the first row start this lane meets = starts in earlier windows + starts in the lanes in front
@@ -1185,6 +1206,9 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
   else
     a.push.count = 0;
 
+  // measured on C4: 1.42 ms with the L2 stream prefetch against 1.34 ms without (more LSU requests, no latency won:
+  // 64 resident warps already cover it); off unless tuning bit 24 is set
+  a.stream_prefetch = ((p->flags >> 24) & 1u) ? 1 : 0;
   a.row_start_bits = p->row_start_bits;
   a.nz_rows = p->nz_rows;
   const bool tma = p->uses_tma;
@@ -1198,7 +1222,12 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
       a.cap = 0;
       const int wpc = kThreads / 32;
       // uses_tma == value / colindex are 16-byte aligned (and vector loads were not disabled with NO_TMA)
-      B200_CUDA(launch_spmv(tma ? k_spmv_warp<true> : k_spmv_warp<false>, (a.ntiles + wpc - 1) / wpc, 0, stream, a, p));
+      // one 128-element window in flight per warp (32 registers, 64 resident warps per SM): C4 1.33 ms against 1.42 ms
+      // with two windows (48 registers, 40 warps); tuning bit 23 selects the two-window kernel
+      const bool q1 = ((p->flags >> 23) & 1u) == 0;
+      RowsKernel kw = q1 ? (tma ? k_spmv_warp<true, 1> : k_spmv_warp<false, 1>)
+                         : (tma ? k_spmv_warp<true, 2> : k_spmv_warp<false, 2>);
+      B200_CUDA(launch_spmv(kw, (a.ntiles + wpc - 1) / wpc, 0, stream, a, p));
     }
   }
   for (int k = 0; k < 3 && !p->direct; ++k) {

@@ -25,6 +25,7 @@ OPTS = {
     "tiled_only": make_options(flags=FLAG_NO_DIRECT),
     "direct": make_options(flags=FLAG_DIRECT),
     "direct_scalar_loads": make_options(flags=FLAG_DIRECT | FLAG_NO_TMA),
+    "direct_two_windows": make_options(flags=FLAG_DIRECT | (1 << 23)),
     "direct_T512_L64": make_options(512, 8, 64, flags=FLAG_DIRECT),
     "mixed_segmented": make_options(flags=(1 << 22) | FLAG_NO_DIRECT),
     "mixed_segmented_small": make_options(256, 4, 16, 2, flags=(1 << 22) | FLAG_NO_DIRECT),
