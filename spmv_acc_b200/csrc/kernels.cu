@@ -814,7 +814,7 @@ __global__ void __launch_bounds__(kThreads, Q == 1 ? 8 : 5) k_spmv_warp(const Sp
   // Everything a finished row needs later (its y, its id, the row pointers of the empty-row pass) is requested now,
   // without a destination register, so that those dependent accesses hit L1 instead of adding round trips to the
   // chain descriptor -> value/colindex/flags -> x gathers. One 128-byte line per lane and array (blocks own <= T rows).
-  {
+  if (a.stream_prefetch != 2) { // (tuning bit 25 switches this block off)
     const int nrows = r1 - r0;
     for (int i = lane * 16; i < nrows; i += 32 * 16)
       prefetch_l1(a.y + r0 + i);
@@ -826,11 +826,11 @@ __global__ void __launch_bounds__(kThreads, Q == 1 ? 8 : 5) k_spmv_warp(const Sp
 
   double cv = 0.0; // open sum (since the last row start) in front of the current 128-element window
   int nstart = 0;  // row starts met so far
-  if (a.stream_prefetch) // tuning bit 24 (off by default, see launch_range)
+  if (a.stream_prefetch == 1) // tuning bit 24 (off by default, see launch_range)
     for (int w = 0; w < kDirectPrefetchWindows; ++w)
       prefetch_window(a, (e0 & ~3) + 128 * w, e1, lane);
   for (int rb = e0 & ~3; rb < e1; rb += 128 * Q) {
-    if (a.stream_prefetch)
+    if (a.stream_prefetch == 1)
       for (int q = 0; q < Q; ++q)
         prefetch_window(a, rb + 128 * (kDirectPrefetchWindows + q), e1, lane);
     double p[Q][4];
@@ -1208,7 +1208,7 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
 
   // measured on C4: 1.42 ms with the L2 stream prefetch against 1.34 ms without (more LSU requests, no latency won:
   // 64 resident warps already cover it); off unless tuning bit 24 is set
-  a.stream_prefetch = ((p->flags >> 24) & 1u) ? 1 : 0;
+  a.stream_prefetch = ((p->flags >> 24) & 1u) ? 1 : (((p->flags >> 25) & 1u) ? 2 : 0);
   a.row_start_bits = p->row_start_bits;
   a.nz_rows = p->nz_rows;
   const bool tma = p->uses_tma;
