@@ -157,6 +157,8 @@ int spmv_b200_plan_create(spmv_b200_plan **out, int32_t m, int32_t n, int64_t nn
   int rc = analysis_prepare(p, static_cast<cudaStream_t>(stream));
   if (rc == SPMV_B200_OK && !(opt && opt->vec_div) && irregular_gathers(p))
     p->vec_div = 8;
+  if (rc == SPMV_B200_OK)
+    p->irregular = irregular_gathers(p);
   // direct form: forced by flag; automatic choice below (auto_direct)
   if (rc == SPMV_B200_OK)
     p->direct = !(p->flags & SPMV_B200_FLAG_NO_DIRECT) && p->nnz > 0 &&

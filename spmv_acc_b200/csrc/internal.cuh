@@ -71,6 +71,7 @@ struct SpmvArgs {
   const int *__restrict__ nz_rows;                 // direct form only
   int read_y;   // 0: beta == 0 and SPMV_B200_FLAG_BETA0_SKIP_Y
   int gather_na; // 1: x gathers use L1::no_allocate
+  int rotate_slots; // MEDIUM kernel: lane groups walk the slots of a round in rotated order (bank conflicts)
   int stream_prefetch; // direct form: keep value / colindex a few windows ahead in L2 (prefetch.global.L2)
   PushArgs push;
 };
@@ -124,6 +125,7 @@ struct spmv_b200_plan {
   int count[3] = {0, 0, 0};
   // direct (warp-per-tile, no shared memory) form for matrices with irregular gathers (SPMV_B200_FLAG_DIRECT / auto)
   bool direct = false;
+  bool irregular = false;                  // gather-coalescing statistic > 0.5 lines per gather (set at plan creation)
   unsigned int *row_start_bits = nullptr;  // bit k (absolute element index) set iff element k is the first of its row
   int *nz_rows = nullptr;                  // ascending ids of the non-empty rows
   int n_nz_rows = 0;

@@ -194,7 +194,7 @@ __device__ __forceinline__ void emit_y(double *__restrict__ y, const PushArgs &p
 // of a round are in flight before the first FMA, and y is fetched before the tile has landed, so that a CTA exposes
 // one round trip to memory per phase (tile, gathers) instead of one per batch of four elements.
 // Rows of one tile whose value / colindex are (being) staged in sval / scol; waits for the TMA phase `parity` of `bar`.
-template <bool TMA, bool VEC, int W, int R>
+template <bool TMA, bool VEC, int W, int R, bool ROT = false>
 __device__ __forceinline__ void rows_tile(const SpmvArgs &a, const double *__restrict__ sval,
                                           const int *__restrict__ scol, int *__restrict__ srow,
                                           unsigned long long *bar, uint32_t parity, int r0, int nrows, int a0, int e0,
@@ -246,21 +246,36 @@ __device__ __forceinline__ void rows_tile(const SpmvArgs &a, const double *__res
         else
           yv[q] = (a.read_y && act && l == 0) ? a.y[r0 + cb + r] : 0.0;
       }
+      // Irregular-gather plans: lane groups of a warp walk the W slots of a round in rotated order. With rows whose
+      // length is a multiple of 16 (32 nnz per row in C3) every group would otherwise read the same shared-memory banks
+      // in the same step (ncu: 8-way conflicts, 130 M extra wavefronts on C3). The rotation depends only on the
+      // group's position in the tile.
+      int rot = ROT ? (g % W) * V : 0; // offset of the first slot this group reads in a round
       for (;;) {
         double xv[R][W];
 #pragma unroll
         for (int q = 0; q < R; ++q) {
 #pragma unroll
           for (int j = 0; j < W; ++j) {
-            const int kk = k[q] + j * V;
+            int kk = k[q] + j * V;
+            if (ROT) {
+              kk += rot;
+              kk -= (kk >= k[q] + W * V) ? W * V : 0; // wrap around inside the round
+            }
             xv[q][j] = (kk < e[q]) ? gather_x(a.x, scol[kk], a.gather_na) : 0.0;
           }
         }
+        if (ROT)
+          asm volatile("" : "+r"(rot)); // recompute the indices below instead of keeping W of them in registers
 #pragma unroll
         for (int q = 0; q < R; ++q) {
 #pragma unroll
           for (int j = 0; j < W; ++j) {
-            const int kk = k[q] + j * V;
+            int kk = k[q] + j * V;
+            if (ROT) {
+              kk += rot;
+              kk -= (kk >= k[q] + W * V) ? W * V : 0;
+            }
             if (kk < e[q])
               sum[q] = fma(sval[kk], xv[q][j], sum[q]);
           }
@@ -290,7 +305,7 @@ __device__ __forceinline__ void rows_tile(const SpmvArgs &a, const double *__res
   }
 }
 
-template <bool TMA, bool VEC, int W, int R>
+template <bool TMA, bool VEC, int W, int R, bool ROT = false>
 __global__ void __launch_bounds__(kThreads) k_spmv_rows(const SpmvArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
@@ -304,7 +319,7 @@ __global__ void __launch_bounds__(kThreads) k_spmv_rows(const SpmvArgs a) {
   const int a0 = e0 & ~3;
 
   tile_issue_loads<TMA>(a, a0, e0, e1, sval, scol, &bar, tid);
-  rows_tile<TMA, VEC, W, R>(a, sval, scol, srow, &bar, 0u, r0, r1 - r0, a0, e0, e1, tid);
+  rows_tile<TMA, VEC, W, R, ROT>(a, sval, scol, srow, &bar, 0u, r0, r1 - r0, a0, e0, e1, tid);
 }
 
 // Persistent form: gridDim.x CTAs walk the tile list with a two-stage ring of shared-memory tiles. The TMA copies
@@ -1035,6 +1050,13 @@ static const RowsVariant kMediumVariants[] = {
     {k_spmv_rows<true, true, 4, 2>, k_spmv_rows<false, true, 4, 2>, k_spmv_rows_persistent<true, 4, 2>, "W4R2"},
     {k_spmv_rows<true, true, 8, 2>, k_spmv_rows<false, true, 8, 2>, k_spmv_rows_persistent<true, 8, 2>, "W8R2"},
 };
+// MEDIUM kernels with the slot rotation (plans with irregular gathers); same order as kMediumVariants
+static const RowsVariant kMediumVariantsRot[] = {
+    {k_spmv_rows<true, true, 8, 1, true>, k_spmv_rows<false, true, 8, 1, true>, k_spmv_rows_persistent<true, 8, 1>, "W8R1r"},
+    {k_spmv_rows<true, true, 4, 1, true>, k_spmv_rows<false, true, 4, 1, true>, k_spmv_rows_persistent<true, 4, 1>, "W4R1r"},
+    {k_spmv_rows<true, true, 4, 2, true>, k_spmv_rows<false, true, 4, 2, true>, k_spmv_rows_persistent<true, 4, 2>, "W4R2r"},
+    {k_spmv_rows<true, true, 8, 2, true>, k_spmv_rows<false, true, 8, 2, true>, k_spmv_rows_persistent<true, 8, 2>, "W8R2r"},
+};
 constexpr int kNumShortVariants = sizeof(kShortVariants) / sizeof(kShortVariants[0]);
 constexpr int kNumMediumVariants = sizeof(kMediumVariants) / sizeof(kMediumVariants[0]);
 
@@ -1123,6 +1145,8 @@ int kernels_configure(spmv_b200_plan *p) {
       (rc = set_smem(vm.persistent, smem_for(p, SPMV_B200_KIND_MEDIUM, true))) ||
       (rc = set_smem(vm.tma, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
       (rc = set_smem(vm.plain, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
+      (rc = set_smem(kMediumVariantsRot[p->variant_medium].tma, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
+      (rc = set_smem(kMediumVariantsRot[p->variant_medium].plain, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
       (rc = set_smem(mixed_kernel(true, p->mixed_threads, p->mixed_queue_form), smem_for(p, SPMV_B200_KIND_MIXED))) ||
       (rc = set_smem(mixed_kernel(false, p->mixed_threads, p->mixed_queue_form), smem_for(p, SPMV_B200_KIND_MIXED))))
     return rc;
@@ -1208,6 +1232,10 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
 
   // measured on C4: 1.42 ms with the L2 stream prefetch against 1.34 ms without (more LSU requests, no latency won:
   // 64 resident warps already cover it); off unless tuning bit 24 is set
+  // slot rotation of the MEDIUM kernel: only where gathers do not coalesce across rows anyway (C3: 1.836 ms against
+  // 1.882 ms); on a stencil it breaks the coalescing of neighbouring rows (C5s: 1.08 ms against 0.97 ms). Tuning bit 26
+  // switches it off.
+  a.rotate_slots = (p->irregular && !((p->flags >> 26) & 1u)) ? 1 : 0;
   a.stream_prefetch = ((p->flags >> 24) & 1u) ? 1 : (((p->flags >> 25) & 1u) ? 2 : 0);
   a.row_start_bits = p->row_start_bits;
   a.nz_rows = p->nz_rows;
@@ -1247,7 +1275,8 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
       continue;
     }
     const RowsVariant &v = k == SPMV_B200_KIND_SHORT ? kShortVariants[p->variant_short]
-                                                     : kMediumVariants[p->variant_medium];
+                                                     : (a.rotate_slots ? kMediumVariantsRot[p->variant_medium]
+                                                                       : kMediumVariants[p->variant_medium]);
     if (tma && persistent) {
       const int grid = a.ntiles < p->persistent_grid[k] ? a.ntiles : p->persistent_grid[k];
       B200_CUDA(launch_spmv(v.persistent, grid, smem_for(p, k, true), stream, a, p));
