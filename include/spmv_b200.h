@@ -134,8 +134,9 @@ int spmv_b200_plan_tile_col_range(spmv_b200_plan *plan, int32_t *h_min, int32_t 
 int spmv_b200_stream_write_flag(void *stream, uint32_t *d_flag, uint32_t value);
 int spmv_b200_stream_write_flags(void *stream, uint32_t *const *d_flags, int32_t count, uint32_t value); /* <= 8 flags, one launch */
 int spmv_b200_stream_wait_flag(void *stream, uint32_t *d_flag, uint32_t value);
-/* waits for up to 8 flags with one launch (a bounded spin in a one-thread kernel; SPMV_B200_FLAG_WAIT=memop in the
- * environment selects cuStreamWaitValue32 per flag instead) */
+/* waits for up to 8 flags with one launch (a spin in a one-thread kernel that gives up after about 10 s so that a
+ * protocol error cannot hang the device; SPMV_B200_FLAG_WAIT=memop in the environment selects cuStreamWaitValue32 per
+ * flag instead, which never gives up) */
 int spmv_b200_stream_wait_flags(void *stream, uint32_t *const *d_flags, int32_t count, uint32_t value);
 int spmv_b200_enable_peer_access(int32_t peer_device);
 

@@ -69,11 +69,22 @@ def _worker(rank, world, port, mode, N, iters, out_dir):
         y = oracle.port_host_spmv(1.0, 0.0, sub_rp, shard.col[sl], shard.val[sl], xf.numpy(), np.zeros(b - a))
         ys[a:b].copy_(torch.from_numpy(y))
 
+    # which row blocks read x entries owned by the other rank (the product gets this from spmv_b200_plan_tile_col_range)
+    reads_halo = np.zeros(tile_row.size - 1, dtype=bool)
+    for t in range(tile_row.size - 1):
+        cols = shard.col[shard.rowptr[tile_row[t]]:shard.rowptr[tile_row[t + 1]]]
+        reads_halo[t] = cols.size > 0 and (cols.min() < lo or cols.max() >= hi)
     x = torch.from_numpy(synth.vector_numpy(n, 2).copy())
     loop = sharded.PowerLoop(n=n, bounds=bounds, spmv=spmv, x=x, x_next=torch.zeros_like(x), need_local=need,
-                             exchange=mode, block_shift=shift, spmv_tiles=spmv_tiles, tile_row=tile_row)
+                             exchange=mode, block_shift=shift, spmv_tiles=spmv_tiles, tile_row=tile_row,
+                             tile_reads_halo=reads_halo)
     if mode == "halo":
-        assert loop.overlapped and loop.boundary and loop.interior
+        assert loop.overlapped and loop.boundary and loop.interior and loop.boundary_reads_all_halo
+        covered = np.zeros(reads_halo.size, dtype=bool)
+        for t0, t1 in loop.boundary:
+            covered[t0:t1] = True
+        assert covered[reads_halo].all()      # every reader of halo entries is a boundary row block
+        assert not covered.all()
     xf = loop.run(iters)
     np.save(Path(out_dir) / f"x_{mode}_{rank}.npy", xf[lo:hi].numpy())
     np.save(Path(out_dir) / f"meta_{mode}_{rank}.npy", np.array([lo, hi, loop.bytes_in_per_iter]))
