@@ -52,3 +52,29 @@ def test_sass_contains_tma_bulk_copies():
         pytest.skip("cuobjdump not available")
     out = subprocess.run([cuobjdump, "-sass", str(_lib.LIB_DIR / "libspmv_b200.so")], capture_output=True, text=True)
     assert "UBLKCP" in out.stdout and "sm_100a" in out.stdout
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/spmv_b200.h must compile as C99 (no C++-isms) and a C program must link against
+    the library and call an entry point that needs no GPU."""
+    import shutil
+    import subprocess
+    import pytest
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    if not Path(gcc).exists():
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "spmv_b200.h"\n'
+                   'int main(void) {\n'
+                   '  spmv_b200_options o = {0, 0, 0, 0, SPMV_B200_FLAG_BETA0_SKIP_Y};\n'
+                   '  spmv_b200_halo_loop_desc d; spmv_b200_push p; (void)o; (void)d; (void)p;\n'
+                   '  printf("%d %d\\n", spmv_b200_abi_version(), spmv_b200_cache_size());\n'
+                   '  return spmv_b200_plan_destroy(0);\n}\n')
+    exe = tmp_path / "abi"
+    lib_dir = _lib.LIB_DIR
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT / 'include'}", str(src),
+                        "-o", str(exe), f"-L{lib_dir}", "-lspmv_b200", f"-Wl,-rpath,{lib_dir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["1", "0"], (out.stdout, out.stderr)
