@@ -335,9 +335,12 @@ def run_b200(args, rank, world, local_rank):
     del csr, x, y
     torch.cuda.empty_cache()
 
-    # ---- the other single-GPU configurations of BASELINE.json (C3 uniform-random, C4 R-MAT): same timing, rank 0 ----
-    if rank == 0 and world == 1 and not args.no_other_configs:
-        line["other_configs"] = run_other_configs(torch, args, peak)
+    # ---- the other one-shot configurations of BASELINE.json (C3 uniform-random, C4 R-MAT): same timing; with N > 1
+    # ranks every rank multiplies its nnz-balanced row shard against the replicated x (strong scaling, no exchange) ----
+    if not args.no_other_configs:
+        other = run_other_configs(torch, dist, rank, world, args, peak)
+        if rank == 0:
+            line["other_configs"] = other
 
     # ---- iterated configuration C5 (power loop with exchange of x) ----
     if not args.no_iterated:
@@ -418,10 +421,13 @@ def run_cusparse(torch, csr, x, y, args):
     return out
 
 
-def run_other_configs(torch, args, peak):
+def run_other_configs(torch, dist, rank, world, args, peak):
     """C3 and C4 of BASELINE.json, device resident, default plan options: ms / GFLOP/s / fraction of the HBM roofline,
-    next to cuSPARSE on the same buffers. Not the headline; reported so that one run covers every single-GPU config."""
-    from spmv_acc_b200 import CsrDesc, SpmvPlan, synth
+    next to cuSPARSE and CUB on the same buffers (N = 1). With N > 1 ranks every rank generates the same matrix, takes
+    the nnz-balanced row shard `spmv_b200_shard_bounds` gives it as a window of the row pointers (no copy) and
+    multiplies it against the replicated x: strong scaling of the one-shot SpMV, no exchange. Not the headline;
+    reported so that one run covers every one-shot config."""
+    from spmv_acc_b200 import CsrDesc, SpmvPlan, shard_bounds, synth
     out = {}
     makers = {
         "C3 uniform-random 1e7 x 1e7, 32 nnz/row": lambda: synth.uniform_device(10_000_000, 10_000_000, 32, seed=1),
@@ -430,13 +436,18 @@ def run_other_configs(torch, args, peak):
     for name, make in makers.items():
         try:
             csr = make()
-            plan = SpmvPlan(CsrDesc(csr.rows, csr.cols, csr.nnz, csr.rowptr, csr.col, csr.val))
+            lo, hi = 0, csr.rows
+            if world > 1:
+                b = shard_bounds(csr.rowptr, csr.rows, world)
+                lo, hi = int(b[rank]), int(b[rank + 1])
+            nnz_local = int(csr.rowptr[hi].item()) - int(csr.rowptr[lo].item())
+            plan = SpmvPlan(CsrDesc(hi - lo, csr.cols, nnz_local, csr.rowptr[lo:hi + 1], csr.col, csr.val))
             info = plan.info()
             x = synth.vector_device(csr.cols, 2)
-            y = synth.vector_device(csr.rows, 3)
+            y = synth.vector_device(hi - lo, 3 + rank)
             for _ in range(5):
                 plan.execute(1.0, 1.0, x, y)
-            torch.cuda.synchronize()
+            sync_all(torch, dist, world)
             reps = 30
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -444,21 +455,31 @@ def run_other_configs(torch, args, peak):
                 plan.execute(1.0, 1.0, x, y)
             e1.record()
             e1.synchronize()
-            ms = e0.elapsed_time(e1) / reps
-            b = alg_bytes(csr.rows, csr.cols, csr.nnz)
-            gbs = b / (ms * 1e-3) / 1e9
-            out[name] = {"ms": ms, "gflops": 2.0 * csr.nnz / (ms * 1e-3) / 1e9, "effective_gbs": gbs,
-                         "frac_of_measured_peak": gbs / peak, "frac_of_nominal_8TBs": gbs / NOMINAL_HBM_GBS,
-                         "form": "direct (warp per row block, no shared memory)" if info.direct else "tiled (TMA)",
-                         "tile_nnz": info.tile_nnz, "tiles_per_kind": list(info.tiles_per_kind),
-                         "split_rows": info.nsplit_rows, "launches_per_spmv": info.launches_per_execute,
-                         "bound": "x gathers (L1 lines in flight), see DESIGN.md §3.5"}
-            if not args.no_context:
-                out[name]["context"] = run_cusparse(torch, csr, x, y, args)
+            sync_all(torch, dist, world)
+            ms_local = e0.elapsed_time(e1) / reps
+            ms = max_over_ranks(torch, dist, world, ms_local)
+            b_local = alg_bytes(hi - lo, csr.cols, nnz_local)  # per rank: its rows, its non-zeros, the whole x
+            gbs = b_local / (ms_local * 1e-3) / 1e9
+            rec = {"ms": ms, "gflops": 2.0 * csr.nnz / (ms * 1e-3) / 1e9, "n_gpus": world,
+                   "scaling": "strong" if world > 1 else "single GPU",
+                   "effective_gbs_rank0": gbs, "frac_of_measured_peak_rank0": gbs / peak,
+                   "frac_of_nominal_8TBs_rank0": gbs / NOMINAL_HBM_GBS,
+                   "form": "direct (warp per row block, no shared memory)" if info.direct else "tiled (TMA)",
+                   "tile_nnz": info.tile_nnz, "tiles_per_kind_rank0": list(info.tiles_per_kind),
+                   "split_rows_rank0": info.nsplit_rows, "launches_per_spmv": info.launches_per_execute,
+                   "rows_rank0": hi - lo, "nnz_rank0": nnz_local,
+                   "bound": "x gathers (L1 lines in flight), see DESIGN.md §3.5"}
+            if world == 1:
+                rec.update({"effective_gbs": gbs, "frac_of_measured_peak": gbs / peak,
+                            "frac_of_nominal_8TBs": gbs / NOMINAL_HBM_GBS})
+                if not args.no_context:
+                    rec["context"] = run_cusparse(torch, csr, x, y, args)
+            out[name] = rec
             plan.destroy()
             del csr, x, y
             torch.cuda.empty_cache()
         except Exception as e:
+            # (a failure is the same on every rank — same code, same matrix — so the ranks stay in step)
             out[name] = {"error": f"{type(e).__name__}: {e}"}
     return out
 
