@@ -449,7 +449,9 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
     B200_CUDA(cudaMemcpyAsync(&h_nz, nzprefix + m, sizeof(int), cudaMemcpyDeviceToHost, stream));
     B200_CUDA(cudaStreamSynchronize(stream));
     p->n_nz_rows = h_nz;
-    B200_CUDA(cudaMalloc(&p->nz_rows, sizeof(int) * ((size_t)h_nz + 1)));
+    // padded by one tile's worth of rows: the direct kernel requests (prefetch, no fault semantics relied upon) the
+    // row ids of a block by its row count, which can exceed its number of non-empty rows
+    B200_CUDA(cudaMalloc(&p->nz_rows, sizeof(int) * ((size_t)h_nz + 1 + (size_t)p->T + 64)));
     k_nz_rows<<<grid_for(m, 256, 148 * 16), 256, 0, stream>>>(nzflag, nzprefix, m, p->nz_rows);
     B200_CUDA(cudaMalloc(&p->desc_direct, sizeof(TileDesc) * (size_t)ntiles));
     k_desc_direct<<<grid_for(ntiles, 256, 1 << 30), 256, 0, stream>>>(ntiles, p->desc_all, nzprefix, p->desc_direct);
