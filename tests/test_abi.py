@@ -78,3 +78,28 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     assert r.returncode == 0, r.stderr
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.split() == ["1", "0"], (out.stdout, out.stderr)
+
+
+def test_direct_kernel_uses_no_shared_memory_and_128_bit_stream_loads():
+    """The direct form exists to leave the whole unified L1/shared array to L1: its kernels must not use shared memory,
+    and value / colindex must be streamed with 128-bit evict-first loads (SASS LDG.E.EF.128)."""
+    import shutil
+    import subprocess
+    import pytest
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        pytest.skip("cuobjdump not available")
+    so = str(_lib.LIB_DIR / "libspmv_b200.so")
+    import re
+    res = subprocess.run([cuobjdump, "-res-usage", so], capture_output=True, text=True).stdout.splitlines()
+    seen = 0
+    for i, line in enumerate(res):
+        if "k_spmv_warp" in line:
+            seen += 1
+            shared = int(re.search(r"SHARED:(\d+)", res[i + 1]).group(1))
+            assert shared <= 1024, res[i + 1]  # 1024 bytes per CTA are reserved by the system on sm_100 for every kernel
+    assert seen == 4  # <VEC, Q> = {true, false} x {1, 2}
+    elf = subprocess.run([cuobjdump, "-elf", so], capture_output=True, text=True).stdout
+    fn = re.search(r"_ZN4b200\d+k_spmv_warpILb1ELi1E\w*", elf).group(0)
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", fn, so], capture_output=True, text=True).stdout
+    assert sass.count("LDG.E.EF.128") >= 3 and "BAR.SYNC" not in sass
