@@ -50,7 +50,7 @@ def read_csr_text(path) -> Tuple[Csr, np.ndarray]:
     def nums(line, dtype):
         toks = [t for t in line.split(" ") if t != ""]
         # the reference parses every token with atof (csr_mtx_reader.hpp:153-158), then narrows
-        return np.array([float(t) for t in toks], dtype=np.float64).astype(dtype)
+        return np.array(toks, dtype=np.float64).astype(dtype)  # one vectorised parse per line
 
     val = nums(lines[1], np.float64)
     col = nums(lines[2], np.int32)
@@ -128,18 +128,50 @@ def _read_mtx_coo(path):
         while line and line.startswith("%"):
             line = f.readline()
         rows, cols, nz = (int(t) for t in line.split()[:3])
-        rr, cc, vv = [], [], []
-        for line in f:
-            if not line.strip() or line.startswith("%"):
-                continue
-            p = line.split()
-            r, c = int(p[0]), int(p[1])
-            if r > rows or c > cols:
-                raise ValueError("index out of bounds in matrix market file")
-            v = 1.0 if pattern else float(p[2])  # complex keeps only the first value token
-            rr.append(r - 1); cc.append(c - 1); vv.append(v)
-            if mirrored and r != c:
-                rr.append(c - 1); cc.append(r - 1); vv.append(v)
+        body = f.read()
+    # fast path: every entry line has the same number of tokens (2 pattern, 3 real / integer, 4 complex) and there are
+    # no comment lines after the size line -> one vectorised parse instead of a Python loop per entry
+    ntok = 2 if pattern else (4 if field == "complex" else 3)
+    flat = None
+    if "%" not in body:
+        try:
+            flat = np.array(body.split(), dtype=np.float64)
+        except ValueError:
+            flat = None
+        if flat is not None and (flat.size % ntok != 0):
+            flat = None
+    if flat is not None:
+        ent = flat.reshape(-1, ntok)
+        r1, c1 = ent[:, 0].astype(np.int64), ent[:, 1].astype(np.int64)
+        v1 = np.ones(r1.size) if pattern else ent[:, 2].copy()  # complex keeps only the first value token
+        if r1.size and (r1.max() > rows or c1.max() > cols):
+            raise ValueError("index out of bounds in matrix market file")
+        if mirrored:
+            # the mirrored copy of an off-diagonal entry follows the entry itself, like the reference reader emits it
+            off = r1 != c1
+            reps = np.where(off, 2, 1)
+            pos = np.cumsum(reps) - reps           # position of each original entry in the output
+            total = int(reps.sum())
+            rr = np.empty(total, np.int64)
+            cc = np.empty(total, np.int64)
+            vv = np.empty(total, np.float64)
+            rr[pos], cc[pos], vv[pos] = r1 - 1, c1 - 1, v1
+            rr[pos[off] + 1], cc[pos[off] + 1], vv[pos[off] + 1] = c1[off] - 1, r1[off] - 1, v1[off]
+        else:
+            rr, cc, vv = r1 - 1, c1 - 1, v1
+        return rows, cols, rr, cc, vv
+    rr, cc, vv = [], [], []
+    for line in body.split("\n"):
+        if not line.strip() or line.startswith("%"):
+            continue
+        p = line.split()
+        r, c = int(p[0]), int(p[1])
+        if r > rows or c > cols:
+            raise ValueError("index out of bounds in matrix market file")
+        v = 1.0 if pattern else float(p[2])  # complex keeps only the first value token
+        rr.append(r - 1); cc.append(c - 1); vv.append(v)
+        if mirrored and r != c:
+            rr.append(c - 1); cc.append(r - 1); vv.append(v)
     return rows, cols, np.array(rr, dtype=np.int64), np.array(cc, dtype=np.int64), np.array(vv, dtype=np.float64)
 
 

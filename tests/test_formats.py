@@ -96,3 +96,29 @@ def test_csr_tool_output_follows_the_reference_tool():
     # parts == 0: one part per row
     assert csr_tool.part_nnz_lines(rp, 0)[1:4] == ["0 2 2", "1 0 0", "2 3 3"]
     assert csr_tool.main(["dist", str(GOLDEN / "rajat03_standin.csr")]) == 0
+
+
+def test_mtx_pattern_complex_and_comment_lines_against_reference_reader(tmp_path):
+    """Field variants and the two parse paths (vectorised; line by line when a comment sits between the entries) give
+    what the reference's MatrixMarket reader gives (cli/matrix_market_reader.hpp:50-303)."""
+    cases = {
+        "pattern_sym.mtx": "%%MatrixMarket matrix coordinate pattern symmetric\n% c\n4 4 4\n1 1\n3 1\n4 2\n4 4\n",
+        "complex_gen.mtx": "%%MatrixMarket matrix coordinate complex general\n3 4 3\n1 4 1.5 -2\n3 1 0.25 7\n2 2 -1 0\n",
+        "integer_herm.mtx": "%%MatrixMarket matrix coordinate integer Hermitian\n3 3 3\n2 1 5\n3 3 -4\n3 2 9\n",
+        "real_comment_inside.mtx": "%%MatrixMarket matrix coordinate real general\n2 3 3\n1 1 1.0\n% a comment\n2 3 2.5\n1 2 -1\n",
+    }
+    for name, text in cases.items():
+        path = tmp_path / name
+        path.write_text(text)
+        ours = formats.read_mtx(path)
+        if oracle.have_ref():
+            rp, col, val, _, cols = oracle.ref_read(str(path), "mtx")
+            assert (ours.rows, ours.cols) == (rp.size - 1, cols), name
+            assert np.array_equal(ours.rowptr, rp) and np.array_equal(ours.col, col), name
+            assert np.array_equal(ours.val, val), name
+    pat = formats.read_mtx(tmp_path / "pattern_sym.mtx")
+    assert pat.nnz == 6 and np.all(pat.val == 1.0)                       # 2 diagonal + 2 mirrored pairs
+    assert formats.read_mtx(tmp_path / "complex_gen.mtx").val.tolist() == [1.5, -1.0, 0.25]   # real parts, (row, col) order
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.mtx").write_text("%%MatrixMarket matrix coordinate real general\n2 2 1\n3 1 1.0\n")
+        formats.read_mtx(tmp_path / "bad.mtx")
