@@ -3,12 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-Headline workload (config C2 of BASELINE.json): 2D 5-point Laplacian on a 4096 x 4096 grid (16.8M rows, 83.9M nnz),
-fp64, alpha = beta = 1 like the reference harness (benchmark/main.cpp:101-102). One step = one SpMV over the whole
-matrix through the C ABI (spmv_b200_execute). With N > 1 ranks (torchrun, one rank per GPU) the grid grows to
-(4096*N) x 4096, rows are cut into N nnz-balanced contiguous shards, x is replicated (one-shot SpMV needs no
-exchange): weak scaling. The iterated configuration (C5, 27-point 384^3 power loop with the NCCL / halo exchange of x)
-is measured by the same run and reported under "iterated".
+Headline workload at every N (config C5 of BASELINE.json, the one its metric "1/2/4/8 B200" is defined on): the 3D
+27-point stencil on a 384^3 grid (56.6M rows, 1.52G nnz), fp64, int32 indices, iterated x <- A*x (alpha = 1, beta = 0).
+One step = one iteration = one SpMV over the whole matrix plus the exchange of x. With N > 1 ranks (torchrun, one rank
+per GPU) the rows are cut into N nnz-balanced contiguous shards (strong scaling); the halo rows of x are pushed into the
+neighbours' memory by the SpMV kernels themselves (spmv_b200_halo_loop_*), NCCL exchanges are timed beside it.
+The one-shot configs C2 / C3 / C4 are measured by the same run and reported under "other_configs", each with its own
+roofline object and an out-of-timed-region check of sampled rows against the reference's CPU SpMV ("verified").
 
 Prints ONE JSON line on rank 0. Keys are described in DESIGN.md §Measurement.
 """
@@ -27,9 +28,18 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+C5_GRID = 384
 C2_GRID = 4096
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
 NOMINAL_HBM_GBS = 8000.0   # BASELINE.json north_star
+METRIC = "fp64 CSR SpMV GFLOP/s (2*nnz/t)"
+
+
+def workload_name(N):
+    n = N ** 3
+    nnz = (3 * N - 2) ** 3
+    return (f"C5: 3D 27-point stencil {N}^3 ({n} rows, {nnz} nnz), fp64, int32 indices, power loop x <- A*x, "
+            f"alpha=1, beta=0")
 
 
 def alg_bytes(m, n, nnz):
@@ -51,10 +61,30 @@ def measured_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this round (profiles/): ncu
+    counters cannot be read inside an unprofiled run, so the number is labelled with its source."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        rec = json.loads(p.read_text())[key]
+        return rec["dram_bytes_per_launch"], f"profiles/{rec['source']} (ncu --set full, same kernel and matrix)"
+    except Exception:
+        return None, "no ncu capture for this configuration"
+
+
+def roofline(b_alg, ms, peak, peak_src, kernel, traffic_key=None, rows=0, nnz=0):
+    achieved = b_alg / (ms * 1e-3) / 1e9
+    traffic, src = profiled_traffic(traffic_key) if traffic_key else (None, "not captured at this N")
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": src, "kernel": kernel, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": b_alg, "frac_of_nominal_8TBs": achieved / NOMINAL_HBM_GBS,
+            "harness_model_gbs": harness_bytes(rows, nnz) / (ms * 1e-3) / 1e9 if rows else None}
+
+
 class ClockSampler:
     """Samples SM clock / throttle reasons of one GPU with NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.02):
+    def __init__(self, index: int, period_s: float = 0.004):
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
@@ -99,6 +129,7 @@ class ClockSampler:
 
     def start(self):
         if self.nv is not None:
+            self._stop.clear()
             self._thread = threading.Thread(target=self._run, daemon=True)
             self._thread.start()
 
@@ -106,6 +137,7 @@ class ClockSampler:
         self._stop.set()
         if self._thread is not None:
             self._thread.join()
+            self._thread = None
 
     def summary(self):
         if not self.samples:
@@ -114,22 +146,47 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pins this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host buffers of the
+    end-to-end path are allocated next to the GPU's PCIe root (every rank on its own node instead of all on node 0)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
+        if node < 0:
+            return {"numa_node": None, "note": "the platform reports no NUMA affinity for this GPU"}
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus_bound": len(allowed)}
+    except Exception as e:
+        return {"numa_node": None, "note": f"{type(e).__name__}: {e}"}
+
+
 # ----------------------------------------------------------------------------------------------------------------
-# reference arm: the reference's own CPU SpMV (cli/verification.cpp:56-66) on the box's host cores
+# the reference's own CPU SpMV (cli/verification.cpp:56-66) on the box's host cores
 # ----------------------------------------------------------------------------------------------------------------
-def host_c2_rows(rows):
-    """First `rows` rows of the C2 matrix on the host (numpy restatement of the device generator)."""
+def host_c5_rows(N, rows):
+    """First `rows` rows of the C5 matrix on the host (numpy restatement of the device generator)."""
     from spmv_acc_b200 import synth
-    return synth.stencil2d_numpy(C2_GRID, 0, rows)
+    return synth.stencil3d_numpy(N, 0, rows)
 
 
-def time_reference_spmv(csr, x, y, reps):
-    import oracle
+def time_reference_spmv(csr, x, y, reps, alpha=1.0, beta=0.0):
     import ctypes as C
+    import oracle
     lib = oracle.oracle._ref_lib() if oracle.have_ref() else oracle.oracle._port_lib()
     fn = lib.ref_host_spmv_axpby if oracle.have_ref() else lib.port_host_spmv_axpby
     P = oracle.oracle._p
-    args = (C.c_double(1.0), C.c_double(1.0), P(csr.val, C.c_double), P(csr.rowptr, C.c_int), P(csr.col, C.c_int),
+    args = (C.c_double(alpha), C.c_double(beta), P(csr.val, C.c_double), P(csr.rowptr, C.c_int), P(csr.col, C.c_int),
             C.c_int(csr.rows), C.c_int(csr.cols), C.c_int(csr.nnz), P(x, C.c_double), P(y, C.c_double))
     times = []
     for _ in range(reps):
@@ -139,36 +196,42 @@ def time_reference_spmv(csr, x, y, reps):
     return times, ("reference" if oracle.have_ref() else "port")
 
 
+def cpu_sample(N, rows):
+    from spmv_acc_b200 import synth
+    csr = host_c5_rows(N, rows)
+    x = synth.vector_numpy(min(N ** 3, rows + N * N + N + 2), 2)  # the columns these rows reference
+    csr.cols = x.size
+    return csr, x, np.zeros(csr.rows)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
-    from spmv_acc_b200 import synth
+    N = args.grid
     total_steps = args.steps + args.warmup
-    budget_s = 90.0
-    # calibrate on 1M rows, then size the per-step sample so the whole run fits the budget
-    probe = host_c2_rows(1 << 20)
-    x = synth.vector_numpy(C2_GRID * C2_GRID, 2)
-    y = synth.vector_numpy(probe.rows, 3)
+    budget_s = 60.0
+    probe, x, y = cpu_sample(N, min(N ** 3, 1 << 19))  # calibrate, then size the per-step sample to the budget
     t, kind = time_reference_spmv(probe, x, y, 2)
     rows_per_s = probe.rows / min(t)
-    rows = int(min(C2_GRID * C2_GRID, max(1 << 16, rows_per_s * budget_s / total_steps)))
-    csr = probe if rows == probe.rows else host_c2_rows(rows)
-    y = synth.vector_numpy(csr.rows, 3)
-    time_reference_spmv(csr, x, y, args.warmup)
-    times, kind = time_reference_spmv(csr, x, y, args.steps)
+    rows = int(min(N ** 3, max(1 << 14, rows_per_s * budget_s / total_steps)))
+    if rows != probe.rows:
+        probe, x, y = cpu_sample(N, rows)
+    time_reference_spmv(probe, x, y, args.warmup)
+    times, kind = time_reference_spmv(probe, x, y, args.steps)
     sec = float(np.mean(times))
-    gflops = 2.0 * csr.nnz / sec / 1e9
-    sample = f"first {csr.rows} of {C2_GRID * C2_GRID} rows of the C2 matrix per step ({csr.nnz} nnz), serial host_spmv"
+    gflops = 2.0 * probe.nnz / sec / 1e9
+    sample = (f"first {probe.rows} of {N ** 3} rows of the C5 matrix per step ({probe.nnz} nnz), serial host_spmv "
+              f"(cli/verification.cpp:56-66), alpha=1, beta=0")
     line = {
-        "impl": "reference", "metric": "fp64 CSR SpMV GFLOP/s (2*nnz/t)", "value": gflops, "unit": "GFLOP/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: 2D 5-point Laplacian 4096x4096 grid, fp64, alpha=beta=1", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": gflops, "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(N), "sample": sample},
         "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": 1, "kind": kind, "sample": sample,
                          "host_cores_available": os.cpu_count(),
-                         "note": "host_spmv (cli/verification.cpp:56-66) is serial: 1 thread is all it can use"},
+                         "note": "host_spmv is serial: one thread is all the reference's CPU path can use"},
         "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "effective_gbs": alg_bytes(csr.rows, csr.cols, csr.nnz) / sec / 1e9,
+        "effective_gbs": alg_bytes(probe.rows, probe.cols, probe.nnz) / sec / 1e9,
     }
     print(json.dumps(line), flush=True)
 
@@ -191,166 +254,163 @@ def max_over_ranks(torch, dist, world, value):
     return float(t.item())
 
 
-def sum_over_ranks(torch, dist, world, value):
-    if world == 1:
-        return value
-    t = torch.tensor([value], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+def min_over_ranks(torch, dist, world, value):
+    return -max_over_ranks(torch, dist, world, -value)
 
 
-def build_headline_shard(torch, rank, world):
-    """Rows [lo, hi) of the (4096*world) x 4096 grid Laplacian owned by this rank (nnz-balanced)."""
-    from spmv_acc_b200 import shard_bounds, synth
-    NY = C2_GRID * world
-    if world == 1:
-        lo, hi = 0, NY * C2_GRID
-        bounds = np.array([lo, hi], dtype=np.int64)
-    else:
-        counts = synth.stencil_row_counts_device("stencil2d", C2_GRID, NY)
-        rowptr = synth._rowptr_from_counts_device(counts)
-        del counts
-        bounds = shard_bounds(rowptr, NY * C2_GRID, world).astype(np.int64)
-        del rowptr
-        torch.cuda.empty_cache()
-        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    csr = synth.stencil2d_device(C2_GRID, lo, hi, NY=NY)
-    return csr, lo, hi, bounds
+def dominant_kernel(info):
+    if info.direct:
+        return "k_spmv_warp (direct form, one warp per row block, no shared memory)"
+    return {0: "k_spmv_rows<TMA, SHORT>", 1: "k_spmv_rows<TMA, MEDIUM>", 2: "k_spmv_mixed<TMA>"}[
+        int(np.argmax(list(info.tiles_per_kind)))]
 
 
-def time_steps(torch, dist, world, fn, steps, warmup, sampler=None):
-    for _ in range(warmup):
-        fn()
+def verify_sampled(torch, csr, plan, alpha, beta, seed_x=2, seed_y=3, count=20000, must_include=(), x=None):
+    """Out of the timed region: one SpMV on fresh vectors, sampled rows against the reference's CPU SpMV."""
+    from oracle import sampled
+    from spmv_acc_b200 import synth
+    try:
+        x = synth.vector_device(csr.cols, seed_x) if x is None else x
+        y0 = synth.vector_device(csr.rows, seed_y)
+        y = y0.clone()
+        plan.execute(alpha, beta, x, y)
+        torch.cuda.synchronize()
+        rows = sampled.sample_rows(csr.rows, count, must_include=must_include)
+        res = sampled.check_sampled_rows(csr.rowptr, csr.col, csr.val, x, y0, y, alpha, beta, rows)
+        y2 = y0.clone()
+        plan.execute(alpha, beta, x, y2)
+        torch.cuda.synchronize()
+        res["bitwise_reproducible"] = bool(torch.equal(y.view(torch.int64), y2.view(torch.int64)))
+        res["ok"] = bool(res["ok"] and res["bitwise_reproducible"])
+        res["alpha_beta"] = [alpha, beta]
+        return res
+    except Exception as e:
+        return {"ok": False, "error": f"{type(e).__name__}: {e}"}
+
+
+def time_plan(torch, dist, world, plan, alpha, beta, x, y, reps, warm=5):
+    for _ in range(warm):
+        plan.execute(alpha, beta, x, y)
     sync_all(torch, dist, world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if sampler:
-        sampler.start()
     e0.record()
-    for _ in range(steps):
-        fn()
+    for _ in range(reps):
+        plan.execute(alpha, beta, x, y)
     e1.record()
     e1.synchronize()
-    if sampler:
-        sampler.stop()
     sync_all(torch, dist, world)
-    return max_over_ranks(torch, dist, world, e0.elapsed_time(e1))  # ms for `steps` steps
+    return e0.elapsed_time(e1) / reps
 
 
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from spmv_acc_b200 import CsrDesc, HostMatrix, SpmvPlan, make_options, synth, _lib
+    from spmv_acc_b200 import sharded
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    numa = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    csr, lo, hi, bounds = build_headline_shard(torch, rank, world)
-    n_global = C2_GRID * C2_GRID * world
-    opt = make_options(args.tile, args.short_max, args.medium_max, args.vec_div, args.flags)
-    t0 = time.perf_counter()
-    plan = SpmvPlan(CsrDesc(csr.rows, csr.cols, csr.nnz, csr.rowptr, csr.col, csr.val), opt)
-    torch.cuda.synchronize()
-    plan_first_ms = (time.perf_counter() - t0) * 1e3  # includes loading the CUDA module (first use of the library)
-    plan.destroy()
-    t0 = time.perf_counter()
-    plan = SpmvPlan(CsrDesc(csr.rows, csr.cols, csr.nnz, csr.rowptr, csr.col, csr.val), opt)
-    torch.cuda.synchronize()
-    plan_ms = (time.perf_counter() - t0) * 1e3
-    info = plan.info()
-    x = synth.vector_device(n_global, 2)
-    y = synth.vector_device(csr.rows, 3 + rank)
-    alpha = beta = 1.0
-
-    def step():
-        plan.execute(alpha, beta, x, y)
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    total_ms = time_steps(torch, dist, world, step, args.steps, args.warmup, sampler)
-    ms_per_step = total_ms / args.steps
-    nnz_total = sum_over_ranks(torch, dist, world, float(csr.nnz))
-    rows_total = sum_over_ranks(torch, dist, world, float(csr.rows))
-    gflops = 2.0 * nnz_total / (ms_per_step * 1e-3) / 1e9
-    # roofline of the dominant kernel (rank 0's launch): algorithmic bytes of this rank's shard per launch. With
-    # several ranks x is replicated but a shard only reads the entries its columns reference (own rows + halo):
-    # count those (4096-entry blocks from the analysis) instead of the whole replicated vector.
-    if world == 1:
-        n_ref = csr.cols
-    else:
-        from spmv_acc_b200 import col_block_bitmap
-        n_ref = min(csr.cols, int(col_block_bitmap(csr.col, csr.nnz, csr.cols, 12).sum()) * 4096)
-    b_alg = alg_bytes(csr.rows, n_ref, csr.nnz)
     peak, peak_src = measured_peak()
-    achieved = b_alg / (ms_per_step * 1e-3) / 1e9
-    traffic = None
-    prof = ROOT / "profiles" / "ncu_c2_summary.json"
-    if prof.exists():
-        try:
-            traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    dominant = "k_spmv_warp (direct form)" if info.direct else {
-        0: "k_spmv_rows<TMA, SHORT>", 1: "k_spmv_rows<TMA, MEDIUM>", 2: "k_spmv_mixed<TMA>"}[
-        int(np.argmax(list(info.tiles_per_kind)))]
+    N = args.grid
 
+    # ---- headline: C5 power loop, strong scaling ----
+    t0 = time.perf_counter()
+    shard = sharded.build_shard("stencil3d", N=N)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    info = shard.plan.info()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    head = sharded.time_power_loop(shard, "fused", iters=args.steps, warmup=args.warmup, sampler=sampler)
+    ms_per_step = head["ms_per_iter"]
+    csr = shard.csr
+    lo, hi = int(shard.bounds[rank]), int(shard.bounds[rank + 1])
+    # roofline of the dominant kernel (rank 0's launch): algorithmic bytes of this rank's shard per launch. x is
+    # replicated, but a shard only reads the entries its columns reference (own rows + halo, 4096-entry blocks)
+    n_ref = shard.n if world == 1 else min(shard.n, int(shard.need.sum()) * (1 << sharded.BLOCK_SHIFT))
+    b_alg = alg_bytes(csr.rows, n_ref, csr.nnz)
+    kernel = dominant_kernel(info) + (" with the halo flag protocol inside (k_spmv_rows_halo)"
+                                      if head.get("single_launch_kernel") else "")
     line = {
-        "metric": "fp64 CSR SpMV GFLOP/s (2*nnz/t)", "value": gflops, "unit": "GFLOP/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "metric": METRIC, "value": head["value"], "unit": "GFLOP/s", "n_gpus": world, "steps": head["iters"],
+        "warmup": head["warmup_iters"], "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": f"C2: 2D 5-point Laplacian, {C2_GRID * world}x{C2_GRID} grid "
-                        f"({int(rows_total)} rows, {int(nnz_total)} nnz), fp64, int32 indices, alpha=beta=1",
-            "sharding": "nnz-balanced contiguous row shards, x replicated, no exchange (one-shot SpMV)",
-            "cache": "inputs larger than L2 (>= 1.0 GB streamed per step vs 126 MB L2); no flush between steps",
-            "tile_nnz": info.tile_nnz, "uses_tma": bool(info.uses_tma),
-            "tiles_per_kind": list(info.tiles_per_kind), "split_rows": info.nsplit_rows,
+            "workload": workload_name(N),
+            "sharding": f"{world} nnz-balanced contiguous row shard(s), x replicated where referenced",
+            "exchange": head["exchange"],
+            "cache": f"inputs larger than L2 ({alg_bytes(csr.rows, n_ref, csr.nnz) / 1e9:.2f} GB streamed per step "
+                     f"and GPU vs 126 MB L2); no flush between steps",
+            "tile_nnz": info.tile_nnz, "uses_tma": bool(info.uses_tma), "tiles_per_kind": list(info.tiles_per_kind),
+            "split_rows": info.nsplit_rows, "launches_per_step": head.get("launches_per_iteration"),
+            "iterations_per_graph_launch": head.get("iterations_per_graph_launch"),
         },
-        "effective_gbs": alg_bytes(int(rows_total), n_global, int(nnz_total)) / (ms_per_step * 1e-3) / 1e9 / 1.0,
-        "roofline": {
-            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "kernel": dominant, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": b_alg, "frac_of_nominal_8TBs": achieved / NOMINAL_HBM_GBS,
-            "harness_model_gbs": harness_bytes(csr.rows, csr.nnz) / (ms_per_step * 1e-3) / 1e9,
-        },
-        "gpu_launches": args.steps * info.launches_per_execute,
-        "plan_create_ms": plan_ms, "plan_create_first_call_ms": plan_first_ms,
+        "effective_gbs": head["effective_gbs"],
+        "roofline": roofline(b_alg, ms_per_step, peak, peak_src, kernel, "c5" if world == 1 and N == C5_GRID else None,
+                             csr.rows, csr.nnz),
+        "gpu_launches": head["iters"] * int(head.get("launches_per_iteration") or 1),
+        "x_checksum_first_16th": head["x_checksum_first_16th"],
+        "build_matrix_and_plan_s": build_s,
         "clocks": sampler.summary() if sampler else None,
+        "host_numa": numa,
     }
+    # correctness gate of the headline configuration, outside the timed region: sampled rows (across the z-plane
+    # boundaries of the shard) of one SpMV against the reference's CPU SpMV, and bitwise reproducibility
+    plane = N * N
+    edge = [r for z in (0, 1, (hi - lo) // plane // 2, (hi - lo) // plane - 1) for r in range(z * plane - 8, z * plane + 8)]
+    ver = verify_sampled(torch, csr, shard.plan, 1.0, 0.0, count=20000, must_include=edge)
+    ok_all = min_over_ranks(torch, dist, world, 1.0 if ver.get("ok") else 0.0) > 0.5
+    line["verified"] = bool(ok_all)
+    line["verification"] = ver
 
-    # ---- context baseline: cuSPARSE on the same device buffers (rank 0 only, not the product path) ----
-    if rank == 0 and not args.no_context:
-        line["context"] = run_cusparse(torch, csr, x, y, args)
+    # ---- the exchange BASELINE.json names (NCCL all-gather of x) and the launch forms, beside the headline ----
+    iterated = {"fused": head}
+    if not args.no_iterated and world > 1:
+        for mode in ("nccl_allgather", "nccl_halo", "fused_multi_launch"):
+            try:
+                iterated[mode] = sharded.time_power_loop(shard, mode, iters=min(args.steps, 100), warmup=4)
+            except Exception as e:
+                iterated[mode] = {"error": f"{type(e).__name__}: {e}"}
+    elif not args.no_iterated and not args.quick:
+        try:
+            iterated["fused_multi_launch"] = sharded.time_power_loop(shard, "fused_multi_launch",
+                                                                    iters=min(args.steps, 100), warmup=4)
+        except Exception as e:
+            iterated["fused_multi_launch"] = {"error": f"{type(e).__name__}: {e}"}
+    line["iterated"] = iterated
 
-    # ---- e2e: the reference-facing host-buffer call (H2D x, y0; SpMV; D2H y) every step ----
+    # ---- e2e: the reference-facing host-buffer call on the same workload (H2D x; SpMV; D2H y every step) ----
     if not args.no_e2e:
-        line["e2e"] = run_e2e(torch, dist, world, csr, x, n_global, nnz_total, args)
+        line["e2e"] = run_e2e(torch, dist, world, shard, args)
 
     # ---- CPU baseline: the reference's own host_spmv on the box's host cores (rank 0, N = 1) ----
     if rank == 0 and world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = run_cpu_baseline(torch, csr, x, args)
+        line["cpu_baseline"] = run_cpu_baseline(N)
 
-    plan.destroy()
-    del csr, x, y
+    shard.destroy()
+    del shard, csr
     torch.cuda.empty_cache()
 
-    # ---- the other one-shot configurations of BASELINE.json (C3 uniform-random, C4 R-MAT): same timing; with N > 1
-    # ranks every rank multiplies its nnz-balanced row shard against the replicated x (strong scaling, no exchange) ----
+    # ---- an iterated matrix whose halo is not sparse (C3-shaped): the all-gather is what `auto` picks there ----
+    if not args.no_iterated and world > 1 and not args.quick:
+        try:
+            ush = sharded.build_shard("uniform", m=10_000_000, k=32)
+            rec = sharded.time_power_loop(ush, "fused", iters=20, warmup=4)
+            rec["workload"] = f"{ush.name}, values / 32, x <- A*x"
+            line["iterated_uniform"] = rec
+            ush.destroy()
+            del ush
+            torch.cuda.empty_cache()
+        except Exception as e:
+            line["iterated_uniform"] = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- the one-shot configurations of BASELINE.json (C2, C3, C4) ----
     if not args.no_other_configs:
-        other = run_other_configs(torch, dist, rank, world, args, peak)
+        other = run_other_configs(torch, dist, rank, world, args, peak, peak_src)
         if rank == 0:
             line["other_configs"] = other
-
-    # ---- iterated configuration C5 (power loop with exchange of x) ----
-    if not args.no_iterated:
-        try:
-            from spmv_acc_b200.sharded import bench_power_loop
-            line["iterated"] = bench_power_loop(args.iter_grid, args.iters, exchange=args.exchange,
-                                                overlap=not args.no_overlap, graph=args.graph,
-                                                fused=not args.no_fused)
-        except Exception as e:  # the headline number must survive a failure of the secondary measurement
-            line["iterated"] = {"error": f"{type(e).__name__}: {e}"}
 
     if world > 1:
         dist.barrier()
@@ -376,10 +436,10 @@ def run_cusparse(torch, csr, x, y, args):
                 out[name] = {"error": rc}
                 continue
             stream = torch.cuda.current_stream().cuda_stream
-            for _ in range(10):
+            for _ in range(5):
                 X.spmv_b200_ctx_cusparse_spmv(h, 1.0, 1.0, stream)
             torch.cuda.synchronize()
-            reps = max(20, min(args.steps, 200))
+            reps = 20
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(reps):
@@ -404,7 +464,7 @@ def run_cusparse(torch, csr, x, y, args):
             for _ in range(5):
                 call()
             torch.cuda.synchronize()
-            reps = max(20, min(args.steps, 200))
+            reps = 20
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(reps):
@@ -421,19 +481,21 @@ def run_cusparse(torch, csr, x, y, args):
     return out
 
 
-def run_other_configs(torch, dist, rank, world, args, peak):
-    """C3 and C4 of BASELINE.json, device resident, default plan options: ms / GFLOP/s / fraction of the HBM roofline,
-    next to cuSPARSE and CUB on the same buffers (N = 1). With N > 1 ranks every rank generates the same matrix, takes
-    the nnz-balanced row shard `spmv_b200_shard_bounds` gives it as a window of the row pointers (no copy) and
-    multiplies it against the replicated x: strong scaling of the one-shot SpMV, no exchange. Not the headline;
-    reported so that one run covers every one-shot config."""
+def run_other_configs(torch, dist, rank, world, args, peak, peak_src):
+    """C2, C3 and C4 of BASELINE.json, device resident, default plan options, one-shot SpMV with alpha = beta = 1 like
+    the reference harness (benchmark/main.cpp:101-102): ms / GFLOP/s / a full roofline object / sampled rows against
+    the reference's CPU SpMV, next to cuSPARSE and CUB on the same buffers (N = 1), plus the timings of
+    (alpha, beta) = (0.75, -0.5) and (1, 0). With N > 1 ranks every rank generates the same matrix, takes the
+    nnz-balanced row shard `spmv_b200_shard_bounds` gives it as a window of the row pointers (no copy) and multiplies
+    it against the replicated x: strong scaling of the one-shot SpMV, no exchange."""
     from spmv_acc_b200 import CsrDesc, SpmvPlan, shard_bounds, synth
     out = {}
     makers = {
-        "C3 uniform-random 1e7 x 1e7, 32 nnz/row": lambda: synth.uniform_device(10_000_000, 10_000_000, 32, seed=1),
-        "C4 R-MAT 2^24 rows, 2^28 nnz": lambda: synth.rmat_device(24, 16, seed=1),
+        "C2 2D 5-point Laplacian 4096x4096 grid": ("c2", lambda: synth.stencil2d_device(C2_GRID)),
+        "C3 uniform-random 1e7 x 1e7, 32 nnz/row": ("c3", lambda: synth.uniform_device(10_000_000, 10_000_000, 32, seed=1)),
+        "C4 R-MAT 2^24 rows, 2^28 nnz": ("c4", lambda: synth.rmat_device(24, 16, seed=1)),
     }
-    for name, make in makers.items():
+    for name, (key, make) in makers.items():
         try:
             csr = make()
             lo, hi = 0, csr.rows
@@ -441,42 +503,43 @@ def run_other_configs(torch, dist, rank, world, args, peak):
                 b = shard_bounds(csr.rowptr, csr.rows, world)
                 lo, hi = int(b[rank]), int(b[rank + 1])
             nnz_local = int(csr.rowptr[hi].item()) - int(csr.rowptr[lo].item())
-            plan = SpmvPlan(CsrDesc(hi - lo, csr.cols, nnz_local, csr.rowptr[lo:hi + 1], csr.col, csr.val))
+            window = synth.Csr(hi - lo, csr.cols, csr.rowptr[lo:hi + 1], csr.col, csr.val)
+            plan = SpmvPlan(CsrDesc(hi - lo, csr.cols, nnz_local, window.rowptr, csr.col, csr.val))
             info = plan.info()
             x = synth.vector_device(csr.cols, 2)
             y = synth.vector_device(hi - lo, 3 + rank)
-            for _ in range(5):
-                plan.execute(1.0, 1.0, x, y)
-            sync_all(torch, dist, world)
-            reps = 30
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(reps):
-                plan.execute(1.0, 1.0, x, y)
-            e1.record()
-            e1.synchronize()
-            sync_all(torch, dist, world)
-            ms_local = e0.elapsed_time(e1) / reps
+            ms_local = time_plan(torch, dist, world, plan, 1.0, 1.0, x, y, 30)
             ms = max_over_ranks(torch, dist, world, ms_local)
             b_local = alg_bytes(hi - lo, csr.cols, nnz_local)  # per rank: its rows, its non-zeros, the whole x
-            gbs = b_local / (ms_local * 1e-3) / 1e9
             rec = {"ms": ms, "gflops": 2.0 * csr.nnz / (ms * 1e-3) / 1e9, "n_gpus": world,
-                   "scaling": "strong" if world > 1 else "single GPU",
-                   "effective_gbs_rank0": gbs, "frac_of_measured_peak_rank0": gbs / peak,
-                   "frac_of_nominal_8TBs_rank0": gbs / NOMINAL_HBM_GBS,
+                   "scaling": "strong" if world > 1 else "single GPU", "alpha_beta": [1.0, 1.0],
+                   "roofline": roofline(b_local, ms_local, peak, peak_src, dominant_kernel(info),
+                                        key if world == 1 else None, hi - lo, nnz_local),
                    "form": "direct (warp per row block, no shared memory)" if info.direct else "tiled (TMA)",
                    "tile_nnz": info.tile_nnz, "tiles_per_kind_rank0": list(info.tiles_per_kind),
                    "split_rows_rank0": info.nsplit_rows, "launches_per_spmv": info.launches_per_execute,
-                   "rows_rank0": hi - lo, "nnz_rank0": nnz_local,
-                   "bound": "x gathers (L1 lines in flight), see DESIGN.md §3.5"}
-            if world == 1:
-                rec.update({"effective_gbs": gbs, "frac_of_measured_peak": gbs / peak,
-                            "frac_of_nominal_8TBs": gbs / NOMINAL_HBM_GBS})
-                if not args.no_context:
-                    rec["context"] = run_cusparse(torch, csr, x, y, args)
+                   "rows_rank0": hi - lo, "nnz_rank0": nnz_local}
+            # the other (alpha, beta) pairs of SURVEY.md §8d
+            y2 = y.clone()
+            rec["ms_alpha_0.75_beta_-0.5"] = max_over_ranks(torch, dist, world,
+                                                            time_plan(torch, dist, world, plan, 0.75, -0.5, x, y2, 10, 2))
+            y2.copy_(y)
+            rec["ms_alpha_1_beta_0"] = max_over_ranks(torch, dist, world,
+                                                      time_plan(torch, dist, world, plan, 1.0, 0.0, x, y2, 10, 2))
+            del y2
+            # correctness gate outside the timed region: the longest rows (split across row blocks), the rows around
+            # them and a random sample against the reference's CPU SpMV
+            lens = (window.rowptr[1:] - window.rowptr[:-1])
+            longest = torch.topk(lens, min(128, lens.numel())).indices.cpu().numpy().tolist()
+            ver = verify_sampled(torch, window, plan, 0.75, -0.5, count=20000, must_include=longest, x=x)
+            rec["verified"] = bool(min_over_ranks(torch, dist, world, 1.0 if ver.get("ok") else 0.0) > 0.5)
+            rec["verification"] = ver
+            del lens
+            if world == 1 and not args.no_context:
+                rec["context"] = run_cusparse(torch, csr, x, y, args)
             out[name] = rec
             plan.destroy()
-            del csr, x, y
+            del csr, window, x, y
             torch.cuda.empty_cache()
         except Exception as e:
             # (a failure is the same on every rank — same code, same matrix — so the ranks stay in step)
@@ -484,48 +547,56 @@ def run_other_configs(torch, dist, rank, world, args, peak):
     return out
 
 
-def run_e2e(torch, dist, world, csr, x, n_global, nnz_total, args):
-    from spmv_acc_b200 import HostMatrix, synth
-    h = synth.to_host(csr)
-    t0 = time.perf_counter()
-    hm = HostMatrix(h.rows, h.cols, h.rowptr, h.col, h.val)
-    cold_s = time.perf_counter() - t0
-    hx = torch.empty(n_global, dtype=torch.float64, pin_memory=True)
-    hy = torch.empty(h.rows, dtype=torch.float64, pin_memory=True)
-    hx.copy_(x)
-    hy.zero_()
-    steps = max(3, min(args.steps, args.e2e_steps))
-    for _ in range(3):
-        hm.spmv(1.0, 1.0, hx, hy)
-    sync_all(torch, dist, world)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        hm.spmv(1.0, 1.0, hx, hy)  # synchronous: returns after the D2H copy of y completed
-    torch.cuda.synchronize()
-    sec = (time.perf_counter() - t0) / steps
-    sec = max_over_ranks(torch, dist, world, sec)
-    x_lo, x_hi = hm.x_range()  # only the referenced part of x is copied (a row shard reads its rows' columns + halo)
-    hm.destroy()
-    return {"value": 2.0 * nnz_total / sec / 1e9, "unit": "GFLOP/s", "ms_per_step": sec * 1e3,
-            "h2d_bytes_per_step": int(8 * ((x_hi - x_lo) + h.rows)), "d2h_bytes_per_step": int(8 * h.rows),
-            "steps": steps, "api": "spmv_b200_hostmat_spmv (matrix resident, x and y0 copied in, y copied out "
-                                   "from/to pinned host memory every step; cli/main.cpp:99-118 pattern)",
-            "cold_upload_and_analyse_ms": cold_s * 1e3}
-
-
-def run_cpu_baseline(torch, csr, x, args):
-    from spmv_acc_b200 import synth
+def run_e2e(torch, dist, world, shard, args):
+    """The same step through the reference-facing host-buffer call: x of the current iterate comes from pinned host
+    memory, y goes back to pinned host memory (spmv_b200_hostmat_spmv on the device-resident matrix, the CLI's
+    pattern cli/main.cpp:99-118). beta = 0 with SPMV_B200_FLAG_BETA0_SKIP_Y: y0 does not travel."""
+    from spmv_acc_b200 import HostMatrix, make_options, synth, FLAG_BETA0_SKIP_Y
     try:
-        rows = 1 << 22  # bounded sample: first 4.19M rows (20.9M nnz), ~0.1 s per pass, 12 passes
-        h = host_c2_rows(rows)
-        hx = x.cpu().numpy()
-        y = synth.vector_numpy(rows, 3)
-        time_reference_spmv(h, hx, y, 2)
-        times, kind = time_reference_spmv(h, hx, y, 10)
+        csr = shard.csr
+        t0 = time.perf_counter()
+        hm = HostMatrix(csr.rows, csr.cols, csr.rowptr, csr.col, csr.val, make_options(flags=FLAG_BETA0_SKIP_Y))
+        cold_s = time.perf_counter() - t0
+        hx = torch.empty(shard.n, dtype=torch.float64, pin_memory=True)
+        hy = torch.empty(csr.rows, dtype=torch.float64, pin_memory=True)
+        x_lo, x_hi = hm.x_range()  # only the referenced part of x is copied (a row shard reads its rows' columns + halo)
+        hx[x_lo:x_hi].copy_(synth.vector_device(shard.n, 2)[x_lo:x_hi])
+        hy.zero_()
+        steps = max(3, min(args.steps, args.e2e_steps))
+        for _ in range(3):
+            hm.spmv(1.0, 0.0, hx, hy)
+        sync_all(torch, dist, world)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            hm.spmv(1.0, 0.0, hx, hy)  # synchronous: returns after the D2H copy of y completed
+        torch.cuda.synchronize()
+        sec_local = (time.perf_counter() - t0) / steps
+        sec = max_over_ranks(torch, dist, world, sec_local)
+        h2d, d2h = int(8 * (x_hi - x_lo)), int(8 * csr.rows)
+        hm.destroy()
+        del hx, hy
+        return {"value": 2.0 * shard.nnz_total / sec / 1e9, "unit": "GFLOP/s", "ms_per_step": sec * 1e3,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
+                "pcie_gbs_rank0": {"h2d_plus_d2h_over_step": (h2d + d2h) / sec_local / 1e9},
+                "api": "spmv_b200_hostmat_spmv (matrix resident on the device, x copied in from and y copied out to "
+                       "pinned host memory every step, row chunks pipelined; cli/main.cpp:99-118 pattern)",
+                "create_and_analyse_ms": cold_s * 1e3}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+def run_cpu_baseline(N):
+    try:
+        rows = min(N ** 3, 1 << 21)  # bounded sample: first 2.1M rows (55M nnz), ~0.06 s per pass
+        h, x, y = cpu_sample(N, rows)
+        time_reference_spmv(h, x, y, 2)
+        times, kind = time_reference_spmv(h, x, y, 40)
         sec = float(np.median(times))
         return {"value": 2.0 * h.nnz / sec / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": kind,
-                "sample": f"first {rows} of {C2_GRID * C2_GRID} rows of the C2 matrix ({h.nnz} nnz), median of 10 passes",
-                "effective_gbs": alg_bytes(h.rows, h.cols, h.nnz) / sec / 1e9, "host_cores_available": os.cpu_count()}
+                "sample": f"first {rows} of {N ** 3} rows of the C5 matrix ({h.nnz} nnz), alpha=1, beta=0, median of 40 "
+                          f"passes ({sum(times):.1f} s of CPU work)",
+                "effective_gbs": alg_bytes(h.rows, h.cols, h.nnz) / sec / 1e9, "host_cores_available": os.cpu_count(),
+                "note": "host_spmv (cli/verification.cpp:56-66) is serial: one thread is all it can use"}
     except Exception as e:
         return {"error": f"{type(e).__name__}: {e}"}
 
@@ -533,28 +604,22 @@ def run_cpu_baseline(torch, csr, x, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100, help="timed iterations of the power loop")
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--tile", type=int, default=0)
-    ap.add_argument("--short-max", type=int, default=0)
-    ap.add_argument("--medium-max", type=int, default=0)
-    ap.add_argument("--vec-div", type=int, default=0)
-    ap.add_argument("--flags", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--grid", type=int, default=C5_GRID, help="edge of the 3D stencil grid (384 = config C5)")
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-context", action="store_true")
-    ap.add_argument("--no-iterated", action="store_true")
-    ap.add_argument("--no-other-configs", action="store_true", help="skip the C3 / C4 lines (N = 1 only)")
-    ap.add_argument("--iter-grid", type=int, default=384)
-    ap.add_argument("--iters", type=int, default=100)
-    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "halo"])
-    ap.add_argument("--no-fused", action="store_true", help="halo exchange with NCCL send/recv instead of the fused push")
-    ap.add_argument("--graph", action="store_true", help="replay the power loop from a CUDA graph")
-    ap.add_argument("--no-overlap", action="store_true", help="do not overlap the halo exchange with interior rows")
+    ap.add_argument("--no-context", action="store_true", help="skip cuSPARSE / CUB on the one-shot configs")
+    ap.add_argument("--no-iterated", action="store_true", help="skip the NCCL exchanges timed beside the headline")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip C2 / C3 / C4")
+    ap.add_argument("--quick", action="store_true", help="headline + e2e + cpu baseline only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.steps = max(args.steps, 2)
+    if args.quick:
+        args.no_other_configs = True
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -15,7 +15,7 @@
  *   csr_adaptive_plus analyze / kernel / destroy phases                    src/acc/hip-csr-adaptive-plus/csr_adaptive_plus_spmv.cpp:16-73
  *        -> spmv_b200_plan_create / spmv_b200_execute / spmv_b200_plan_destroy
  *   host_spmv caller pattern of the CLI (H2D y0, spmv, D2H y)              cli/main.cpp:99-118
- *        -> spmv_b200_hostmat_create / spmv_b200_hostmat_spmv / spmv_b200_hostmat_destroy
+ *        -> spmv_b200_hostmat_create[_device] / spmv_b200_hostmat_spmv / spmv_b200_hostmat_destroy
  *
  * All device pointers are owned by the caller and must stay valid for the life of a plan.
  * Indices are 0-based int32, values fp64, rows may be empty, columns need not be sorted.
@@ -29,13 +29,14 @@
 extern "C" {
 #endif
 
-#define SPMV_B200_ABI_VERSION 1
+#define SPMV_B200_ABI_VERSION 2
 
 /* status codes */
 #define SPMV_B200_OK 0
 #define SPMV_B200_ERR_ARG 1
 #define SPMV_B200_ERR_CUDA 2
 #define SPMV_B200_ERR_UNSUPPORTED 3
+#define SPMV_B200_ERR_TIMEOUT 4 /* fused halo loop: a neighbour GPU did not signal in time */
 
 /* option flags */
 #define SPMV_B200_FLAG_NO_TMA 1u       /* stream tiles with plain loads instead of cp.async.bulk            */
@@ -129,23 +130,24 @@ int spmv_b200_execute_tiles_push(spmv_b200_plan *plan, double alpha, double beta
 /* smallest / largest column index referenced by each tile (h_min / h_max: int32 [ntiles]; INT32_MAX / -1 if empty):
  * a sharded caller uses it to find the row blocks that read entries of x owned by other GPUs */
 int spmv_b200_plan_tile_col_range(spmv_b200_plan *plan, int32_t *h_min, int32_t *h_max, void *stream);
-/* stream-ordered 32-bit flags in (peer) device memory: write `value`, or block the stream until *flag >= value.
- * Used to order the iterations of neighbouring GPUs without a collective. */
-int spmv_b200_stream_write_flag(void *stream, uint32_t *d_flag, uint32_t value);
-int spmv_b200_stream_write_flags(void *stream, uint32_t *const *d_flags, int32_t count, uint32_t value); /* <= 8 flags, one launch */
-int spmv_b200_stream_wait_flag(void *stream, uint32_t *d_flag, uint32_t value);
-/* waits for up to 8 flags with one launch (a spin in a one-thread kernel that gives up after about 10 s so that a
- * protocol error cannot hang the device; SPMV_B200_FLAG_WAIT=memop in the environment selects cuStreamWaitValue32 per
- * flag instead, which never gives up) */
-int spmv_b200_stream_wait_flags(void *stream, uint32_t *const *d_flags, int32_t count, uint32_t value);
 int spmv_b200_enable_peer_access(int32_t peer_device);
 
-/* The iterated loop x <- A*x of one rank with the fused halo exchange, enqueued natively (no host work per iteration
- * beyond the launches): iteration k waits until every neighbour's flag is >= k, multiplies buf[k%2] into rows
- * [row_lo,row_hi) of buf[(k+1)%2] -- boundary row blocks first, pushing the rows other GPUs reference straight into
- * their buffers (push[(k+1)%2]) --, raises its flag in the neighbours' memory to k+1 and multiplies the interior blocks.
- * n_boundary == 0: the whole shard is one launch (push included) followed by the flags. */
+/* The iterated loop x <- A*x of one rank (one row shard) with the halo exchange fused into the SpMV kernels. Iteration k
+ * multiplies buf[k%2] into rows [row_lo,row_hi) of buf[(k+1)%2]; rows other GPUs reference are stored straight into
+ * their buffers as well (push[(k+1)%2], NVLink stores). Iterations of neighbouring GPUs are ordered by 32-bit flags in
+ * each other's memory, no collective and no host synchronisation: the boundary row blocks of iteration k wait until
+ * every neighbour's flag is >= k, and the last of them to finish raises this rank's flag in the neighbours' memory to
+ * k+1; the interior row blocks need neither. With a plan of one row-kernel kind the whole iteration is ONE launch
+ * (flag wait and flag store inside the SpMV kernel, boundary row blocks scheduled first), and runs of iterations are
+ * replayed from a CUDA graph built at creation (20 iterations per graph launch, SPMV_B200_HALO_GRAPH_CHUNK in the
+ * environment; the epoch the flags are compared with lives in device memory, so one graph serves every run); other plans fall back to wait kernel / boundary launches / flag kernel / interior
+ * launches. n_boundary == 0: the whole shard is one launch that waits first and signals last.
+ * A wait that lasts longer than SPMV_B200_FLAG_TIMEOUT_MS (environment, default 10000, 0 = for ever) marks the loop as
+ * failed, stops signalling (so the failure reaches the neighbours instead of stale rows) and makes
+ * spmv_b200_halo_loop_sync return SPMV_B200_ERR_TIMEOUT. */
 #define SPMV_B200_MAX_RANGES 16
+#define SPMV_B200_HALO_NO_GRAPH 1u     /* enqueue every iteration separately */
+#define SPMV_B200_HALO_MULTI_LAUNCH 2u /* never use the single-launch kernel */
 typedef struct spmv_b200_halo_loop_desc {
   spmv_b200_plan *plan;
   double *buf[2];
@@ -157,9 +159,21 @@ typedef struct spmv_b200_halo_loop_desc {
   int32_t n_boundary, n_interior;
   int32_t boundary[2 * SPMV_B200_MAX_RANGES]; /* (tile_lo, tile_hi) pairs                             */
   int32_t interior[2 * SPMV_B200_MAX_RANGES];
+  uint32_t flags;                             /* SPMV_B200_HALO_*                                     */
 } spmv_b200_halo_loop_desc;
-int spmv_b200_halo_loop_run(const spmv_b200_halo_loop_desc *desc, int32_t first_iteration, int32_t iterations,
-                            void *stream);
+typedef struct spmv_b200_halo_loop_info {
+  int64_t iterations_enqueued;
+  int32_t single_launch;          /* 1: one kernel launch per iteration                       */
+  int32_t uses_graph;             /* iterations replayed per CUDA graph launch (0: no graph) */
+  int32_t launches_per_iteration;
+  int32_t boundary_row_blocks;
+} spmv_b200_halo_loop_info;
+typedef struct spmv_b200_halo_loop spmv_b200_halo_loop;
+int spmv_b200_halo_loop_create(spmv_b200_halo_loop **out, const spmv_b200_halo_loop_desc *desc);
+int spmv_b200_halo_loop_run(spmv_b200_halo_loop *loop, int32_t iterations, void *stream); /* asynchronous */
+int spmv_b200_halo_loop_sync(spmv_b200_halo_loop *loop, void *stream); /* waits; reports flag time-outs */
+int spmv_b200_halo_loop_get_info(const spmv_b200_halo_loop *loop, spmv_b200_halo_loop_info *info);
+int spmv_b200_halo_loop_destroy(spmv_b200_halo_loop *loop);
 /* exchange buffers other GPUs (other processes) store into: allocated with cudaMalloc on the current device and
  * exported as a 64-byte CUDA IPC handle; the consumer opens the handle with ITS device current, which is what maps
  * the memory for its kernels (cudaIpcMemLazyEnablePeerAccess). peer_free / peer_close release them. */
@@ -179,12 +193,24 @@ int spmv_b200_csr_spmv(int32_t trans, double alpha, double beta, int32_t m, int3
                        double *d_y);
 int spmv_b200_sparse_spmv(int32_t trans, double alpha, double beta, int32_t m, int32_t n, const int32_t *d_rowptr,
                           const int32_t *d_colidx, const double *d_val, const double *d_x, double *d_y);
-int spmv_b200_cache_invalidate(void); /* drop every cached plan (call after rewriting a matrix in place) */
+/* The analysis behind these two calls is cached per (pointers, shape, device). Every hit re-reads a fingerprint of the
+ * row pointers on the device (rowptr[0], rowptr[m], 2048 evenly spaced entries) and analyses again when it differs, so
+ * an allocator that hands the same addresses to another matrix cannot resurrect a stale plan. A matrix whose row
+ * pointers are rewritten in place without changing any sampled entry must still be announced with
+ * spmv_b200_cache_invalidate(). SPMV_B200_CACHE_TRUST=1 in the environment skips the check. */
+int spmv_b200_cache_invalidate(void); /* drop every cached plan */
 int spmv_b200_cache_size(void);
+int64_t spmv_b200_cache_revalidations(void); /* hits whose fingerprint did not match (the matrix was analysed again) */
 
 /* ---- host-buffer path: matrix uploaded and analysed once, vectors copied every call ---- */
 int spmv_b200_hostmat_create(spmv_b200_hostmat **out, int32_t m, int32_t n, int64_t nnz, const int32_t *h_rowptr,
                              const int32_t *h_colidx, const double *h_val, const spmv_b200_options *opt);
+/* the same for a matrix that already lives in device memory (the CLI's create_device_data, cli/utils.hpp:94-116, done by
+ * the caller): the arrays are not copied and must outlive the handle; nnz < 0 = read it from rowptr on the device */
+int spmv_b200_hostmat_create_device(spmv_b200_hostmat **out, int32_t m, int32_t n, int64_t nnz,
+                                    const int32_t *d_rowptr, const int32_t *d_colidx, const double *d_val,
+                                    const spmv_b200_options *opt);
+/* y0 = h_y is copied in unless beta == 0 and the plan was created with SPMV_B200_FLAG_BETA0_SKIP_Y */
 int spmv_b200_hostmat_spmv(spmv_b200_hostmat *hm, double alpha, double beta, const double *h_x, double *h_y);
 /* columns [col_lo, col_hi) the matrix references: the only part of h_x that hostmat_spmv reads and copies */
 int spmv_b200_hostmat_x_range(const spmv_b200_hostmat *hm, int32_t *col_lo, int32_t *col_hi);

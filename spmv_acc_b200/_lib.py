@@ -14,12 +14,12 @@ LIB_DIR = PKG / "lib"
 # every symbol include/spmv_b200.h declares (tests/test_abi.py checks the header against this list)
 ABI_SYMBOLS = [
     "spmv_b200_abi_version", "spmv_b200_last_error", "spmv_b200_plan_create", "spmv_b200_execute",
-    "spmv_b200_execute_tiles", "spmv_b200_execute_push", "spmv_b200_stream_write_flag", "spmv_b200_stream_wait_flag",
-    "spmv_b200_execute_tiles_push", "spmv_b200_plan_tile_col_range", "spmv_b200_stream_write_flags", "spmv_b200_stream_wait_flags",
-    "spmv_b200_halo_loop_run", "spmv_b200_enable_peer_access", "spmv_b200_peer_alloc", "spmv_b200_peer_open", "spmv_b200_peer_close",
-    "spmv_b200_peer_free",
+    "spmv_b200_execute_tiles", "spmv_b200_execute_push", "spmv_b200_execute_tiles_push", "spmv_b200_plan_tile_col_range",
+    "spmv_b200_halo_loop_create", "spmv_b200_halo_loop_run", "spmv_b200_halo_loop_sync", "spmv_b200_halo_loop_get_info",
+    "spmv_b200_halo_loop_destroy", "spmv_b200_enable_peer_access", "spmv_b200_peer_alloc", "spmv_b200_peer_open",
+    "spmv_b200_peer_close", "spmv_b200_peer_free", "spmv_b200_cache_revalidations",
     "spmv_b200_plan_destroy", "spmv_b200_plan_get_info", "spmv_b200_plan_export", "spmv_b200_csr_spmv",
-    "spmv_b200_sparse_spmv", "spmv_b200_cache_invalidate", "spmv_b200_cache_size", "spmv_b200_hostmat_create",
+    "spmv_b200_sparse_spmv", "spmv_b200_cache_invalidate", "spmv_b200_cache_size", "spmv_b200_hostmat_create", "spmv_b200_hostmat_create_device",
     "spmv_b200_hostmat_spmv", "spmv_b200_hostmat_x_range", "spmv_b200_hostmat_destroy", "spmv_b200_host_spmv", "spmv_b200_coo_to_csr", "spmv_b200_shard_bounds",
     "spmv_b200_col_block_bitmap",
 ]
@@ -46,7 +46,18 @@ class HaloLoopDesc(C.Structure):
     _fields_ = [("plan", C.c_void_p), ("buf", C.c_void_p * 2), ("row_lo", C.c_int32), ("row_hi", C.c_int32),
                 ("n_neigh", C.c_int32), ("wait_flags", C.c_void_p * MAX_PUSH), ("signal_flags", C.c_void_p * MAX_PUSH),
                 ("push", Push * 2), ("n_boundary", C.c_int32), ("n_interior", C.c_int32),
-                ("boundary", C.c_int32 * (2 * MAX_RANGES)), ("interior", C.c_int32 * (2 * MAX_RANGES))]
+                ("boundary", C.c_int32 * (2 * MAX_RANGES)), ("interior", C.c_int32 * (2 * MAX_RANGES)),
+                ("flags", C.c_uint32)]
+
+
+class HaloLoopInfo(C.Structure):
+    _fields_ = [("iterations_enqueued", C.c_int64), ("single_launch", C.c_int32), ("uses_graph", C.c_int32),
+                ("launches_per_iteration", C.c_int32), ("boundary_row_blocks", C.c_int32)]
+
+
+HALO_NO_GRAPH = 1
+HALO_MULTI_LAUNCH = 2
+ERR_TIMEOUT = 4
 
 
 class PlanInfo(C.Structure):
@@ -97,11 +108,11 @@ def lib() -> C.CDLL:
         L.spmv_b200_execute_push.argtypes = [vp, dbl, dbl, vp, vp, C.POINTER(Push), vp]
         L.spmv_b200_execute_tiles_push.argtypes = [vp, dbl, dbl, vp, vp, i32, i32, C.POINTER(Push), vp]
         L.spmv_b200_plan_tile_col_range.argtypes = [vp, vp, vp, vp]
-        L.spmv_b200_stream_write_flags.argtypes = [vp, C.POINTER(C.c_void_p), i32, C.c_uint32]
-        L.spmv_b200_stream_wait_flags.argtypes = [vp, C.POINTER(C.c_void_p), i32, C.c_uint32]
-        L.spmv_b200_halo_loop_run.argtypes = [C.POINTER(HaloLoopDesc), i32, i32, vp]
-        L.spmv_b200_stream_write_flag.argtypes = [vp, vp, C.c_uint32]
-        L.spmv_b200_stream_wait_flag.argtypes = [vp, vp, C.c_uint32]
+        L.spmv_b200_halo_loop_create.argtypes = [C.POINTER(vp), C.POINTER(HaloLoopDesc)]
+        L.spmv_b200_halo_loop_run.argtypes = [vp, i32, vp]
+        L.spmv_b200_halo_loop_sync.argtypes = [vp, vp]
+        L.spmv_b200_halo_loop_get_info.argtypes = [vp, C.POINTER(HaloLoopInfo)]
+        L.spmv_b200_halo_loop_destroy.argtypes = [vp]
         L.spmv_b200_enable_peer_access.argtypes = [i32]
         L.spmv_b200_peer_alloc.argtypes = [C.POINTER(vp), i64, C.c_char_p]
         L.spmv_b200_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
@@ -113,6 +124,7 @@ def lib() -> C.CDLL:
         L.spmv_b200_csr_spmv.argtypes = [i32, dbl, dbl, i32, i32, i32, vp, vp, vp, vp, vp]
         L.spmv_b200_sparse_spmv.argtypes = [i32, dbl, dbl, i32, i32, vp, vp, vp, vp, vp]
         L.spmv_b200_hostmat_create.argtypes = [C.POINTER(vp), i32, i32, i64, vp, vp, vp, C.POINTER(Options)]
+        L.spmv_b200_hostmat_create_device.argtypes = [C.POINTER(vp), i32, i32, i64, vp, vp, vp, C.POINTER(Options)]
         L.spmv_b200_hostmat_spmv.argtypes = [vp, dbl, dbl, vp, vp]
         L.spmv_b200_hostmat_destroy.argtypes = [vp]
         L.spmv_b200_hostmat_x_range.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
@@ -123,6 +135,7 @@ def lib() -> C.CDLL:
         for s in ABI_SYMBOLS:
             if s not in ("spmv_b200_last_error",):
                 getattr(L, s).restype = C.c_int
+        L.spmv_b200_cache_revalidations.restype = C.c_int64
         L.spmv_b200_last_error.restype = C.c_char_p
         _lib = L
     return _lib

@@ -222,14 +222,25 @@ class SpmvPlan:
 class HostMatrix:
     """Matrix given in host memory: uploaded + analysed once; every ``spmv`` copies x, y0 in and y out."""
 
-    def __init__(self, rows: int, cols: int, rowptr: np.ndarray, colindex: np.ndarray, value: np.ndarray,
+    def __init__(self, rows: int, cols: int, rowptr: Any, colindex: Any, value: Any,
                  options: Optional[Options] = None):
+        """Host arrays are uploaded; device tensors (the CLI's create_device_data done by the caller) are used in
+        place and must outlive this object."""
         self._h = C.c_void_p()
         self.rows, self.cols, self.nnz = int(rows), int(cols), int(len(value))
-        rc = _lib.lib().spmv_b200_hostmat_create(C.byref(self._h), self.rows, self.cols, self.nnz, _ptr(rowptr),
-                                                 _ptr(colindex), _ptr(value),
-                                                 C.byref(options) if options is not None else None)
-        check(rc, "hostmat_create")
+        opt = C.byref(options) if options is not None else None
+        on_device = [bool(getattr(t, "is_cuda", False)) for t in (rowptr, colindex, value)]
+        if all(on_device):
+            self._keep = (rowptr, colindex, value)
+            rc = _lib.lib().spmv_b200_hostmat_create_device(C.byref(self._h), self.rows, self.cols, self.nnz,
+                                                            _ptr(rowptr), _ptr(colindex), _ptr(value), opt)
+            check(rc, "hostmat_create_device")
+        elif any(on_device):
+            raise SpmvB200Error("HostMatrix: rowptr / colindex / value must be all host or all device arrays")
+        else:
+            rc = _lib.lib().spmv_b200_hostmat_create(C.byref(self._h), self.rows, self.cols, self.nnz, _ptr(rowptr),
+                                                     _ptr(colindex), _ptr(value), opt)
+            check(rc, "hostmat_create")
 
     def spmv(self, alpha: float, beta: float, h_x: Any, h_y: Any) -> None:
         check(_lib.lib().spmv_b200_hostmat_spmv(self._h, float(alpha), float(beta), _ptr(h_x), _ptr(h_y)),
@@ -261,23 +272,44 @@ def host_spmv(alpha: float, beta: float, rows: int, cols: int, rowptr: np.ndarra
     check(rc, "host_spmv")
 
 
-def stream_write_flag(address: int, value: int, stream: Optional[int] = None) -> None:
-    """Stream-ordered 32-bit store (with a system-scope memory barrier) to device memory, possibly another GPU's."""
-    check(_lib.lib().spmv_b200_stream_write_flag(_current_stream() if stream is None else stream, int(address),
-                                                 int(value)), "stream_write_flag")
+class HaloLoop:
+    """x <- A*x on one row shard with the halo exchange fused into the SpMV kernels (``spmv_b200_halo_loop_*``).
+    ``desc`` is a filled ``_lib.HaloLoopDesc``; ``run`` enqueues iterations on the current stream, ``sync`` waits for
+    them and raises ``SpmvB200Error`` if a neighbour's flag timed out."""
+
+    def __init__(self, desc: "_lib.HaloLoopDesc"):
+        self._h = C.c_void_p()
+        self._desc = desc  # keeps the plan / buffers named by the descriptor alive with the loop
+        check(_lib.lib().spmv_b200_halo_loop_create(C.byref(self._h), C.byref(desc)), "halo_loop_create")
+
+    def run(self, iterations: int, stream: Optional[int] = None) -> None:
+        check(_lib.lib().spmv_b200_halo_loop_run(self._h, int(iterations),
+                                                 _current_stream() if stream is None else stream), "halo_loop_run")
+
+    def sync(self, stream: Optional[int] = None) -> None:
+        check(_lib.lib().spmv_b200_halo_loop_sync(self._h, _current_stream() if stream is None else stream),
+              "halo_loop_sync")
+
+    def info(self) -> "_lib.HaloLoopInfo":
+        info = _lib.HaloLoopInfo()
+        check(_lib.lib().spmv_b200_halo_loop_get_info(self._h, C.byref(info)), "halo_loop_get_info")
+        return info
+
+    def destroy(self) -> None:
+        if self._h:
+            _lib.lib().spmv_b200_halo_loop_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
 
 
-def stream_write_flags(addresses: list, value: int, stream: Optional[int] = None) -> None:
-    """``stream_write_flag`` for up to 8 flags with a single launch."""
-    arr = (C.c_void_p * max(len(addresses), 1))(*[int(a) for a in addresses])
-    check(_lib.lib().spmv_b200_stream_write_flags(_current_stream() if stream is None else stream, arr,
-                                                  len(addresses), int(value)), "stream_write_flags")
-
-
-def stream_wait_flag(address: int, value: int, stream: Optional[int] = None) -> None:
-    """Blocks the stream (not the host) until the 32-bit word at ``address`` is >= value."""
-    check(_lib.lib().spmv_b200_stream_wait_flag(_current_stream() if stream is None else stream, int(address),
-                                                int(value)), "stream_wait_flag")
+def cache_revalidations() -> int:
+    """Stateless calls whose cached plan did not match the matrix found at the same addresses (analysed again)."""
+    return int(_lib.lib().spmv_b200_cache_revalidations())
 
 
 def enable_peer_access(peer_device: int) -> None:

@@ -370,14 +370,15 @@ int analysis_prepare(spmv_b200_plan *p, cudaStream_t stream) {
   p->elem_end = h_be[1];
   p->gather_active = p->gather_lines = p->sample_nnz = p->sample_nnz_long = 0;
   if (total > 0 && p->col) {
-    unsigned long long *d_stat = nullptr, h_stat[4];
-    B200_CUDA(cudaMalloc(&d_stat, sizeof(h_stat)));
+    unsigned long long h_stat[4];
+    DeviceScratch stat_buf;
+    B200_CUDA(stat_buf.alloc(sizeof(h_stat)));
+    unsigned long long *d_stat = stat_buf.as<unsigned long long>();
     B200_CUDA(cudaMemsetAsync(d_stat, 0, sizeof(h_stat), stream));
     k_gather_stat<<<kGatherSamples * 32 / 256, 256, 0, stream>>>(p->rowptr, p->col, p->m, p->medium_max, d_stat);
     B200_CUDA(cudaGetLastError());
     B200_CUDA(cudaMemcpyAsync(h_stat, d_stat, sizeof(h_stat), cudaMemcpyDeviceToHost, stream));
     B200_CUDA(cudaStreamSynchronize(stream));
-    B200_CUDA(cudaFree(d_stat));
     p->gather_active = (long long)h_stat[0];
     p->gather_lines = (long long)h_stat[1];
     p->sample_nnz = (long long)h_stat[2];
@@ -402,8 +403,7 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
   const int ntiles = (int)nt;
   p->ntiles = ntiles;
 
-  int *tile_aux = nullptr;
-  unsigned long long *d_hist = nullptr;
+  DeviceScratch aux_buf, hist_buf; // freed on every return path
   size_t ws = 0;
   B200_CUDA(cudaMalloc(&p->tile_row, sizeof(int) * (ntiles + 1)));
   B200_CUDA(cudaMalloc(&p->tile_elem, sizeof(int) * (ntiles + 1)));
@@ -411,8 +411,10 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
   B200_CUDA(cudaMalloc(&p->tile_split, ntiles + 1));
   B200_CUDA(cudaMalloc(&p->tile_maxlen, sizeof(int) * ntiles));
   B200_CUDA(cudaMalloc(&p->tile_kind, ntiles));
-  B200_CUDA(cudaMalloc(&tile_aux, sizeof(int) * (ntiles + 1)));
-  B200_CUDA(cudaMalloc(&d_hist, sizeof(unsigned long long) * 8));
+  B200_CUDA(aux_buf.alloc(sizeof(int) * (ntiles + 1)));
+  B200_CUDA(hist_buf.alloc(sizeof(unsigned long long) * 8));
+  int *tile_aux = aux_buf.as<int>();
+  unsigned long long *d_hist = hist_buf.as<unsigned long long>();
   ws += sizeof(int) * (size_t)(ntiles + 1) * 3 + (ntiles + 1) + sizeof(int) * (size_t)ntiles + ntiles;
   B200_CUDA(cudaMemsetAsync(p->tile_maxlen, 0, sizeof(int) * ntiles, stream));
   B200_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 8, stream));
@@ -432,19 +434,19 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
   B200_CUDA(cudaGetLastError());
   if (p->direct) {
     const size_t words = (size_t)((p->elem_end + 31) / 32) + 16; // slack: a warp reads whole 128-element windows
-    int *nzflag = nullptr, *nzprefix = nullptr;
-    void *scan_tmp = nullptr;
+    DeviceScratch nzflag_buf, nzprefix_buf, scan_buf;
     size_t scan_bytes = 0;
     B200_CUDA(cudaMalloc(&p->row_start_bits, sizeof(unsigned int) * words));
     B200_CUDA(cudaMemsetAsync(p->row_start_bits, 0, sizeof(unsigned int) * words, stream));
-    B200_CUDA(cudaMalloc(&nzflag, sizeof(int) * ((size_t)m + 1)));
-    B200_CUDA(cudaMalloc(&nzprefix, sizeof(int) * ((size_t)m + 1)));
+    B200_CUDA(nzflag_buf.alloc(sizeof(int) * ((size_t)m + 1)));
+    B200_CUDA(nzprefix_buf.alloc(sizeof(int) * ((size_t)m + 1)));
+    int *nzflag = nzflag_buf.as<int>(), *nzprefix = nzprefix_buf.as<int>();
     k_row_start_bits<<<grid_for((long long)m + 1, 256, 148 * 16), 256, 0, stream>>>(p->rowptr, m, p->row_start_bits,
                                                                                     nzflag);
     B200_CUDA(cudaGetLastError());
     B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, nzflag, nzprefix, m + 1, stream));
-    B200_CUDA(cudaMalloc(&scan_tmp, scan_bytes ? scan_bytes : 16));
-    B200_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, nzflag, nzprefix, m + 1, stream));
+    B200_CUDA(scan_buf.alloc(scan_bytes));
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(scan_buf.p, scan_bytes, nzflag, nzprefix, m + 1, stream));
     int h_nz = 0;
     B200_CUDA(cudaMemcpyAsync(&h_nz, nzprefix + m, sizeof(int), cudaMemcpyDeviceToHost, stream));
     B200_CUDA(cudaStreamSynchronize(stream));
@@ -457,9 +459,6 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
     k_desc_direct<<<grid_for(ntiles, 256, 1 << 30), 256, 0, stream>>>(ntiles, p->desc_all, nzprefix, p->desc_direct);
     B200_CUDA(cudaGetLastError());
     B200_CUDA(cudaStreamSynchronize(stream));
-    B200_CUDA(cudaFree(scan_tmp));
-    B200_CUDA(cudaFree(nzflag));
-    B200_CUDA(cudaFree(nzprefix));
     ws += sizeof(unsigned int) * words + sizeof(int) * ((size_t)h_nz + 1) + sizeof(TileDesc) * (size_t)ntiles;
   }
 
@@ -473,8 +472,6 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
   B200_CUDA(cudaMemcpyAsync(h_aux.data(), tile_aux, sizeof(int) * (ntiles + 1), cudaMemcpyDeviceToHost, stream));
   B200_CUDA(cudaMemcpyAsync(h_hist, d_hist, sizeof(h_hist), cudaMemcpyDeviceToHost, stream));
   B200_CUDA(cudaStreamSynchronize(stream));
-  B200_CUDA(cudaFree(tile_aux));
-  B200_CUDA(cudaFree(d_hist));
   for (int b = 0; b < 4; ++b) {
     p->bin_rows[b] = (long long)h_hist[b];
     p->bin_nnz[b] = (long long)h_hist[4 + b];
@@ -533,6 +530,32 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
   }
   B200_CUDA(cudaStreamSynchronize(stream));
   p->workspace_bytes = ws;
+  return SPMV_B200_OK;
+}
+
+// descriptors in a caller-given tile order (the fused halo loop walks boundary row blocks first)
+int analysis_gather_descs(const TileDesc *d_all, const int *h_order, int n, TileDesc **d_out, cudaStream_t stream) {
+  *d_out = nullptr;
+  if (n <= 0)
+    return SPMV_B200_OK;
+  int *d_order = nullptr;
+  TileDesc *out = nullptr;
+  B200_CUDA(cudaMalloc(&d_order, sizeof(int) * (size_t)n));
+  cudaError_t e = cudaMalloc(&out, sizeof(TileDesc) * (size_t)n);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(d_order, h_order, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) {
+    k_gather_desc<<<grid_for(n, 256, 1 << 30), 256, 0, stream>>>(d_order, n, d_all, out);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(stream);
+  cudaFree(d_order);
+  if (e != cudaSuccess) {
+    cudaFree(out);
+    B200_CUDA(e);
+  }
+  *d_out = out;
   return SPMV_B200_OK;
 }
 

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <list>
+#include <map>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -309,151 +310,262 @@ int spmv_b200_plan_tile_col_range(spmv_b200_plan *plan, int32_t *h_min, int32_t 
   return analysis_tile_col_range(plan, h_min, h_max, static_cast<cudaStream_t>(stream));
 }
 
-// stream memory operations of the driver API, fetched at run time (no link-time dependency on libcuda)
-namespace {
-typedef int (*StreamMemOp32)(void *stream, unsigned long long addr, unsigned int value, unsigned int flags);
-StreamMemOp32 driver_fn(const char *name) {
-  void *fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
-    return nullptr;
-  return reinterpret_cast<StreamMemOp32>(fn);
-}
-} // namespace
-
-// The flag may live in another GPU's memory (IPC mapping): a one-thread kernel with a system-scope fence is the
-// portable way to publish it after the stores of the preceding kernels in the stream.
-__global__ void k_write_flag(uint32_t *flag, uint32_t value) {
-  __threadfence_system();
-  *reinterpret_cast<volatile uint32_t *>(flag) = value;
-}
-
-int spmv_b200_stream_write_flag(void *stream, uint32_t *d_flag, uint32_t value) {
-  if (!d_flag) {
-    set_error("stream_write_flag: flag is NULL");
-    return SPMV_B200_ERR_ARG;
-  }
-  k_write_flag<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(d_flag, value);
-  B200_CUDA(cudaGetLastError());
-  return SPMV_B200_OK;
-}
-
-struct FlagList {
-  uint32_t *p[SPMV_B200_MAX_PUSH];
-  int n;
+// ---------------------------------------------------------------------------------------------------------------
+// fused halo loop: x <- A*x on one row shard, halo rows pushed into the neighbours' buffers by the SpMV kernels
+// ---------------------------------------------------------------------------------------------------------------
+struct spmv_b200_halo_loop {
+  spmv_b200_halo_loop_desc d;
+  PushArgs push[2];
+  HaloSync sync;
+  unsigned int *state = nullptr; // device: epoch, finished boundary CTAs, error
+  TileDesc *desc_order = nullptr; // every tile, boundary row blocks first (single-launch mode)
+  bool single_launch = false;
+  bool use_graph = true;
+  long long k = 0; // iterations enqueued so far
+  int chunk = 0;   // iterations per graph launch (even; the graph always starts at an even iteration)
+  cudaGraphExec_t graph = nullptr;
 };
-__global__ void k_write_flags(FlagList f, uint32_t value) {
-  __threadfence_system();
-  if ((int)threadIdx.x < f.n)
-    *reinterpret_cast<volatile uint32_t *>(f.p[threadIdx.x]) = value;
+
+static int halo_enqueue_iteration(spmv_b200_halo_loop *L, int parity, cudaStream_t stream);
+static int halo_build_graph(spmv_b200_halo_loop *L);
+
+static unsigned long long halo_timeout_ns() {
+  const char *e = getenv("SPMV_B200_FLAG_TIMEOUT_MS");
+  const long long ms = e ? atoll(e) : 10000; // a peer that does not answer for 10 s is taken for dead; 0 = wait for ever
+  return ms <= 0 ? 0ull : (unsigned long long)ms * 1000000ull;
 }
 
-int spmv_b200_stream_write_flags(void *stream, uint32_t *const *d_flags, int32_t count, uint32_t value) {
-  if (count < 0 || count > SPMV_B200_MAX_PUSH || (count > 0 && !d_flags)) {
-    set_error("stream_write_flags: bad argument");
+int spmv_b200_halo_loop_create(spmv_b200_halo_loop **out, const spmv_b200_halo_loop_desc *d) {
+  if (!out || !d || !d->plan || !d->buf[0] || !d->buf[1]) {
+    set_error("halo_loop_create: bad argument");
     return SPMV_B200_ERR_ARG;
   }
-  if (count == 0)
-    return SPMV_B200_OK;
-  FlagList f;
-  f.n = count;
-  for (int i = 0; i < SPMV_B200_MAX_PUSH; ++i)
-    f.p[i] = i < count ? d_flags[i] : nullptr;
-  k_write_flags<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(f, value);
-  B200_CUDA(cudaGetLastError());
-  return SPMV_B200_OK;
-}
-
-// Waiting inside a one-thread kernel instead of a stream memory operation: the flags are local memory written by the
-// neighbours over NVLink. The spin is bounded (about 10 s) so that a protocol error cannot hang the device.
-__global__ void k_wait_flags(FlagList f, uint32_t value) {
-  if ((int)threadIdx.x < f.n) {
-    const volatile uint32_t *p = reinterpret_cast<volatile uint32_t *>(f.p[threadIdx.x]);
-    const long long t0 = clock64();
-    while (*p < value && clock64() - t0 < 20000000000LL) {
+  *out = nullptr;
+  const spmv_b200_plan *p = d->plan;
+  if (d->n_neigh < 0 || d->n_neigh > SPMV_B200_MAX_PUSH || d->n_boundary < 0 || d->n_boundary > SPMV_B200_MAX_RANGES ||
+      d->n_interior < 0 || d->n_interior > SPMV_B200_MAX_RANGES || d->row_lo < 0 || d->row_hi < d->row_lo ||
+      d->row_hi - d->row_lo != p->m) {
+    set_error("halo_loop_create: inconsistent descriptor");
+    return SPMV_B200_ERR_ARG;
+  }
+  // the ranges must be disjoint, inside [0, ntiles) and (when a boundary is given) cover every tile
+  std::vector<int> order;
+  std::vector<char> seen((size_t)p->ntiles, 0);
+  int nb_tiles = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int n = pass == 0 ? d->n_boundary : d->n_interior;
+    const int32_t *r = pass == 0 ? d->boundary : d->interior;
+    for (int i = 0; i < n; ++i) {
+      if (r[2 * i] < 0 || r[2 * i + 1] > p->ntiles || r[2 * i] > r[2 * i + 1]) {
+        set_error("halo_loop_create: tile range out of bounds");
+        return SPMV_B200_ERR_ARG;
+      }
+      for (int t = r[2 * i]; t < r[2 * i + 1]; ++t) {
+        if (seen[(size_t)t]) {
+          set_error("halo_loop_create: tile ranges overlap");
+          return SPMV_B200_ERR_ARG;
+        }
+        seen[(size_t)t] = 1;
+        order.push_back(t);
+      }
+    }
+    if (pass == 0)
+      nb_tiles = (int)order.size();
+  }
+  if (d->n_boundary > 0 && (int)order.size() != p->ntiles) {
+    set_error("halo_loop_create: boundary + interior ranges do not cover every row block");
+    return SPMV_B200_ERR_ARG;
+  }
+  if (d->n_boundary > 0 && p->nsplit > 0) {
+    set_error("halo_loop_create: a plan with split rows cannot be run boundary-first");
+    return SPMV_B200_ERR_UNSUPPORTED;
+  }
+  if (d->n_boundary == 0) { // no split schedule: the whole shard is "boundary" (waits first, signals when all is stored)
+    order.resize((size_t)p->ntiles);
+    for (int t = 0; t < p->ntiles; ++t)
+      order[(size_t)t] = t;
+    nb_tiles = p->ntiles;
+  }
+  spmv_b200_halo_loop *L = new (std::nothrow) spmv_b200_halo_loop();
+  if (!L) {
+    set_error("halo_loop_create: out of host memory");
+    return SPMV_B200_ERR_ARG;
+  }
+  L->d = *d;
+  for (int b = 0; b < 2; ++b)
+    if (int rc = convert_push(p, &d->push[b], &L->push[b], "halo_loop_create")) {
+      delete L;
+      return rc;
+    }
+  cudaError_t e = cudaMalloc(&L->state, 4 * sizeof(unsigned int));
+  if (e == cudaSuccess)
+    e = cudaMemset(L->state, 0, 4 * sizeof(unsigned int));
+  if (e != cudaSuccess) {
+    cudaFree(L->state);
+    delete L;
+    B200_CUDA(e);
+  }
+  for (int j = 0; j < SPMV_B200_MAX_PUSH; ++j) {
+    L->sync.wait[j] = j < d->n_neigh ? d->wait_flags[j] : nullptr;
+    L->sync.signal[j] = j < d->n_neigh ? d->signal_flags[j] : nullptr;
+    if (j < d->n_neigh && (!d->wait_flags[j] || !d->signal_flags[j])) {
+      cudaFree(L->state);
+      delete L;
+      set_error("halo_loop_create: NULL flag pointer");
+      return SPMV_B200_ERR_ARG;
     }
   }
-  __threadfence_system();
+  L->sync.n_neigh = d->n_neigh;
+  L->sync.n_boundary = d->n_neigh > 0 ? nb_tiles : 0; // a rank without neighbours orders nothing
+  L->sync.state = L->state;
+  L->sync.timeout_ns = halo_timeout_ns();
+  L->use_graph = !(d->flags & SPMV_B200_HALO_NO_GRAPH);
+  L->single_launch = !(d->flags & SPMV_B200_HALO_MULTI_LAUNCH) && kernels_halo_single_launch_ok(p);
+  if (L->single_launch) {
+    if (int rc = analysis_gather_descs(p->desc_all, order.data(), p->ntiles, &L->desc_order, nullptr)) {
+      cudaFree(L->state);
+      delete L;
+      return rc;
+    }
+  }
+  if (L->use_graph) {
+    const char *e = getenv("SPMV_B200_HALO_GRAPH_CHUNK");
+    int c = e ? atoi(e) : 20;
+    L->chunk = c < 2 ? 2 : (c > 1000 ? 1000 : (c & ~1));
+    if (int rc = halo_build_graph(L)) {
+      const std::string keep = g_last_error;
+      spmv_b200_halo_loop_destroy(L);
+      g_last_error = keep;
+      return rc;
+    }
+  }
+  *out = L;
+  return SPMV_B200_OK;
 }
 
-int spmv_b200_stream_wait_flags(void *stream, uint32_t *const *d_flags, int32_t count, uint32_t value) {
-  if (count < 0 || count > SPMV_B200_MAX_PUSH || (count > 0 && !d_flags)) {
-    set_error("stream_wait_flags: bad argument");
-    return SPMV_B200_ERR_ARG;
-  }
-  if (count == 0)
-    return SPMV_B200_OK;
-  static const bool use_memop = [] {
-    const char *e = getenv("SPMV_B200_FLAG_WAIT");
-    return e && std::string(e) == "memop";
-  }();
-  if (use_memop) {
-    for (int i = 0; i < count; ++i)
-      if (int rc = spmv_b200_stream_wait_flag(stream, d_flags[i], value))
+// one iteration, enqueued (also under stream capture): parity of the source buffer is a launch parameter, the epoch
+// the flags are compared with lives in device memory
+static int halo_enqueue_iteration(spmv_b200_halo_loop *L, int parity, cudaStream_t stream) {
+  const spmv_b200_halo_loop_desc &d = L->d;
+  const double *src = d.buf[parity];
+  double *ys = d.buf[parity ^ 1] + d.row_lo;
+  const PushArgs *push = &L->push[parity ^ 1];
+  if (L->single_launch)
+    return kernels_launch_halo(d.plan, L->desc_order, src, ys, push, L->sync, stream);
+  int rc;
+  if (d.n_neigh > 0 && (rc = kernels_halo_wait(L->sync, stream)))
+    return rc;
+  if (d.n_boundary > 0) {
+    for (int r = 0; r < d.n_boundary; ++r)
+      if (d.boundary[2 * r + 1] > d.boundary[2 * r] &&
+          (rc = kernels_launch_tiles(d.plan, 1.0, 0.0, src, ys, d.boundary[2 * r], d.boundary[2 * r + 1], stream, push)))
+        return rc;
+    if (d.n_neigh > 0 && (rc = kernels_halo_signal(L->sync, stream)))
+      return rc;
+    for (int r = 0; r < d.n_interior; ++r)
+      if (d.interior[2 * r + 1] > d.interior[2 * r] &&
+          (rc = kernels_launch_tiles(d.plan, 1.0, 0.0, src, ys, d.interior[2 * r], d.interior[2 * r + 1], stream)))
         return rc;
     return SPMV_B200_OK;
   }
-  FlagList f;
-  f.n = count;
-  for (int i = 0; i < SPMV_B200_MAX_PUSH; ++i)
-    f.p[i] = i < count ? d_flags[i] : nullptr;
-  k_wait_flags<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(f, value);
-  B200_CUDA(cudaGetLastError());
+  if ((rc = kernels_launch(d.plan, 1.0, 0.0, src, ys, stream, push)))
+    return rc;
+  return d.n_neigh > 0 ? kernels_halo_signal(L->sync, stream) : SPMV_B200_OK;
+}
+
+// `chunk` iterations captured into one executable graph (on a stream of our own: the caller's may be the legacy null
+// stream, which cannot be captured). Nothing is executed here.
+static int halo_build_graph(spmv_b200_halo_loop *L) {
+  cudaStream_t cs = nullptr;
+  cudaGraph_t graph = nullptr;
+  B200_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+  int rc = SPMV_B200_OK;
+  if (e == cudaSuccess) {
+    for (int i = 0; i < L->chunk && rc == SPMV_B200_OK; ++i)
+      rc = halo_enqueue_iteration(L, i & 1, cs);
+    e = cudaStreamEndCapture(cs, &graph);
+  }
+  if (e == cudaSuccess && rc == SPMV_B200_OK)
+    e = cudaGraphInstantiate(&L->graph, graph, 0);
+  if (graph)
+    cudaGraphDestroy(graph);
+  cudaStreamDestroy(cs);
+  if (rc != SPMV_B200_OK)
+    return rc;
+  B200_CUDA(e);
   return SPMV_B200_OK;
 }
 
-int spmv_b200_stream_wait_flag(void *stream, uint32_t *d_flag, uint32_t value) {
-  static StreamMemOp32 fn = driver_fn("cuStreamWaitValue32");
-  if (!fn) {
-    set_error("cuStreamWaitValue32 is not available");
-    return SPMV_B200_ERR_UNSUPPORTED;
-  }
-  const int rc = fn(stream, (unsigned long long)(uintptr_t)d_flag, value, 0u /* CU_STREAM_WAIT_VALUE_GEQ */);
-  if (rc != 0) {
-    set_error("cuStreamWaitValue32 failed with CUresult " + std::to_string(rc));
-    return SPMV_B200_ERR_CUDA;
-  }
-  return SPMV_B200_OK;
-}
-
-int spmv_b200_halo_loop_run(const spmv_b200_halo_loop_desc *d, int32_t first_iteration, int32_t iterations,
-                            void *stream) {
-  if (!d || !d->plan || !d->buf[0] || !d->buf[1] || first_iteration < 0 || iterations < 0) {
+int spmv_b200_halo_loop_run(spmv_b200_halo_loop *L, int32_t iterations, void *stream_) {
+  if (!L || iterations < 0) {
     set_error("halo_loop_run: bad argument");
     return SPMV_B200_ERR_ARG;
   }
-  if (d->n_neigh < 0 || d->n_neigh > SPMV_B200_MAX_PUSH || d->n_boundary < 0 || d->n_boundary > SPMV_B200_MAX_RANGES ||
-      d->n_interior < 0 || d->n_interior > SPMV_B200_MAX_RANGES || d->row_lo < 0 || d->row_hi < d->row_lo ||
-      d->row_hi - d->row_lo != d->plan->m) {
-    set_error("halo_loop_run: inconsistent descriptor");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int left = iterations, rc;
+  if (left > 0 && (L->k & 1)) { // graph launches start at an even iteration
+    if ((rc = halo_enqueue_iteration(L, 1, stream)))
+      return rc;
+    ++L->k;
+    --left;
+  }
+  while (L->graph && left >= L->chunk) {
+    B200_CUDA(cudaGraphLaunch(L->graph, stream));
+    L->k += L->chunk;
+    left -= L->chunk;
+  }
+  for (; left > 0; --left, ++L->k)
+    if ((rc = halo_enqueue_iteration(L, (int)(L->k & 1), stream)))
+      return rc;
+  return SPMV_B200_OK;
+}
+
+int spmv_b200_halo_loop_sync(spmv_b200_halo_loop *L, void *stream) {
+  if (!L) {
+    set_error("halo_loop_sync: loop is NULL");
     return SPMV_B200_ERR_ARG;
   }
-  for (int32_t i = 0; i < iterations; ++i) {
-    const int32_t k = first_iteration + i;
-    int rc;
-    if (k > 0 && (rc = spmv_b200_stream_wait_flags(stream, d->wait_flags, d->n_neigh, (uint32_t)k)))
-      return rc;
-    const double *src = d->buf[k & 1];
-    double *ys = d->buf[(k + 1) & 1] + d->row_lo;
-    const spmv_b200_push *push = &d->push[(k + 1) & 1];
-    if (d->n_boundary > 0) {
-      for (int r = 0; r < d->n_boundary; ++r)
-        if ((rc = spmv_b200_execute_tiles_push(d->plan, 1.0, 0.0, src, ys, d->boundary[2 * r], d->boundary[2 * r + 1],
-                                               push, stream)))
-          return rc;
-      if ((rc = spmv_b200_stream_write_flags(stream, d->signal_flags, d->n_neigh, (uint32_t)(k + 1))))
-        return rc;
-      for (int r = 0; r < d->n_interior; ++r)
-        if ((rc = spmv_b200_execute_tiles(d->plan, 1.0, 0.0, src, ys, d->interior[2 * r], d->interior[2 * r + 1],
-                                          stream)))
-          return rc;
-    } else {
-      if ((rc = spmv_b200_execute_push(d->plan, 1.0, 0.0, src, ys, push, stream)))
-        return rc;
-      if ((rc = spmv_b200_stream_write_flags(stream, d->signal_flags, d->n_neigh, (uint32_t)(k + 1))))
-        return rc;
-    }
+  B200_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  unsigned int st[4] = {0, 0, 0, 0};
+  B200_CUDA(cudaMemcpy(st, L->state, sizeof(st), cudaMemcpyDeviceToHost));
+  if (st[2] != 0u) {
+    set_error("halo loop: a neighbour's flag did not reach iteration " + std::to_string(st[2] & 0x7fffffffu) +
+              " in time; x is not valid from that iteration on");
+    return SPMV_B200_ERR_TIMEOUT;
   }
+  return SPMV_B200_OK;
+}
+
+int spmv_b200_halo_loop_get_info(const spmv_b200_halo_loop *L, spmv_b200_halo_loop_info *info) {
+  if (!L || !info) {
+    set_error("halo_loop_get_info: NULL argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  std::memset(info, 0, sizeof(*info));
+  info->iterations_enqueued = L->k;
+  info->single_launch = L->single_launch ? 1 : 0;
+  info->uses_graph = L->graph ? L->chunk : 0;
+  info->boundary_row_blocks = L->sync.n_boundary;
+  int launches = 1;
+  if (!L->single_launch) {
+    const spmv_b200_halo_loop_desc &d = L->d;
+    spmv_b200_plan_info pi;
+    spmv_b200_plan_get_info(d.plan, &pi);
+    launches = (d.n_neigh > 0 ? 2 : 1) + (d.n_boundary > 0 ? d.n_boundary + d.n_interior : pi.launches_per_execute);
+  }
+  info->launches_per_iteration = launches;
+  return SPMV_B200_OK;
+}
+
+int spmv_b200_halo_loop_destroy(spmv_b200_halo_loop *L) {
+  if (!L)
+    return SPMV_B200_OK;
+  if (L->graph)
+    cudaGraphExecDestroy(L->graph);
+  cudaFree(L->desc_order);
+  cudaFree(L->state);
+  delete L;
   return SPMV_B200_OK;
 }
 
@@ -635,13 +747,12 @@ int spmv_b200_plan_export(spmv_b200_plan *p, int32_t what, void *h_dst, int64_t 
     return SPMV_B200_ERR_ARG;
   }
   if (what == SPMV_B200_EXPORT_ROW_BIN) {
-    unsigned char *d_tmp = nullptr;
-    B200_CUDA(cudaMalloc(&d_tmp, (size_t)bytes));
-    int rc = analysis_row_bins(p, d_tmp, nullptr);
-    if (rc == SPMV_B200_OK && cudaMemcpy(h_dst, d_tmp, (size_t)bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
-      rc = cuda_fail(cudaGetLastError(), "cudaMemcpy(row bins)", __FILE__, __LINE__);
-    cudaFree(d_tmp);
-    return rc;
+    DeviceScratch tmp;
+    B200_CUDA(tmp.alloc((size_t)bytes));
+    if (int rc = analysis_row_bins(p, tmp.as<unsigned char>(), nullptr))
+      return rc;
+    B200_CUDA(cudaMemcpy(h_dst, tmp.p, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return SPMV_B200_OK;
   }
   if (what == SPMV_B200_EXPORT_TILE_NZBASE) { // field head_end of the direct descriptors
     std::vector<TileDesc> h((size_t)nt);
@@ -655,9 +766,47 @@ int spmv_b200_plan_export(spmv_b200_plan *p, int32_t what, void *h_dst, int64_t 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// stateless entry points: a small plan cache keyed on the device pointers and the shape
+// stateless entry points: a small plan cache keyed on the device pointers and the shape, validated on every hit
 // ---------------------------------------------------------------------------------------------------------------
+// sparse_csr_spmv has no handle (src/acc/api/spmv.h:20-21), so the one-time analysis is kept in a cache. Pointers and
+// shape alone do not identify a matrix: a caching allocator hands the same addresses to the next matrix of the same
+// size. Everything a plan derives (row blocks, split rows, row-start flags) is a function of the row pointers, so every
+// hit re-reads a fingerprint of them on the device -- rowptr[0], rowptr[m] and kFingerSamples evenly spaced entries,
+// hashed position-wise -- and a mismatch drops the plan and analyses again. Cost: one single-CTA kernel and a read of
+// 8 bytes of mapped host memory per call (SPMV_B200_CACHE_TRUST=1 in the environment skips it for callers that
+// guarantee immutable matrices; the plan API never pays it).
 namespace {
+constexpr int kFingerSamples = 2048;
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) k_fingerprint(const int *__restrict__ rowptr, int m,
+                                                      unsigned long long *__restrict__ out) {
+  __shared__ unsigned long long sh[8];
+  unsigned long long h = 0ull; // wrapping sum of position-keyed hashes: independent of the order of the additions
+  for (int i = threadIdx.x; i <= kFingerSamples; i += blockDim.x) {
+    const long long pos = ((long long)m * i) / kFingerSamples; // i == kFingerSamples: rowptr[m]
+    h += mix64(((unsigned long long)pos << 32) ^ (unsigned int)__ldg(rowptr + pos));
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+    h += __shfl_xor_sync(0xffffffffu, h, off);
+  if ((threadIdx.x & 31) == 0)
+    sh[threadIdx.x >> 5] = h;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0ull;
+    for (int w = 0; w < 8; ++w)
+      t += sh[w];
+    *out = t | 1ull; // never 0: 0 marks "not written yet"
+  }
+}
+
 struct CacheKey {
   const void *rowptr, *col, *val;
   int m, n, device;
@@ -668,36 +817,76 @@ struct CacheKey {
 struct CacheEntry {
   CacheKey key;
   spmv_b200_plan *plan;
+  unsigned long long fingerprint;
 };
 std::mutex g_cache_mutex;
 std::list<CacheEntry> g_cache; // most recently used first
 constexpr size_t kCacheCapacity = 16;
+unsigned long long *g_finger_host = nullptr; // mapped pinned word the fingerprint kernel writes
+long long g_cache_revalidations = 0;         // hits whose fingerprint did not match (plan analysed again)
 
-int cached_plan(int m, int n, long long nnz, const int *rowptr, const int *col, const double *val,
-                spmv_b200_plan **out) {
+bool cache_trusted() {
+  static const bool t = [] {
+    const char *e = getenv("SPMV_B200_CACHE_TRUST");
+    return e && e[0] == '1';
+  }();
+  return t;
+}
+
+// fingerprint of rowptr as it is now in device memory (null stream; returns after the kernel has finished)
+int read_fingerprint(const int *rowptr, int m, unsigned long long *out) {
+  *out = 1ull;
+  if (m <= 0 || !rowptr)
+    return SPMV_B200_OK;
+  if (!g_finger_host)
+    B200_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&g_finger_host), sizeof(unsigned long long), cudaHostAllocMapped));
+  unsigned long long *d_out = nullptr;
+  B200_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_out), g_finger_host, 0));
+  *g_finger_host = 0ull;
+  k_fingerprint<<<1, 256, 0, nullptr>>>(rowptr, m, d_out);
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaStreamSynchronize(nullptr));
+  *out = *reinterpret_cast<volatile unsigned long long *>(g_finger_host);
+  return SPMV_B200_OK;
+}
+
+// Looks the matrix up (or analyses it) and enqueues the SpMV, all under the cache lock: another host thread cannot
+// evict or invalidate the plan between the lookup and the launches.
+int cached_spmv(int m, int n, long long nnz, const int *rowptr, const int *col, const double *val, double alpha,
+                double beta, const double *x, double *y) {
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
   const CacheKey key{rowptr, col, val, m, n, dev};
   std::lock_guard<std::mutex> lock(g_cache_mutex);
+  unsigned long long fp = 1ull;
+  const bool validate = !cache_trusted();
+  if (validate)
+    if (int rc = read_fingerprint(rowptr, m, &fp))
+      return rc;
   for (auto it = g_cache.begin(); it != g_cache.end(); ++it) {
-    if (it->key == key && (nnz < 0 || it->plan->nnz == nnz)) {
-      g_cache.splice(g_cache.begin(), g_cache, it);
-      *out = g_cache.front().plan;
-      return SPMV_B200_OK;
+    if (!(it->key == key))
+      continue;
+    if ((nnz >= 0 && it->plan->nnz != nnz) || (validate && it->fingerprint != fp)) {
+      // same addresses, other contents: the old analysis is worthless
+      ++g_cache_revalidations;
+      spmv_b200_plan_destroy(it->plan);
+      g_cache.erase(it);
+      break;
     }
+    g_cache.splice(g_cache.begin(), g_cache, it);
+    return spmv_b200_execute(g_cache.front().plan, alpha, beta, x, y, nullptr);
   }
   spmv_b200_plan *p = nullptr;
   const int rc = spmv_b200_plan_create(&p, m, n, nnz, rowptr, col, val, nullptr, nullptr);
   if (rc != SPMV_B200_OK)
     return rc;
-  g_cache.push_front(CacheEntry{key, p});
+  g_cache.push_front(CacheEntry{key, p, fp});
   while (g_cache.size() > kCacheCapacity) {
     // plans may still have kernels in flight on the null stream; cudaFree synchronises implicitly
     spmv_b200_plan_destroy(g_cache.back().plan);
     g_cache.pop_back();
   }
-  *out = p;
-  return SPMV_B200_OK;
+  return spmv_b200_execute(p, alpha, beta, x, y, nullptr);
 }
 } // namespace
 
@@ -708,11 +897,7 @@ int spmv_b200_csr_spmv(int32_t trans, double alpha, double beta, int32_t m, int3
     set_error("csr_spmv: only operation_none (trans = 0) is supported");
     return SPMV_B200_ERR_UNSUPPORTED;
   }
-  spmv_b200_plan *p = nullptr;
-  const int rc = cached_plan(m, n, nnz, d_rowptr, d_colidx, d_val, &p);
-  if (rc != SPMV_B200_OK)
-    return rc;
-  return spmv_b200_execute(p, alpha, beta, d_x, d_y, nullptr);
+  return cached_spmv(m, n, nnz, d_rowptr, d_colidx, d_val, alpha, beta, d_x, d_y);
 }
 
 int spmv_b200_sparse_spmv(int32_t trans, double alpha, double beta, int32_t m, int32_t n, const int32_t *d_rowptr,
@@ -722,11 +907,7 @@ int spmv_b200_sparse_spmv(int32_t trans, double alpha, double beta, int32_t m, i
     set_error("sparse_spmv: only operation_none (trans = 0) is supported");
     return SPMV_B200_ERR_UNSUPPORTED;
   }
-  spmv_b200_plan *p = nullptr;
-  const int rc = cached_plan(m, n, -1, d_rowptr, d_colidx, d_val, &p);
-  if (rc != SPMV_B200_OK)
-    return rc;
-  return spmv_b200_execute(p, alpha, beta, d_x, d_y, nullptr);
+  return cached_spmv(m, n, -1, d_rowptr, d_colidx, d_val, alpha, beta, d_x, d_y);
 }
 
 int spmv_b200_cache_invalidate(void) {
@@ -744,6 +925,11 @@ int spmv_b200_cache_size(void) {
   return (int)g_cache.size();
 }
 
+int64_t spmv_b200_cache_revalidations(void) {
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  return (int64_t)g_cache_revalidations;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host-buffer path (the CLI's pattern: matrix uploaded once, y0 copied in and y copied out around every call,
 // cli/utils.hpp:94-116 and cli/main.cpp:99-118)
@@ -756,6 +942,7 @@ struct spmv_b200_hostmat {
   double *d_val = nullptr;
   double *d_x = nullptr;
   double *d_y = nullptr;
+  bool owns_matrix = true; // false: rowptr / col / val are the caller's device arrays (hostmat_create_device)
   spmv_b200_plan *plan = nullptr;
   cudaStream_t stream = nullptr;                 // compute (and the non-pipelined path)
   cudaStream_t s_in = nullptr, s_out = nullptr;  // host->device and device->host copy streams (pipelined path)
@@ -779,9 +966,11 @@ int spmv_b200_hostmat_destroy(spmv_b200_hostmat *hm) {
   if (hm->stream)
     cudaStreamSynchronize(hm->stream);
   spmv_b200_plan_destroy(hm->plan);
-  cudaFree(hm->d_rowptr);
-  cudaFree(hm->d_col);
-  cudaFree(hm->d_val);
+  if (hm->owns_matrix) {
+    cudaFree(hm->d_rowptr);
+    cudaFree(hm->d_col);
+    cudaFree(hm->d_val);
+  }
   cudaFree(hm->d_x);
   cudaFree(hm->d_y);
   for (cudaEvent_t e : hm->ev_in)
@@ -799,7 +988,7 @@ int spmv_b200_hostmat_destroy(spmv_b200_hostmat *hm) {
 
 static int hostmat_build(spmv_b200_hostmat *hm, const int32_t *h_rowptr, const int32_t *h_colidx, const double *h_val,
                          const spmv_b200_options *opt) {
-  const size_t m = (size_t)hm->m, n = (size_t)hm->n, nnz = (size_t)hm->nnz;
+  const size_t m = (size_t)hm->m, n = (size_t)hm->n, nnz = hm->nnz > 0 ? (size_t)hm->nnz : 0;
   B200_CUDA(cudaStreamCreateWithFlags(&hm->stream, cudaStreamNonBlocking));
   B200_CUDA(cudaStreamCreateWithFlags(&hm->s_in, cudaStreamNonBlocking));
   B200_CUDA(cudaStreamCreateWithFlags(&hm->s_out, cudaStreamNonBlocking));
@@ -810,22 +999,26 @@ static int hostmat_build(spmv_b200_hostmat *hm, const int32_t *h_rowptr, const i
     B200_CUDA(cudaEventCreateWithFlags(&hm->ev_in[c], cudaEventDisableTiming));
     B200_CUDA(cudaEventCreateWithFlags(&hm->ev_done[c], cudaEventDisableTiming));
   }
-  B200_CUDA(cudaMalloc(&hm->d_rowptr, sizeof(int) * (m + 1)));
-  B200_CUDA(cudaMalloc(&hm->d_col, sizeof(int) * (nnz ? nnz : 1)));
-  B200_CUDA(cudaMalloc(&hm->d_val, sizeof(double) * (nnz ? nnz : 1)));
+  if (hm->owns_matrix) {
+    B200_CUDA(cudaMalloc(&hm->d_rowptr, sizeof(int) * (m + 1)));
+    B200_CUDA(cudaMalloc(&hm->d_col, sizeof(int) * (nnz ? nnz : 1)));
+    B200_CUDA(cudaMalloc(&hm->d_val, sizeof(double) * (nnz ? nnz : 1)));
+  }
   B200_CUDA(cudaMalloc(&hm->d_x, sizeof(double) * (n ? n : 1)));
   B200_CUDA(cudaMalloc(&hm->d_y, sizeof(double) * (m ? m : 1)));
-  B200_CUDA(cudaMemcpyAsync(hm->d_rowptr, h_rowptr, sizeof(int) * (m + 1), cudaMemcpyHostToDevice, hm->stream));
-  if (nnz) {
-    B200_CUDA(cudaMemcpyAsync(hm->d_col, h_colidx, sizeof(int) * nnz, cudaMemcpyHostToDevice, hm->stream));
-    B200_CUDA(cudaMemcpyAsync(hm->d_val, h_val, sizeof(double) * nnz, cudaMemcpyHostToDevice, hm->stream));
+  if (hm->owns_matrix) {
+    B200_CUDA(cudaMemcpyAsync(hm->d_rowptr, h_rowptr, sizeof(int) * (m + 1), cudaMemcpyHostToDevice, hm->stream));
+    if (nnz) {
+      B200_CUDA(cudaMemcpyAsync(hm->d_col, h_colidx, sizeof(int) * nnz, cudaMemcpyHostToDevice, hm->stream));
+      B200_CUDA(cudaMemcpyAsync(hm->d_val, h_val, sizeof(double) * nnz, cudaMemcpyHostToDevice, hm->stream));
+    }
   }
   int rc = spmv_b200_plan_create(&hm->plan, hm->m, hm->n, hm->nnz, hm->d_rowptr, hm->d_col, hm->d_val, opt, hm->stream);
   if (rc != SPMV_B200_OK)
     return rc;
   hm->col_lo = 0;
   hm->col_hi = hm->n;
-  if (hm->plan->ntiles > 0 && nnz > 0) {
+  if (hm->plan->ntiles > 0 && hm->plan->nnz > 0) {
     std::vector<int> cmin((size_t)hm->plan->ntiles);
     hm->tile_cmax.resize((size_t)hm->plan->ntiles);
     if ((rc = analysis_tile_col_range(hm->plan, cmin.data(), hm->tile_cmax.data(), hm->stream)))
@@ -879,12 +1072,47 @@ int spmv_b200_hostmat_create(spmv_b200_hostmat **out, int32_t m, int32_t n, int6
   return SPMV_B200_OK;
 }
 
+int spmv_b200_hostmat_create_device(spmv_b200_hostmat **out, int32_t m, int32_t n, int64_t nnz,
+                                    const int32_t *d_rowptr, const int32_t *d_colidx, const double *d_val,
+                                    const spmv_b200_options *opt) {
+  if (!out || m < 0 || n < 0 || nnz > 0x7fffffffLL || (m > 0 && !d_rowptr)) {
+    set_error("hostmat_create_device: invalid argument");
+    return SPMV_B200_ERR_ARG;
+  }
+  *out = nullptr;
+  spmv_b200_hostmat *hm = new (std::nothrow) spmv_b200_hostmat();
+  if (!hm) {
+    set_error("hostmat_create_device: out of host memory");
+    return SPMV_B200_ERR_ARG;
+  }
+  hm->m = m;
+  hm->n = n;
+  hm->nnz = nnz; // < 0: the analysis reads it from rowptr
+  hm->owns_matrix = false;
+  hm->d_rowptr = const_cast<int *>(d_rowptr);
+  hm->d_col = const_cast<int *>(d_colidx);
+  hm->d_val = const_cast<double *>(d_val);
+  int rc = hostmat_build(hm, nullptr, nullptr, nullptr, opt);
+  if (rc == SPMV_B200_OK)
+    hm->nnz = hm->plan->nnz;
+  if (rc != SPMV_B200_OK) {
+    const std::string keep = g_last_error;
+    spmv_b200_hostmat_destroy(hm);
+    g_last_error = keep;
+    return rc;
+  }
+  *out = hm;
+  return SPMV_B200_OK;
+}
+
 int spmv_b200_hostmat_spmv(spmv_b200_hostmat *hm, double alpha, double beta, const double *h_x, double *h_y) {
   if (!hm || (hm->n > 0 && !h_x) || (hm->m > 0 && !h_y)) {
     set_error("hostmat_spmv: invalid argument");
     return SPMV_B200_ERR_ARG;
   }
   const spmv_b200_plan *p = hm->plan;
+  // beta == 0 with SPMV_B200_FLAG_BETA0_SKIP_Y: the kernels never read y, so y0 does not travel either
+  const bool send_y0 = !(beta == 0.0 && (p->flags & SPMV_B200_FLAG_BETA0_SKIP_Y));
   // Pipelined path (no split rows, enough tiles): x goes up first; then the rows are walked in chunks of tiles, the y0
   // chunk c+1 travels host->device while chunk c is multiplied and the y chunk c-1 travels device->host, so the two
   // PCIe directions are busy at the same time. Rows of a chunk are final once its kernels have run.
@@ -909,14 +1137,18 @@ int spmv_b200_hostmat_spmv(spmv_b200_hostmat *hm, double alpha, double beta, con
                                   cudaMemcpyHostToDevice, hm->s_in));
         x_sent = need;
       }
-      if (rhi > rlo)
+      if (rhi > rlo && send_y0)
         B200_CUDA(cudaMemcpyAsync(hm->d_y + rlo, h_y + rlo, sizeof(double) * (rhi - rlo), cudaMemcpyHostToDevice,
                                   hm->s_in));
       B200_CUDA(cudaEventRecord(hm->ev_in[c], hm->s_in));
       B200_CUDA(cudaStreamWaitEvent(hm->stream, hm->ev_in[c], 0));
       const int rc = kernels_launch_tiles(p, alpha, beta, hm->d_x, hm->d_y, tlo, thi, hm->stream);
-      if (rc != SPMV_B200_OK)
+      if (rc != SPMV_B200_OK) { // copies of earlier chunks are still in flight on the caller's buffers
+        cudaStreamSynchronize(hm->s_in);
+        cudaStreamSynchronize(hm->stream);
+        cudaStreamSynchronize(hm->s_out);
         return rc;
+      }
       B200_CUDA(cudaEventRecord(hm->ev_done[c], hm->stream));
       B200_CUDA(cudaStreamWaitEvent(hm->s_out, hm->ev_done[c], 0));
       if (rhi > rlo)
@@ -930,7 +1162,7 @@ int spmv_b200_hostmat_spmv(spmv_b200_hostmat *hm, double alpha, double beta, con
   if (hm->col_hi > hm->col_lo)
     B200_CUDA(cudaMemcpyAsync(hm->d_x + hm->col_lo, h_x + hm->col_lo, sizeof(double) * (size_t)(hm->col_hi - hm->col_lo),
                               cudaMemcpyHostToDevice, hm->stream));
-  if (hm->m > 0)
+  if (hm->m > 0 && send_y0)
     B200_CUDA(cudaMemcpyAsync(hm->d_y, h_y, sizeof(double) * (size_t)hm->m, cudaMemcpyHostToDevice, hm->stream));
   const int rc = spmv_b200_execute(hm->plan, alpha, beta, hm->d_x, hm->d_y, hm->stream);
   if (rc != SPMV_B200_OK)

@@ -32,6 +32,20 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
       return ::b200::cuda_fail(_e, #call, __FILE__, __LINE__);                                                         \
   } while (0)
 
+// scratch device memory / events that must not outlive an early error return (B200_CUDA returns from the function)
+struct DeviceScratch {
+  void *p = nullptr;
+  DeviceScratch() = default;
+  DeviceScratch(const DeviceScratch &) = delete;
+  DeviceScratch &operator=(const DeviceScratch &) = delete;
+  ~DeviceScratch() {
+    if (p)
+      cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
 // Everything a CTA needs to know about its tile, packed into 32 bytes so that the prologue of a CTA is a single
 // round trip to memory (two 128-bit loads) before the TMA copies can be issued. Built per tile kind by the analysis.
 struct __align__(16) TileDesc {
@@ -72,8 +86,21 @@ struct SpmvArgs {
   int read_y;   // 0: beta == 0 and SPMV_B200_FLAG_BETA0_SKIP_Y
   int gather_na; // 1: x gathers use L1::no_allocate
   int rotate_slots; // MEDIUM kernel: lane groups walk the slots of a round in rotated order (bank conflicts)
-  int stream_prefetch; // direct form: keep value / colindex a few windows ahead in L2 (prefetch.global.L2)
   PushArgs push;
+};
+
+// Ordering of the iterations of neighbouring GPUs inside the SpMV kernel of the fused halo loop (capi.cu,
+// spmv_b200_halo_loop_*): CTAs [0, n_boundary) stream the boundary row blocks. Each of them waits until every
+// neighbour's flag has reached the epoch (the neighbour's rows of the current x have arrived and it no longer reads the
+// buffer about to be overwritten) before it gathers x; the last of them to finish raises this rank's flag in the
+// neighbours' memory and advances the epoch. state = {epoch, finished boundary CTAs, error}.
+struct HaloSync {
+  unsigned int *wait[kMaxPush];   // local words written by the neighbours
+  unsigned int *signal[kMaxPush]; // words in the neighbours' memory written by this rank
+  int n_neigh;
+  int n_boundary;
+  unsigned int *state;
+  unsigned long long timeout_ns; // a wait that lasts longer sets state[2] and stops signalling (0 = wait for ever)
 };
 
 struct FixupArgs {
@@ -144,6 +171,7 @@ struct spmv_b200_plan {
 namespace b200 {
 
 // analysis.cu
+int analysis_gather_descs(const TileDesc *d_all, const int *h_order, int n, TileDesc **d_out, cudaStream_t stream);
 int analysis_prepare(spmv_b200_plan *p, cudaStream_t stream); // reads rowptr[0], rowptr[m]
 int analysis_run(spmv_b200_plan *p, cudaStream_t stream);
 int analysis_row_bins(const spmv_b200_plan *p, unsigned char *d_out, cudaStream_t stream);
@@ -163,5 +191,13 @@ int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const dou
 // tiles [tile_lo, tile_hi) only; the plan must have no split rows (their partial sums cross tile ranges)
 int kernels_launch_tiles(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y, int tile_lo,
                          int tile_hi, cudaStream_t stream, const PushArgs *push = nullptr);
+// fused halo loop: can the whole shard run as ONE launch with the flag protocol inside the kernel?
+bool kernels_halo_single_launch_ok(const spmv_b200_plan *p);
+// one iteration as one launch: `desc` lists every tile of the plan, boundary row blocks first (y = A*x, beta = 0)
+int kernels_launch_halo(const spmv_b200_plan *p, const TileDesc *desc, const double *x, double *y,
+                        const PushArgs *push, const HaloSync &sync, cudaStream_t stream);
+// the same protocol as separate one-CTA kernels (plans the single-launch kernel does not cover)
+int kernels_halo_wait(const HaloSync &sync, cudaStream_t stream);
+int kernels_halo_signal(const HaloSync &sync, cudaStream_t stream);
 
 } // namespace b200

@@ -322,6 +322,87 @@ __global__ void __launch_bounds__(kThreads) k_spmv_rows(const SpmvArgs a) {
   rows_tile<TMA, VEC, W, R, ROT>(a, sval, scol, srow, &bar, 0u, r0, r1 - r0, a0, e0, e1, tid);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused halo loop: the same row kernel with the ordering of neighbouring GPUs' iterations inside it
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(unsigned int *p, unsigned int v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// one thread: blocks until every neighbour's flag has reached the epoch; returns the epoch
+__device__ __forceinline__ unsigned int halo_wait(const HaloSync &h) {
+  const unsigned int k = ld_volatile_u32(h.state);
+  if (k == 0u)
+    return k;
+  const unsigned long long t0 = global_timer_ns();
+  for (int j = 0; j < h.n_neigh; ++j) {
+    while (ld_volatile_u32(h.wait[j]) < k) {
+      if (ld_volatile_u32(h.state + 2) != 0u)
+        return k; // another CTA has already given up
+      if (h.timeout_ns != 0ull && global_timer_ns() - t0 > h.timeout_ns) {
+        atomicCAS(h.state + 2, 0u, 0x80000000u | k); // sticky: the host reads it in spmv_b200_halo_loop_sync
+        return k;
+      }
+      __nanosleep(64);
+    }
+  }
+  __threadfence_system(); // the neighbours' pushed rows are ordered before their flag
+  return k;
+}
+
+// one thread, after all stores of the boundary row blocks: publish epoch + 1 to the neighbours (never after a timeout:
+// a rank that multiplied a stale halo must not hand its rows on as if they were good; its neighbours then time out too)
+__device__ __forceinline__ void halo_signal(const HaloSync &h, unsigned int k) {
+  __threadfence_system();
+  st_volatile_u32(h.state, k + 1u);
+  if (ld_volatile_u32(h.state + 2) == 0u)
+    for (int j = 0; j < h.n_neigh; ++j)
+      st_volatile_u32(h.signal[j], k + 1u);
+}
+
+template <bool VEC, int W, int R>
+__global__ void __launch_bounds__(kThreads) k_spmv_rows_halo(const SpmvArgs a, const HaloSync h) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ unsigned int s_epoch;
+  double *sval = reinterpret_cast<double *>(smem_raw);
+  int *scol = reinterpret_cast<int *>(sval + a.cap);
+  int *srow = scol + a.cap;
+
+  const int tid = threadIdx.x;
+  const TileDesc d = load_desc(a.desc, blockIdx.x);
+  const int a0 = d.e0 & ~3;
+  const bool boundary = (int)blockIdx.x < h.n_boundary;
+
+  tile_issue_loads<true>(a, a0, d.e0, d.e1, sval, scol, &bar, tid); // value / colindex do not depend on the halo
+  if (boundary && tid == 0)
+    s_epoch = halo_wait(h); // rows_tile starts with a CTA barrier, in front of the first gather of x
+  rows_tile<true, VEC, W, R>(a, sval, scol, srow, &bar, 0u, d.r0, d.r1 - d.r0, a0, d.e0, d.e1, tid);
+  if (boundary) {
+    __syncthreads(); // every row of this block has been stored (locally and into the neighbours' buffers)
+    if (tid == 0) {
+      __threadfence_system();
+      if (atomicAdd(h.state + 1, 1u) == (unsigned int)h.n_boundary - 1u) { // last boundary row block of the iteration
+        st_volatile_u32(h.state + 1, 0u);
+        halo_signal(h, s_epoch);
+      }
+    }
+  }
+}
+
+__global__ void k_halo_wait(const HaloSync h) { (void)halo_wait(h); }
+__global__ void k_halo_signal(const HaloSync h) { halo_signal(h, ld_volatile_u32(h.state)); }
+
 // Persistent form: gridDim.x CTAs walk the tile list with a two-stage ring of shared-memory tiles. The TMA copies
 // of tile i+1 are issued before tile i is processed, so the stream of value / colindex keeps flowing while the CTA
 // gathers x (the gather phase is bound by L1 wavefronts, the stream by HBM: the two overlap instead of alternating).
@@ -777,34 +858,51 @@ __global__ void __launch_bounds__(NT, 1536 / NT) k_spmv_seg(const SpmvArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Direct form: one warp per row block of 256 items, no shared memory (matrices whose x gathers do not coalesce)
+// Direct form: one warp per row block, no shared memory (matrices whose x gathers do not coalesce across rows)
 // ---------------------------------------------------------------------------------------------------------------
 // A gather in flight holds a 128-byte line of L1, and L1 is what the shared-memory carve-out leaves of the 256 KB
 // unified array: with tiles staged in shared memory the gather rate of an SM drops by 2-4x (profiles/, gather bound
-// against carve-out). Here value / colindex go straight into registers (each lane owns 4 consecutive elements: one
-// 128-bit load of colindex, two of value, fully used sectors), the products stay in registers, and rows are delimited
-// by the row-start bit flags of the analysis instead of row pointers:
-//   * a lane sums its 4 products up to the first row start ("head"), finishes the rows that begin and end inside its
-//     chunk on its own, and leaves the rest open;
-//   * a segmented warp scan (shuffles) gives every lane the open sum in front of it, which completes its head;
-//   * the row a finished sum belongs to is nz_rows[nzbase + ordinal of its row start]; the open sums at the two ends
-//     of a block are the fragments of rows split across blocks (partials -> k_fixup), or the block's last row.
+// against carve-out). Here value / colindex go straight into registers and rows are delimited by the row-start bit
+// flags of the analysis instead of row pointers.
+//
+// Element ownership is lane-contiguous: a warp walks its block in 128-element windows aligned to 32 elements, and
+// gather instruction j of a window serves elements 32j + lane. Consecutive lanes then gather for consecutive non-zeros,
+// which in a sorted row are neighbouring columns, so one instruction touches every 128-byte line of x once (with four
+// consecutive elements per lane the four gather instructions of a window each touched the lines of the whole window:
+// 456 M sectors for 268 M non-zeros on the R-MAT matrix). The 32 row-start flags of sub-window j are exactly one word of
+// the flag array, known to every lane, so the segmented sums need no flag shuffles:
+//   * every lane keeps an open sum `acc` of its own products since the last row start (no warp reduction per window:
+//     a window inside one long row costs four adds per lane);
+//   * a sub-window with row starts closes the open row (one butterfly over acc + the products in front of the first
+//     start), finishes the rows that begin and end inside it with a segmented scan whose predicate is a bit test on the
+//     flag word, and leaves the products behind the last start in acc;
+//   * the row a finished sum belongs to is nz_rows[nzbase + ordinal of its row start]; the open sums at the two ends of
+//     a block are the fragments of rows split across blocks (partials -> k_fixup), or the block's last row.
 // No barrier, no atomics; the order of every addition is fixed by the block geometry (bitwise reproducible).
 // Analogue of the reference's flat / merge-path kernels (src/acc/hip-flat/flat_imp_one_pass.hpp:15-77,
 // benchmark/merge-path/merge_path_reduction.h:80-136) without atomicAdd and without the per-element row search.
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// one 128-element window of colindex (4 lines) and value (8 lines) requested into L2 by lanes 0-11: no destination
-// register, so a warp can keep its streams several windows ahead of the window it is summing
-constexpr int kDirectPrefetchWindows = 4;
-__device__ __forceinline__ void prefetch_window(const SpmvArgs &a, int w0, int e1, int lane) {
-  if (w0 < e1) {
-    if (lane < 4)
-      prefetch_l2(a.col + w0 + 32 * lane);
-    else if (lane < 12)
-      prefetch_l2(a.val + w0 + 16 * (lane - 4));
-  }
+// loads of the direct kernel as volatile asm: issued in program order (see the element loop)
+__device__ __forceinline__ int ld_cs_s32(const int *p) {
+  int v;
+  asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_cs_f64(const double *p) {
+  double v;
+  asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_nc_f64(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned ld_nc_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
 }
 
 __device__ __forceinline__ void finish_row(const SpmvArgs &a, int row, double sum) {
@@ -812,180 +910,143 @@ __device__ __forceinline__ void finish_row(const SpmvArgs &a, int row, double su
   emit_y(a.y, a.push, row, a.alpha * sum + a.beta * yv);
 }
 
-// Q = 128-element windows a warp has in flight at a time: 2 (8 gathers per lane, 48 registers, 5 CTAs/SM) or 1 (4 gathers
-// per lane, fewer registers, more resident warps).
-template <bool VEC, int Q>
-__global__ void __launch_bounds__(kThreads, Q == 1 ? 8 : 5) k_spmv_warp(const SpmvArgs a) {
+// one 32-bit field of a tile descriptor, fetched again where it is needed (the asm keeps the compiler from merging the
+// load with the one at the top of the kernel and carrying the value in a register through the element loop)
+__device__ __forceinline__ int desc_field(const TileDesc *__restrict__ desc, int i, int field) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(reinterpret_cast<const int *>(desc + i) + field));
+  return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// MINB = resident CTAs per SM the register allocation aims for (8: 32 registers, 64 warps; 6: 40 registers, 48 warps)
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_spmv_warp(const SpmvArgs a) {
   const int lane = threadIdx.x & 31;
   const int ti = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (ti >= a.ntiles)
     return;
-  const TileDesc d = load_desc(a.desc, ti);
-  const int t = d.tile, r0 = d.r0, r1 = d.r1, e0 = d.e0, e1 = d.e1;
-  const int nzbase = d.head_end; // direct descriptors: non-empty rows in front of this block
-  const bool split_begin = (d.flags & 1) != 0, split_end = (d.flags & 2) != 0;
-  const long long arr_end = a.nnz;
-
-  // Everything a finished row needs later (its y, its id, the row pointers of the empty-row pass) is requested now,
-  // without a destination register, so that those dependent accesses hit L1 instead of adding round trips to the
-  // chain descriptor -> value/colindex/flags -> x gathers. One 128-byte line per lane and array (blocks own <= T rows).
-  if (a.stream_prefetch != 2) { // (tuning bit 25 switches this block off)
-    const int nrows = r1 - r0;
+  // Only e0 / e1 / nzbase stay in registers across the element loop; the other descriptor fields are needed once per
+  // block (its first row start, its end) and are fetched again there (an L1 hit) instead of occupying four registers.
+  int e0, e1, nzi; // nzi: index into nz_rows of the next row start (starts at the number of non-empty rows in front of
+                   // this block = field head_end of the direct descriptors)
+  {
+    const TileDesc d = load_desc(a.desc, ti);
+    e0 = d.e0, e1 = d.e1, nzi = d.head_end;
+    // Everything a finished row needs later (its y, its id, the row pointers of the empty-row pass) is requested now,
+    // without a destination register, so that those dependent accesses hit L1 instead of adding round trips to the
+    // chain descriptor -> value/colindex/flags -> x gathers. One 128-byte line per lane and array (blocks own <= T rows).
+    const int nrows = d.r1 - d.r0;
     for (int i = lane * 16; i < nrows; i += 32 * 16)
-      prefetch_l1(a.y + r0 + i);
+      prefetch_l1(a.y + d.r0 + i);
     for (int i = lane * 32; i <= nrows; i += 32 * 32) {
-      prefetch_l1(a.rowptr + r0 + i);
-      prefetch_l1(a.nz_rows + nzbase + i);
+      prefetch_l1(a.rowptr + d.r0 + i);
+      prefetch_l1(a.nz_rows + nzi + i);
     }
   }
 
-  double cv = 0.0; // open sum (since the last row start) in front of the current 128-element window
-  int nstart = 0;  // row starts met so far
-  if (a.stream_prefetch == 1) // tuning bit 24 (off by default, see launch_range)
-    for (int w = 0; w < kDirectPrefetchWindows; ++w)
-      prefetch_window(a, (e0 & ~3) + 128 * w, e1, lane);
-  for (int rb = e0 & ~3; rb < e1; rb += 128 * Q) {
-    if (a.stream_prefetch == 1)
-      for (int q = 0; q < Q; ++q)
-        prefetch_window(a, rb + 128 * (kDirectPrefetchWindows + q), e1, lane);
-    double p[Q][4];
-    unsigned nib[Q];
+  double acc = 0.0;     // this lane's products since the last row start
+  bool started = false; // a row start has been met
+  // flag words of the four sub-windows of a window: lane l fetches word (l & 3). Requested one window ahead, so that the
+  // load never sits behind the wait for the gathers in the instruction stream (the array is padded by a window).
+  unsigned wnext = ld_nc_u32(a.row_start_bits + ((e0 & ~31) >> 5) + (lane & 3));
+  for (int rb = e0 & ~31; rb < e1; rb += 128) {
+    // Issue order: flag word of the next window, colindex, x gathers, value. The column registers are dead once
+    // the gathers are issued, so the value loads reuse them: 16 data registers at the peak instead of 20. Elements of
+    // the neighbouring blocks (first / last window) are predicated off: (unsigned)(i - e0) < span <=> e0 <= i < e1.
+    const unsigned span = (unsigned)(e1 - e0);
+    const int i0 = rb + lane;
+    unsigned wq = wnext;
+    wnext = ld_nc_u32(a.row_start_bits + (rb >> 5) + 4 + (lane & 3));
+    double p[4], v[4];
     {
-      int c[Q][4];
-      double v[Q][4];
+      int c[4];
 #pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const int i0 = rb + 128 * q + 4 * lane;
-        nib[q] = 0u;
+      for (int j = 0; j < 4; ++j)
+        c[j] = (unsigned)(i0 + 32 * j - e0) < span ? ld_cs_s32(a.col + i0 + 32 * j) : -1;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          c[q][k] = -1;
-          v[q][k] = 0.0;
-        }
-        if (i0 < e1 && i0 + 4 > e0) { // the chunk intersects the block
-          const unsigned w = __ldg(a.row_start_bits + (i0 >> 5));
-          nib[q] = (w >> (i0 & 31)) & 0xfu;
-          if (VEC && (long long)i0 + 4 <= arr_end) {
-            const int4 cc = __ldcs(reinterpret_cast<const int4 *>(a.col + i0));
-            const double2 v01 = __ldcs(reinterpret_cast<const double2 *>(a.val + i0));
-            const double2 v23 = __ldcs(reinterpret_cast<const double2 *>(a.val + i0) + 1);
-            c[q][0] = cc.x, c[q][1] = cc.y, c[q][2] = cc.z, c[q][3] = cc.w;
-            v[q][0] = v01.x, v[q][1] = v01.y, v[q][2] = v23.x, v[q][3] = v23.y;
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if ((long long)i0 + k < arr_end) {
-                c[q][k] = __ldcs(a.col + i0 + k);
-                v[q][k] = __ldcs(a.val + i0 + k);
-              }
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (i0 + k < e0 || i0 + k >= e1) { // elements of the neighbouring blocks
-              c[q][k] = -1;
-              nib[q] &= ~(1u << k);
-            }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < Q; ++q)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          p[q][k] = c[q][k] >= 0 ? gather_x(a.x, c[q][k], a.gather_na) : 0.0;
-#pragma unroll
-      for (int q = 0; q < Q; ++q)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          p[q][k] *= v[q][k];
+      for (int j = 0; j < 4; ++j)
+        p[j] = c[j] >= 0 ? ld_nc_f64(a.x + c[j]) : 0.0;
     }
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      if (rb + 128 * q >= e1) // warp-uniform
-        break;
-      // ordinal of the first row start this lane meets = starts in earlier windows + starts in the lanes in front
-      int incl = __popc(nib[q]);
-      const bool any_start = __any_sync(0xffffffffu, nib[q] != 0u);
-      if (any_start) {
+    for (int j = 0; j < 4; ++j)
+      v[j] = (unsigned)(i0 + 32 * j - e0) < span ? ld_cs_f64(a.val + i0 + 32 * j) : 0.0;
+    // row starts of the neighbouring blocks do not count; a sub-window that has row starts broadcasts its word by shuffle
+    {
+      const int lo = e0 - (rb + 32 * (lane & 3)), hi = e1 - (rb + 32 * (lane & 3));
+      unsigned keep = hi <= 0 ? 0u : (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u));
+      if (lo > 0)
+        keep &= lo >= 32 ? 0u : ~((1u << lo) - 1u);
+      wq &= keep;
+    }
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const int o = __shfl_up_sync(0xffffffffu, incl, off);
-          if (lane >= off)
-            incl += o;
-        }
-      }
-      const int total = any_start ? __shfl_sync(0xffffffffu, incl, 31) : 0;
-      if (total == 0) { // the whole window lies inside one row (long rows): one warp sum, nothing to finish
-        double w = (p[q][0] + p[q][1]) + (p[q][2] + p[q][3]);
+    for (int j = 0; j < 4; ++j)
+      p[j] *= v[j];
+    if (!__any_sync(0xffffffffu, wq != 0u)) { // the whole window lies inside one row (long rows): four adds per lane
+      acc += (p[0] + p[1]) + (p[2] + p[3]);
+      continue;
+    }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-          w += __shfl_xor_sync(0xffffffffu, w, off);
-        cv += w;
+    for (int j = 0; j < 4; ++j) {
+      const unsigned wj = __shfl_sync(0xffffffffu, wq, j);
+      if (wj == 0u) { // warp-uniform
+        acc += p[j];
         continue;
       }
-      int s = nstart + incl - __popc(nib[q]);
-      const int sfirst = s;
-      bool f = false;
-      double head = 0.0, acc = 0.0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if ((nib[q] >> k) & 1u) { // a row starts here: the sum in front of it is complete
-          if (!f) {
-            f = true;
-            head = acc; // completed below, with the open sums of the lanes in front
-          } else {
-            finish_row(a, __ldg(a.nz_rows + nzbase + s - 1), acc);
-          }
-          acc = 0.0;
-          ++s;
-        }
-        acc += p[q][k];
-      }
-      // segmented inclusive scan of (f, open sum)
-      double v = acc;
-      int ff = f ? 1 : 0;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const double vv = __shfl_up_sync(0xffffffffu, v, off);
-        const int fo = __shfl_up_sync(0xffffffffu, ff, off);
-        if (lane >= off) {
-          if (!ff)
-            v = vv + v;
-          ff |= fo;
-        }
-      }
-      double ev = __shfl_up_sync(0xffffffffu, v, 1);
-      int ef = __shfl_up_sync(0xffffffffu, ff, 1);
+      // the open row ends in front of the first start of this sub-window
+      const int first = __ffs(wj) - 1;
+      const double open = warp_sum(acc + (lane < first ? p[j] : 0.0));
       if (lane == 0) {
-        ev = 0.0;
-        ef = 0;
+        if (started)
+          finish_row(a, __ldg(a.nz_rows + nzi - 1), open);
+        else if (desc_field(a.desc, ti, 7) & 1) // in front of the block's first row start: fragment of a split row
+          a.partials[2 * (size_t)desc_field(a.desc, ti, 6)] = open;
       }
-      if (f) {
-        const double tot = (ef ? ev : cv + ev) + head;
-        if (sfirst == 0) { // the sum in front of the block's first row start: fragment of a row that began earlier
-          if (split_begin)
-            a.partials[2 * (size_t)t] = tot;
-        } else {
-          finish_row(a, __ldg(a.nz_rows + nzbase + sfirst - 1), tot);
+      const int cnt = __popc(wj);
+      int last = first;
+      if (cnt > 1) {
+        // rows that begin and end inside the sub-window: segmented inclusive scan over the lanes; lane L takes the
+        // value of lane L - off iff no row starts in (L - off, L], which is a bit test on the flag word
+        double s = p[j];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const double o = __shfl_up_sync(0xffffffffu, s, off);
+          if (lane >= off && ((wj >> (lane - off + 1)) & ((1u << off) - 1u)) == 0u)
+            s += o;
         }
+        last = 31 - __clz(wj);
+        // a segment ends at lane L iff a row starts at L + 1; its ordinal is that of the last start at or below L
+        if (lane >= first && lane < last && ((wj >> (lane + 1)) & 1u))
+          finish_row(a, __ldg(a.nz_rows + nzi + __popc(wj & ((2u << lane) - 1u)) - 1), s);
       }
-      const double v31 = __shfl_sync(0xffffffffu, v, 31);
-      const int f31 = __shfl_sync(0xffffffffu, ff, 31);
-      cv = f31 ? v31 : cv + v31;
-      nstart += total;
+      acc = lane >= last ? p[j] : 0.0; // products behind the last start stay open
+      nzi += cnt;
+      started = true;
     }
   }
   // rows without elements only need the epilogue
-  for (int r = r0 + lane; r < r1; r += 32)
-    if (__ldg(a.rowptr + r) == __ldg(a.rowptr + r + 1))
-      finish_row(a, r, 0.0);
-  if (lane == 0) { // the open sum at the end of the block
-    if (nstart == 0) {
-      if (split_begin)
-        a.partials[2 * (size_t)t] = cv; // the whole block lies inside one row
-    } else if (split_end) {
-      a.partials[2 * (size_t)t + 1] = cv;
+  {
+    const int r1 = desc_field(a.desc, ti, 1);
+    for (int r = desc_field(a.desc, ti, 0) + lane; r < r1; r += 32)
+      if (__ldg(a.rowptr + r) == __ldg(a.rowptr + r + 1))
+        finish_row(a, r, 0.0);
+  }
+  const double open = warp_sum(acc); // the open sum at the end of the block
+  if (lane == 0) {
+    const int t = desc_field(a.desc, ti, 6), flags = desc_field(a.desc, ti, 7);
+    if (!started) {
+      if (flags & 1)
+        a.partials[2 * (size_t)t] = open; // the whole block lies inside one row
+    } else if (flags & 2) {
+      a.partials[2 * (size_t)t + 1] = open;
     } else {
-      finish_row(a, __ldg(a.nz_rows + nzbase + nstart - 1), cv);
+      finish_row(a, __ldg(a.nz_rows + nzi - 1), open);
     }
   }
 }
@@ -1139,10 +1200,19 @@ int kernels_configure(spmv_b200_plan *p) {
   }
   int rc;
   const RowsVariant &vs = kShortVariants[p->variant_short], &vm = kMediumVariants[p->variant_medium];
+  const bool persistent = (p->flags & SPMV_B200_FLAG_PERSISTENT) != 0;
+  // every kernel that may be launched must fit the opt-in shared-memory limit of the device: say so here, in words,
+  // instead of letting cudaFuncSetAttribute fail with an opaque error
+  for (int k = 0; k < 3; ++k) {
+    const size_t need = smem_for(p, k, persistent && k != SPMV_B200_KIND_MIXED);
+    if (need > (size_t)max_optin) {
+      set_error("tile_nnz too large for the shared memory of this device" +
+                std::string(persistent ? " (the persistent kernels keep two tiles per CTA)" : ""));
+      return SPMV_B200_ERR_ARG;
+    }
+  }
   if ((rc = set_smem(vs.tma, smem_for(p, SPMV_B200_KIND_SHORT))) ||
       (rc = set_smem(vs.plain, smem_for(p, SPMV_B200_KIND_SHORT))) ||
-      (rc = set_smem(vs.persistent, smem_for(p, SPMV_B200_KIND_SHORT, true))) ||
-      (rc = set_smem(vm.persistent, smem_for(p, SPMV_B200_KIND_MEDIUM, true))) ||
       (rc = set_smem(vm.tma, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
       (rc = set_smem(vm.plain, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
       (rc = set_smem(kMediumVariantsRot[p->variant_medium].tma, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
@@ -1150,21 +1220,25 @@ int kernels_configure(spmv_b200_plan *p) {
       (rc = set_smem(mixed_kernel(true, p->mixed_threads, p->mixed_queue_form), smem_for(p, SPMV_B200_KIND_MIXED))) ||
       (rc = set_smem(mixed_kernel(false, p->mixed_threads, p->mixed_queue_form), smem_for(p, SPMV_B200_KIND_MIXED))))
     return rc;
-  // persistent kernels: one wave of CTAs, as many as fit on the device
-  int sms = 0;
-  B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  int occ_s = 0, occ_m = 0;
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, vs.persistent, kThreads,
-                                                          smem_for(p, SPMV_B200_KIND_SHORT, true)));
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_m, vm.persistent, kThreads,
-                                                          smem_for(p, SPMV_B200_KIND_MEDIUM, true)));
-  p->persistent_grid[SPMV_B200_KIND_SHORT] = sms * (occ_s > 0 ? occ_s : 1);
-  p->persistent_grid[SPMV_B200_KIND_MEDIUM] = sms * (occ_m > 0 ? occ_m : 1);
-  if (const char *env = getenv("SPMV_B200_PERSIST_CTAS")) { // development knob: CTAs per SM of the persistent kernels
-    const int c = atoi(env);
-    if (c > 0) {
-      p->persistent_grid[SPMV_B200_KIND_SHORT] = sms * (c < occ_s ? c : occ_s);
-      p->persistent_grid[SPMV_B200_KIND_MEDIUM] = sms * (c < occ_m ? c : occ_m);
+  if (persistent) { // one wave of CTAs, as many as fit on the device
+    if ((rc = set_smem(vs.persistent, smem_for(p, SPMV_B200_KIND_SHORT, true))) ||
+        (rc = set_smem(vm.persistent, smem_for(p, SPMV_B200_KIND_MEDIUM, true))))
+      return rc;
+    int sms = 0;
+    B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int occ_s = 0, occ_m = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, vs.persistent, kThreads,
+                                                            smem_for(p, SPMV_B200_KIND_SHORT, true)));
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_m, vm.persistent, kThreads,
+                                                            smem_for(p, SPMV_B200_KIND_MEDIUM, true)));
+    p->persistent_grid[SPMV_B200_KIND_SHORT] = sms * (occ_s > 0 ? occ_s : 1);
+    p->persistent_grid[SPMV_B200_KIND_MEDIUM] = sms * (occ_m > 0 ? occ_m : 1);
+    if (const char *env = getenv("SPMV_B200_PERSIST_CTAS")) { // development knob: CTAs per SM of the persistent kernels
+      const int c = atoi(env);
+      if (c > 0) {
+        p->persistent_grid[SPMV_B200_KIND_SHORT] = sms * (c < occ_s ? c : occ_s);
+        p->persistent_grid[SPMV_B200_KIND_MEDIUM] = sms * (c < occ_m ? c : occ_m);
+      }
     }
   }
   return SPMV_B200_OK;
@@ -1230,13 +1304,10 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
   else
     a.push.count = 0;
 
-  // measured on C4: 1.42 ms with the L2 stream prefetch against 1.34 ms without (more LSU requests, no latency won:
-  // 64 resident warps already cover it); off unless tuning bit 24 is set
   // slot rotation of the MEDIUM kernel: only where gathers do not coalesce across rows anyway (C3: 1.836 ms against
   // 1.882 ms); on a stencil it breaks the coalescing of neighbouring rows (C5s: 1.08 ms against 0.97 ms). Tuning bit 26
   // switches it off.
   a.rotate_slots = (p->irregular && !((p->flags >> 26) & 1u)) ? 1 : 0;
-  a.stream_prefetch = ((p->flags >> 24) & 1u) ? 1 : (((p->flags >> 25) & 1u) ? 2 : 0);
   a.row_start_bits = p->row_start_bits;
   a.nz_rows = p->nz_rows;
   const bool tma = p->uses_tma;
@@ -1249,12 +1320,8 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
       a.ntiles = hi - lo;
       a.cap = 0;
       const int wpc = kThreads / 32;
-      // uses_tma == value / colindex are 16-byte aligned (and vector loads were not disabled with NO_TMA)
-      // one 128-element window in flight per warp (32 registers, 64 resident warps per SM): C4 1.33 ms against 1.42 ms
-      // with two windows (48 registers, 40 warps); tuning bit 23 selects the two-window kernel
-      const bool q1 = ((p->flags >> 23) & 1u) == 0;
-      RowsKernel kw = q1 ? (tma ? k_spmv_warp<true, 1> : k_spmv_warp<false, 1>)
-                         : (tma ? k_spmv_warp<true, 2> : k_spmv_warp<false, 2>);
+      // tuning bit 23: register allocation for 6 resident CTAs per SM instead of 8
+      RowsKernel kw = ((p->flags >> 23) & 1u) ? k_spmv_warp<6> : k_spmv_warp<8>;
       B200_CUDA(launch_spmv(kw, (a.ntiles + wpc - 1) / wpc, 0, stream, a, p));
     }
   }
@@ -1299,6 +1366,79 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
     const int warps_per_cta = kThreads / 32;
     k_fixup<<<(p->nsplit + warps_per_cta - 1) / warps_per_cta, kThreads, 0, stream>>>(f);
   }
+  B200_CUDA(cudaGetLastError());
+  return SPMV_B200_OK;
+}
+
+// ---- fused halo loop ----
+typedef void (*HaloKernel)(const SpmvArgs, const HaloSync);
+static HaloKernel halo_kernel(const spmv_b200_plan *p, int *kind) {
+  if (!p->uses_tma || p->direct || p->nsplit > 0 || p->ntiles == 0 || (p->flags & SPMV_B200_FLAG_PERSISTENT))
+    return nullptr;
+  if (p->count[SPMV_B200_KIND_SHORT] == p->ntiles) {
+    *kind = SPMV_B200_KIND_SHORT;
+    if (p->variant_short == 0)
+      return k_spmv_rows_halo<false, 6, 1>;
+    if (p->variant_short == 1)
+      return k_spmv_rows_halo<false, 8, 1>;
+  } else if (p->count[SPMV_B200_KIND_MEDIUM] == p->ntiles && !p->irregular) {
+    *kind = SPMV_B200_KIND_MEDIUM;
+    if (p->variant_medium == 0)
+      return k_spmv_rows_halo<true, 8, 1>;
+  }
+  return nullptr;
+}
+
+// true if the plan is covered by the single-launch kernel; raises its dynamic shared-memory limit (once, here: the
+// launches themselves may be recorded by a stream capture, where attribute calls do not belong)
+bool kernels_halo_single_launch_ok(const spmv_b200_plan *p) {
+  int kind = 0;
+  HaloKernel k = halo_kernel(p, &kind);
+  return k != nullptr && set_smem(k, smem_for(p, kind)) == SPMV_B200_OK;
+}
+
+int kernels_launch_halo(const spmv_b200_plan *p, const TileDesc *desc, const double *x, double *y,
+                        const PushArgs *push, const HaloSync &sync, cudaStream_t stream) {
+  int kind = 0;
+  HaloKernel k = halo_kernel(p, &kind);
+  if (!k) {
+    set_error("kernels_launch_halo: plan not covered by the single-launch kernel");
+    return SPMV_B200_ERR_UNSUPPORTED;
+  }
+  SpmvArgs a = {};
+  a.rowptr = p->rowptr;
+  a.col = p->col;
+  a.val = p->val;
+  a.x = x;
+  a.y = y;
+  a.alpha = 1.0;
+  a.beta = 0.0;
+  a.desc = desc;
+  a.partials = nullptr;
+  a.nnz = p->elem_end;
+  a.ntiles = p->ntiles;
+  a.cap = cap_for(p, kind);
+  a.vec_div = p->vec_div;
+  a.read_y = 0; // y is a slice of the next x: never read (SPMV_B200_FLAG_BETA0_SKIP_Y semantics)
+  a.gather_na = (p->flags & SPMV_B200_FLAG_GATHER_NO_L1) ? 1 : 0;
+  a.rotate_slots = 0;
+  if (push)
+    a.push = *push;
+  else
+    a.push.count = 0;
+  k<<<p->ntiles, kThreads, smem_for(p, kind), stream>>>(a, sync);
+  B200_CUDA(cudaGetLastError());
+  return SPMV_B200_OK;
+}
+
+int kernels_halo_wait(const HaloSync &sync, cudaStream_t stream) {
+  k_halo_wait<<<1, 1, 0, stream>>>(sync);
+  B200_CUDA(cudaGetLastError());
+  return SPMV_B200_OK;
+}
+
+int kernels_halo_signal(const HaloSync &sync, cudaStream_t stream) {
+  k_halo_signal<<<1, 1, 0, stream>>>(sync);
   B200_CUDA(cudaGetLastError());
   return SPMV_B200_OK;
 }

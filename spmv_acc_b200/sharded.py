@@ -6,8 +6,10 @@ against oracle/analysis_port.c:port_shard_bounds). x is replicated; a one-shot S
 
 In an iterated loop (x <- A*x) every rank writes its y shard straight into its slice of the next x and the slices are
 exchanged:
-  * ``allgather`` — every slice goes to every rank (NCCL broadcasts of the unequal slices = all-gather-v). This is the
-    exchange BASELINE.json names; it moves 8*n*(G-1)/G bytes into every GPU per iteration.
+  * ``allgather`` — every slice goes to every rank: ONE grouped NCCL collective per iteration (ncclAllGather in place
+    when the slices have equal length, otherwise one ncclGroup of broadcasts of the unequal slices = all-gather-v) on a
+    communication stream, overlapped with the row blocks that only read this rank's own columns. This is the exchange
+    BASELINE.json names; it moves 8*n*(G-1)/G bytes into every GPU per iteration.
   * ``halo``      — only the 4096-entry blocks of x that a rank's columns actually reference are sent to it
     (grouped NCCL send/recv). The needed blocks come from the analysis (``spmv_b200_col_block_bitmap``) and are
     exchanged once at set-up. For a z-slab sharded 27-point stencil that is one xy-plane per neighbour instead of the
@@ -53,6 +55,12 @@ def merge_runs(blocks: np.ndarray, lo: int, hi: int, shift: int = BLOCK_SHIFT) -
     return runs
 
 
+def _ranges(marks: np.ndarray) -> List[Tuple[int, int]]:
+    """Maximal runs [a, b) of True in a boolean array."""
+    edges = np.flatnonzero(np.diff(np.concatenate(([False], np.asarray(marks, dtype=bool), [False])).astype(np.int8)))
+    return [(int(edges[i]), int(edges[i + 1])) for i in range(0, edges.size, 2)]
+
+
 def exchange_schedule(need: np.ndarray, bounds: np.ndarray, rank: int, shift: int = BLOCK_SHIFT):
     """need[q, b] = 1 if rank q references block b of x. Returns (sends, recvs): lists of (peer, start, end) element
     ranges of x, ordered by (peer, start) on both sides so that matching send/recv pairs line up."""
@@ -74,6 +82,39 @@ def exchange_schedule(need: np.ndarray, bounds: np.ndarray, rank: int, shift: in
             for a, e in merge_runs(blk[need[rank, blk] != 0], lo, hi, shift):
                 recvs.append((p, a, e))
     return sends, recvs
+
+
+def split_boundary_interior(sends, tile_row, tile_reads_halo, lo: int):
+    """(boundary, interior) tile ranges of a shard for the halo exchange, or None if most of the shard is boundary.
+    Boundary = row blocks that produce a row another rank receives, plus (when known) every row block that reads an
+    entry of x owned by another rank: once the boundary blocks of an iteration are done, this rank neither owes anybody
+    a row of that iteration nor reads a halo entry of it, which is what lets a neighbour overwrite the halo early
+    (fused push) while the interior is still being multiplied."""
+    tr = np.asarray(tile_row, dtype=np.int64)
+    nt = tr.size - 1
+    if nt <= 0:
+        return None
+    marks = np.zeros(nt, dtype=bool)
+    for _, a, e in sends:
+        t0 = int(np.searchsorted(tr, a - lo, side="right")) - 1
+        t1 = int(np.searchsorted(tr, e - lo, side="left"))
+        marks[max(t0, 0):min(t1, nt)] = True
+    if tile_reads_halo is not None:
+        marks |= np.asarray(tile_reads_halo, dtype=bool)[:nt]
+    if marks.sum() * 2 > nt:
+        return None  # nothing to hide the exchange behind
+    return _ranges(marks), _ranges(~marks)
+
+
+def split_by_remote_reads(tile_row, tile_reads_halo):
+    """(readers of remote columns, the rest) as tile ranges, or None if most row blocks read remote columns."""
+    if tile_reads_halo is None:
+        return None
+    nt = np.asarray(tile_row).size - 1
+    marks = np.asarray(tile_reads_halo, dtype=bool)[:nt]
+    if nt <= 0 or marks.sum() * 2 > nt:
+        return None
+    return _ranges(marks), _ranges(~marks)
 
 
 @dataclass
@@ -98,6 +139,7 @@ class PowerLoop:
     recvs: list = field(default_factory=list)
     mode: str = ""
     bytes_in_per_iter: int = 0
+    _ag_native: Optional[bool] = None  # None: not tried yet; False: the backend refused, use broadcasts
 
     def __post_init__(self):
         import torch
@@ -122,44 +164,55 @@ class PowerLoop:
         self._plan_overlap()
 
     def _plan_overlap(self):
-        """Row blocks that produce rows another rank needs are computed first; their exchange then runs on a second
-        stream while the rest of the shard is multiplied."""
+        """halo: row blocks that produce rows another rank needs are computed first; their exchange then runs on a
+        second stream while the rest of the shard is multiplied. allgather: the collective of x runs while the row
+        blocks that read only this rank's own columns are multiplied; the others follow."""
         self.overlapped = False
-        if not (self.overlap and self.mode == "halo" and self.spmv_tiles is not None and self.tile_row is not None):
+        if not (self.overlap and self.spmv_tiles is not None and self.tile_row is not None):
             return
-        tr = np.asarray(self.tile_row, dtype=np.int64)
-        nt = tr.size - 1
-        lo = int(self.bounds[self.rank])
-        marks = np.zeros(nt, dtype=bool)
-        for _, a, e in self.sends:
-            t0 = int(np.searchsorted(tr, a - lo, side="right")) - 1
-            t1 = int(np.searchsorted(tr, e - lo, side="left"))
-            marks[max(t0, 0):min(t1, nt)] = True
-        # Row blocks that read entries owned by other ranks count as boundary too: once the boundary blocks of an
-        # iteration are done, this rank neither owes anybody a row of that iteration nor reads a halo entry of it, which is
-        # what lets a neighbour overwrite the halo early (fused push) while the interior is still being multiplied.
-        self.boundary_reads_all_halo = self.tile_reads_halo is not None
-        if self.tile_reads_halo is not None:
-            marks |= np.asarray(self.tile_reads_halo, dtype=bool)[:nt]
-        if nt == 0 or marks.sum() * 2 > nt:
-            return  # most of the shard is boundary: nothing to hide the exchange behind
-        edges = np.flatnonzero(np.diff(np.concatenate(([False], marks, [False])).astype(np.int8)))
-        self.boundary = [(int(edges[i]), int(edges[i + 1])) for i in range(0, edges.size, 2)]
-        inv = ~marks
-        edges = np.flatnonzero(np.diff(np.concatenate(([False], inv, [False])).astype(np.int8)))
-        self.interior = [(int(edges[i]), int(edges[i + 1])) for i in range(0, edges.size, 2)]
+        if self.mode == "allgather":
+            split = split_by_remote_reads(self.tile_row, self.tile_reads_halo)
+        elif self.mode == "halo":
+            self.boundary_reads_all_halo = self.tile_reads_halo is not None
+            split = split_boundary_interior(self.sends, self.tile_row, self.tile_reads_halo,
+                                            int(self.bounds[self.rank]))
+        else:
+            split = None
+        if split is None:
+            return
+        self.boundary, self.interior = split
         self.overlapped = True
         if self.x.is_cuda:
             import torch
             self.comm_stream = torch.cuda.Stream()
 
+    def _allgather(self, v):
+        """Every rank's slice of v to every rank, one collective."""
+        dist = _dist()
+        sizes = np.diff(self.bounds)
+        lo, hi = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+        if self._ag_native is not False and v.is_cuda:
+            try:
+                if np.all(sizes == sizes[0]):
+                    dist.all_gather_into_tensor(v, v[lo:hi])  # in place: ncclAllGather, no staging copy
+                else:
+                    # unequal slices: ProcessGroupNCCL turns this into ONE ncclGroup of broadcasts (all-gather-v)
+                    dist.all_gather([v[int(self.bounds[g]):int(self.bounds[g + 1])] for g in range(self.world)], v[lo:hi])
+                self._ag_native = True
+                return
+            except Exception:
+                if self._ag_native is True:
+                    raise
+                self._ag_native = False  # backend without unequal all_gather: broadcasts below
+        for src in range(self.world):
+            a, e = int(self.bounds[src]), int(self.bounds[src + 1])
+            if e > a:
+                dist.broadcast(v[a:e], src)
+
     def _exchange(self, v):
         dist = _dist()
         if self.mode == "allgather":
-            for src in range(self.world):
-                lo, hi = int(self.bounds[src]), int(self.bounds[src + 1])
-                if hi > lo:
-                    dist.broadcast(v[lo:hi], src)
+            self._allgather(v)
         elif self.mode == "halo":
             ops = [dist.P2POp(dist.isend, v[a:e], p) for p, a, e in self.sends]
             ops += [dist.P2POp(dist.irecv, v[a:e], p) for p, a, e in self.recvs]
@@ -169,8 +222,26 @@ class PowerLoop:
 
     def step(self):
         lo, hi = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
-        if self.world > 1 and getattr(self, "overlapped", False):
-            ys = self.x_next[lo:hi]
+        ys = self.x_next[lo:hi]
+        if self.world > 1 and self.mode == "allgather":
+            # Invariant between steps: this rank's own slice of x is final, the other slices are one step old. The
+            # collective that refreshes them runs next to the row blocks that do not read them.
+            if getattr(self, "overlapped", False) and self.x.is_cuda:
+                import torch
+                cur = torch.cuda.current_stream()
+                self.comm_stream.wait_event(cur.record_event())
+                with torch.cuda.stream(self.comm_stream):
+                    self._allgather(self.x)
+                    done = self.comm_stream.record_event()
+                for t0, t1 in self.interior:
+                    self.spmv_tiles(self.x, ys, t0, t1)
+                cur.wait_event(done)
+                for t0, t1 in self.boundary:
+                    self.spmv_tiles(self.x, ys, t0, t1)
+            else:
+                self._allgather(self.x)
+                self.spmv(self.x, ys)
+        elif self.world > 1 and getattr(self, "overlapped", False):
             for t0, t1 in self.boundary:
                 self.spmv_tiles(self.x, ys, t0, t1)
             if self.x.is_cuda:
@@ -188,15 +259,21 @@ class PowerLoop:
                 for t0, t1 in self.interior:
                     self.spmv_tiles(self.x, ys, t0, t1)
         else:
-            self.spmv(self.x, self.x_next[lo:hi])
+            self.spmv(self.x, ys)
             if self.world > 1:
                 self._exchange(self.x_next)
         self.x, self.x_next = self.x_next, self.x
 
-    def run(self, iters: int):
+    def finish(self):
+        """Makes every slice of x current (allgather mode leaves the other ranks' slices one step behind)."""
+        if self.world > 1 and self.mode == "allgather":
+            self._allgather(self.x)
+        return self.x
+
+    def run(self, iters: int, finish: bool = True):
         for _ in range(iters):
             self.step()
-        return self.x
+        return self.finish() if finish else self.x
 
     def capture(self):
         """Captures two iterations (one ping-pong period of the x buffers) into a CUDA graph: the kernels, the grouped
@@ -224,26 +301,54 @@ class PowerLoop:
         return self.x
 
 
-class FusedHaloLoop:
-    """x <- A*x with the halo exchange fused into the SpMV kernels: the epilogue of the kernels stores the rows a
-    neighbour references straight into that neighbour's copy of the next x (peer memory mapped through CUDA IPC,
-    NVLink stores), and iterations of neighbouring GPUs are ordered with stream-ordered flags
-    (cuStreamWriteValue32 / cuStreamWaitValue32) instead of a collective: one kernel launch per iteration, no NCCL
-    kernel, no host synchronisation. Double buffering: iteration k reads buf[k % 2] and writes buf[(k+1) % 2] here
-    and in the neighbours; a rank starts iteration k only after every neighbour has raised its flag to k, which means
-    the neighbour's rows for x_k have arrived and the neighbour no longer reads the buffer about to be overwritten."""
+def make_halo_desc(plan, buf_ptrs, lo: int, hi: int, wait_flags: list, signal_flags: list, push: list,
+                   boundary: list, interior: list, flags: int = 0):
+    """Fills a ``spmv_b200_halo_loop_desc``. push[b] = [(row_lo, row_hi, dst_address)] for destination buffer parity b
+    (dst already offset so that it is indexed by the shard-local row)."""
+    from . import _lib
+    if len(wait_flags) > _lib.MAX_PUSH or max(len(push[0]), len(push[1])) > _lib.MAX_PUSH:
+        raise RuntimeError("too many neighbours / push ranges for the fused halo exchange")
+    if max(len(boundary), len(interior)) > _lib.MAX_RANGES:
+        raise RuntimeError("too many row-block ranges for the fused halo exchange")
+    d = _lib.HaloLoopDesc()
+    d.plan = plan._h
+    d.buf[0], d.buf[1] = int(buf_ptrs[0]), int(buf_ptrs[1])
+    d.row_lo, d.row_hi = int(lo), int(hi)
+    d.n_neigh = len(wait_flags)
+    for j, (w, g) in enumerate(zip(wait_flags, signal_flags)):
+        d.wait_flags[j], d.signal_flags[j] = int(w), int(g)
+    for b in (0, 1):
+        d.push[b].count = len(push[b])
+        for j, (rl, rh, dst) in enumerate(push[b]):
+            d.push[b].row_lo[j], d.push[b].row_hi[j], d.push[b].dst[j] = int(rl), int(rh), int(dst)
+    d.n_boundary, d.n_interior = len(boundary), len(interior)
+    for j, (t0, t1) in enumerate(boundary):
+        d.boundary[2 * j], d.boundary[2 * j + 1] = int(t0), int(t1)
+    for j, (t0, t1) in enumerate(interior):
+        d.interior[2 * j], d.interior[2 * j + 1] = int(t0), int(t1)
+    d.flags = int(flags)
+    return d
 
-    def __init__(self, base: PowerLoop, plan):
+
+class FusedHaloLoop:
+    """x <- A*x with the halo exchange fused into the SpMV kernels (``spmv_b200_halo_loop_*``): the epilogue of the
+    kernels stores the rows a neighbour references straight into that neighbour's copy of the next x (peer memory
+    mapped through CUDA IPC, NVLink stores), and iterations of neighbouring GPUs are ordered with flags in each other's
+    memory that the boundary row blocks of the SpMV kernel itself wait for and raise: one kernel launch per iteration,
+    replayed from a CUDA graph, no NCCL kernel, no host synchronisation. Double buffering: iteration k reads
+    buf[k % 2] and writes buf[(k+1) % 2] here and in the neighbours; the boundary row blocks of iteration k start only
+    after every neighbour has raised its flag to k, which means the neighbour's rows for x_k have arrived and the
+    neighbour no longer reads the buffer about to be overwritten."""
+
+    def __init__(self, base: PowerLoop, plan, flags: int = 0):
         import torch
-        from . import PeerBuffer
+        from . import HaloLoop, PeerBuffer
         dist = _dist()
         assert base.world > 1 and base.x.is_cuda
         self.base, self.plan = base, plan
         self.rank, self.world = base.rank, base.world
         self.lo, self.hi = int(base.bounds[self.rank]), int(base.bounds[self.rank + 1])
         self.neigh = sorted({p for p, _, _ in base.sends} | {p for p, _, _ in base.recvs})
-        if len(base.sends) > _lib_max_push():
-            raise RuntimeError("too many push ranges for the fused halo exchange")
         # one exported allocation per rank: [x buffer 0 | x buffer 1 | flags], opened by the neighbours with THEIR
         # device current (that is what maps it for their kernels; a torch-IPC tensor is mapped for the owner's device)
         n = base.n
@@ -257,96 +362,48 @@ class FusedHaloLoop:
         dist.all_gather_object(everyone, (self.own.handle, self.own.nbytes))
         self.peer = {p: PeerBuffer.open(*everyone[p]) for p in self.neigh}
         # push descriptors for both buffer parities: destination = neighbour's buffer, indexed by my local row
-        self.push = [[(a - self.lo, e - self.lo, self.peer[p].address + b * self.xbytes + 8 * self.lo)
-                      for p, a, e in base.sends] for b in (0, 1)]
-        self.k = 0
+        push = [[(a - self.lo, e - self.lo, self.peer[p].address + b * self.xbytes + 8 * self.lo)
+                 for p, a, e in base.sends] for b in (0, 1)]
         # boundary-first schedule only if the boundary blocks are known to contain every reader of halo entries
         self.split = bool(getattr(base, "overlapped", False) and getattr(base, "boundary_reads_all_halo", False))
-        self.desc = self._native_desc()
+        desc = make_halo_desc(
+            plan, [self.bufs[0].data_ptr(), self.bufs[1].data_ptr()], self.lo, self.hi,
+            [self.flags.data_ptr() + 4 * p for p in self.neigh],
+            [self.peer[p].address + 2 * self.xbytes + 4 * self.rank for p in self.neigh], push,
+            base.boundary if self.split else [], base.interior if self.split else [], flags)
+        self.loop = HaloLoop(desc)
+        self.k = 0
         dist.barrier()
 
-    def _native_desc(self):
-        """Descriptor of spmv_b200_halo_loop_run: the whole loop is then enqueued by the C library, one call per run."""
-        from . import _lib
-        if len(self.neigh) > _lib.MAX_PUSH:
-            return None
-        if self.split and max(len(self.base.boundary), len(self.base.interior)) > _lib.MAX_RANGES:
-            return None
-        d = _lib.HaloLoopDesc()
-        d.plan = self.plan._h
-        d.buf[0], d.buf[1] = self.bufs[0].data_ptr(), self.bufs[1].data_ptr()
-        d.row_lo, d.row_hi = self.lo, self.hi
-        d.n_neigh = len(self.neigh)
-        for j, p in enumerate(self.neigh):
-            d.wait_flags[j] = self.flags.data_ptr() + 4 * p
-            d.signal_flags[j] = self.peer[p].address + 2 * self.xbytes + 4 * self.rank
-        for b in (0, 1):
-            d.push[b].count = len(self.push[b])
-            for j, (lo, hi, dst) in enumerate(self.push[b]):
-                d.push[b].row_lo[j], d.push[b].row_hi[j], d.push[b].dst[j] = int(lo), int(hi), int(dst)
-        if self.split:
-            d.n_boundary, d.n_interior = len(self.base.boundary), len(self.base.interior)
-            for j, (t0, t1) in enumerate(self.base.boundary):
-                d.boundary[2 * j], d.boundary[2 * j + 1] = t0, t1
-            for j, (t0, t1) in enumerate(self.base.interior):
-                d.interior[2 * j], d.interior[2 * j + 1] = t0, t1
-        return d
-
     def close(self):
-        import torch
-        torch.cuda.synchronize()
+        """Waits for the enqueued iterations (raises if a neighbour's flag timed out) and releases the mappings."""
+        err = None
+        try:
+            self.loop.sync()
+        except Exception as e:  # keep going: the peers must still be released collectively
+            err = e
         _dist().barrier()
+        self.loop.destroy()
         for pb in self.peer.values():
             pb.release()
         self.peer = {}
         _dist().barrier()
         self.bufs, self.flags = [], None
         self.own.release()
+        if err is not None:
+            raise err
 
-    def step(self):
-        from . import stream_wait_flag, stream_write_flags
-        k = self.k
-        if k > 0:
-            for p in self.neigh:  # neighbour p has pushed its rows of x_k and no longer reads the halo of x_(k-1)
-                stream_wait_flag(self.flags.data_ptr() + 4 * p, k)
-        src, dst = self.bufs[k % 2], self.bufs[(k + 1) % 2]
-        ys, push = dst[self.lo:self.hi], self.push[(k + 1) % 2]
-        flags = [self.peer[p].address + 2 * self.xbytes + 4 * self.rank for p in self.neigh]
-        if self.split:
-            # boundary row blocks first (they produce every pushed row and are the only readers of halo entries), then
-            # the flags, then the interior: the neighbours get their go-ahead a few percent into the iteration
-            for t0, t1 in self.base.boundary:
-                self.plan.execute_tiles_push(1.0, 0.0, src, ys, t0, t1, push)
-            stream_write_flags(flags, k + 1)
-            for t0, t1 in self.base.interior:
-                self.plan.execute_tiles(1.0, 0.0, src, ys, t0, t1)
-        else:
-            self.plan.execute_push(1.0, 0.0, src, ys, push)
-            stream_write_flags(flags, k + 1)
-        self.k = k + 1
-
-    def run(self, iters: int, native: bool = True):
-        if native and self.desc is not None:
-            import ctypes as C
-            import torch
-            from . import _lib
-            _lib.check(_lib.lib().spmv_b200_halo_loop_run(C.byref(self.desc), self.k, int(iters),
-                                                          int(torch.cuda.current_stream().cuda_stream)),
-                       "halo_loop_run")
-            self.k += int(iters)
-            return self.x
-        for _ in range(iters):
-            self.step()
+    def run(self, iters: int):
+        self.loop.run(int(iters))
+        self.k += int(iters)
         return self.x
+
+    def sync(self):
+        self.loop.sync()
 
     @property
     def x(self):
         return self.bufs[self.k % 2]
-
-
-def _lib_max_push() -> int:
-    from . import _lib
-    return _lib.MAX_PUSH
 
 
 def bits_checksum(t) -> int:
@@ -355,28 +412,75 @@ def bits_checksum(t) -> int:
     return int(t.view(torch.int64).sum().item())
 
 
-def build_stencil3d_power_loop(N: int, exchange: str = "auto", options=None, overlap: bool = True):
-    """Rank-local pieces of the C5 configuration: 27-point averaging stencil on an N^3 grid, rows sharded by nnz."""
+@dataclass
+class Shard:
+    """This rank's rows of an iterated configuration: matrix, plan and what the exchange schedules need."""
+    name: str
+    n: int
+    bounds: np.ndarray
+    csr: "object"
+    plan: "object"
+    need: np.ndarray
+    tile_row: Optional[np.ndarray]
+    reads_halo: Optional[np.ndarray]
+    nnz_total: int = 0
+
+    def destroy(self):
+        self.plan.destroy()
+
+
+def build_shard(kind: str = "stencil3d", N: int = 384, m: int = 0, k: int = 32, options=None) -> Shard:
+    """kind = "stencil3d": 27-point averaging stencil on an N^3 grid (config C5); kind = "uniform": m x m matrix with k
+    uniformly random columns per row, values scaled by 1/k (C3-shaped; every rank needs all of x). Rows are sharded
+    by nnz (``spmv_b200_shard_bounds``); each rank generates only its own rows."""
     import torch
     from . import CsrDesc, SpmvPlan, col_block_bitmap, make_options, shard_bounds, synth, FLAG_BETA0_SKIP_Y
     rank, world = world_info()
-    n = N ** 3
-    if world == 1:
-        bounds = np.array([0, n], dtype=np.int64)
+    if kind == "stencil3d":
+        n = N ** 3
+        if world == 1:
+            bounds = np.array([0, n], dtype=np.int64)
+        else:
+            counts = synth.stencil_row_counts_device("stencil3d", N)
+            rowptr = synth._rowptr_from_counts_device(counts)
+            del counts
+            bounds = shard_bounds(rowptr, n, world).astype(np.int64)
+            del rowptr
+            torch.cuda.empty_cache()
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        csr = synth.stencil3d_device(N, lo, hi)
+        name = f"27-point stencil {N}^3"
+    elif kind == "uniform":
+        n = int(m)
+        bounds = np.array([(n * g) // world for g in range(world + 1)], dtype=np.int64)  # k per row: rows = nnz balance
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        csr = synth.uniform_device(n, n, k, seed=1, r_lo=lo, r_hi=hi)
+        csr.val.mul_(1.0 / k)  # keeps 100 iterations of x <- A*x inside the fp64 range
+        name = f"uniform-random {n} x {n}, {k} nnz/row"
     else:
-        counts = synth.stencil_row_counts_device("stencil3d", N)
-        rowptr = synth._rowptr_from_counts_device(counts)
-        del counts
-        bounds = shard_bounds(rowptr, n, world).astype(np.int64)
-        del rowptr
-        torch.cuda.empty_cache()
-    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    csr = synth.stencil3d_device(N, lo, hi)
+        raise ValueError(kind)
     opt = options if options is not None else make_options(flags=FLAG_BETA0_SKIP_Y)
     plan = SpmvPlan(CsrDesc(csr.rows, csr.cols, csr.nnz, csr.rowptr, csr.col, csr.val), opt)
     need = col_block_bitmap(csr.col, csr.nnz, n, BLOCK_SHIFT) if world > 1 else np.zeros(0, np.uint8)
-    x = synth.vector_device(n, 2)
-    x_next = torch.zeros_like(x)
+    info = plan.info()
+    tile_row = reads_halo = None
+    if info.nsplit_rows == 0 and world > 1:
+        cmin, cmax = plan.tile_col_range()
+        reads_halo = (cmin < lo) | (cmax >= hi)
+        tile_row = plan.export("tile_row")
+    nnz_total = csr.nnz
+    if world > 1:
+        t = torch.tensor([float(csr.nnz)], dtype=torch.float64, device="cuda")
+        _dist().all_reduce(t)
+        nnz_total = int(t.item())
+    return Shard(name, n, bounds, csr, plan, need, tile_row, reads_halo, nnz_total)
+
+
+def make_loop(shard: Shard, exchange: str = "auto", overlap: bool = True) -> PowerLoop:
+    """A fresh loop (x = the seeded start vector) over an existing shard."""
+    import torch
+    from . import synth
+    plan = shard.plan
 
     def spmv(xf, ys):
         plan.execute(1.0, 0.0, xf, ys)
@@ -384,27 +488,60 @@ def build_stencil3d_power_loop(N: int, exchange: str = "auto", options=None, ove
     def spmv_tiles(xf, ys, t0, t1):
         plan.execute_tiles(1.0, 0.0, xf, ys, t0, t1)
 
-    info = plan.info()
-    can_split = info.nsplit_rows == 0 and world > 1
-    reads_halo = None
-    if can_split:
-        cmin, cmax = plan.tile_col_range()
-        reads_halo = (cmin < lo) | (cmax >= hi)
-    loop = PowerLoop(n=n, bounds=bounds, spmv=spmv, x=x, x_next=x_next, need_local=need, exchange=exchange,
-                     spmv_tiles=spmv_tiles if can_split else None,
-                     tile_row=plan.export("tile_row") if can_split else None, tile_reads_halo=reads_halo,
-                     overlap=overlap)
-    return loop, plan, csr
+    x = synth.vector_device(shard.n, 2)
+    return PowerLoop(n=shard.n, bounds=shard.bounds, spmv=spmv, x=x, x_next=torch.zeros_like(x),
+                     need_local=shard.need, exchange=exchange,
+                     spmv_tiles=spmv_tiles if shard.tile_row is not None else None, tile_row=shard.tile_row,
+                     tile_reads_halo=shard.reads_halo, overlap=overlap)
 
 
-def bench_power_loop(N: int = 384, iters: int = 100, exchange: str = "auto", warmup: int = 4,
-                     overlap: bool = True, graph: bool = False, fused: bool = True) -> dict:
-    """Times `iters` iterations of x <- A*x for the 27-point N^3 stencil on all ranks (device events, max over ranks)."""
+def build_stencil3d_power_loop(N: int, exchange: str = "auto", options=None, overlap: bool = True):
+    """(loop, plan, csr) of the C5 configuration for this rank."""
+    shard = build_shard("stencil3d", N=N, options=options)
+    return make_loop(shard, exchange, overlap), shard.plan, shard.csr
+
+
+class LocalLoop:
+    """The natively enqueued loop of a single rank (no neighbours): same runner as FusedHaloLoop, nothing to order."""
+
+    def __init__(self, base: PowerLoop, plan, flags: int = 0):
+        from . import HaloLoop
+        self.bufs = [base.x, base.x_next]
+        desc = make_halo_desc(plan, [self.bufs[0].data_ptr(), self.bufs[1].data_ptr()], 0, base.n, [], [], [[], []],
+                              [], [], flags)
+        self.loop = HaloLoop(desc)
+        self.k = 0
+        self.split = False
+
+    def run(self, iters: int):
+        self.loop.run(int(iters))
+        self.k += int(iters)
+        return self.x
+
+    def close(self):
+        self.loop.sync()
+        self.loop.destroy()
+
+    @property
+    def x(self):
+        return self.bufs[self.k % 2]
+
+
+MODES = ("fused", "fused_multi_launch", "nccl_halo", "nccl_allgather")
+
+
+def time_power_loop(shard: Shard, mode: str = "fused", iters: int = 100, warmup: int = 4, sampler=None) -> dict:
+    """Times `iters` iterations of x <- A*x on all ranks (CUDA events on the launching stream, max over ranks).
+
+    mode: "fused" (halo rows pushed by the SpMV kernels, one launch per iteration, CUDA graph; the single-rank loop
+    runs through the same native runner), "fused_multi_launch" (the same protocol as separate wait / boundary / flag /
+    interior launches without a graph), "nccl_halo" (grouped NCCL send/recv of the halo blocks overlapped with the
+    interior row blocks, CUDA graph), "nccl_allgather" (one grouped NCCL all-gather of x per iteration overlapped with
+    the row blocks that read only local columns, CUDA graph)."""
     import torch
+    from . import _lib
     dist = _dist()
     rank, world = world_info()
-    loop, plan, csr = build_stencil3d_power_loop(N, exchange, overlap=overlap)
-    nnz_local = csr.nnz
 
     def sync():
         torch.cuda.synchronize()
@@ -412,71 +549,91 @@ def bench_power_loop(N: int = 384, iters: int = 100, exchange: str = "auto", war
             dist.barrier()
         torch.cuda.synchronize()
 
-    # the same number of iterations runs in every mode, so the checksums of x stay comparable
-    warmup = max(4, warmup + warmup % 2)
-    iters += iters % 2
-    fused = bool(fused and world > 1 and loop.mode == "halo" and not graph)
-    runner = loop
-    fused_error = ""
-    if fused:
+    warmup = max(4, int(warmup))
+    iters = int(iters)
+    exchange = {"nccl_allgather": "allgather", "nccl_halo": "halo"}.get(mode, "auto")
+    loop = make_loop(shard, exchange)
+    native = mode in ("fused", "fused_multi_launch") and (world == 1 or loop.mode == "halo")
+    note = ""
+    runner = None
+    if native:
+        flags = (_lib.HALO_NO_GRAPH | _lib.HALO_MULTI_LAUNCH) if mode == "fused_multi_launch" else 0
         try:
-            runner = FusedHaloLoop(loop, plan)
-        except Exception as e:  # no peer path / IPC unavailable: keep the NCCL send/recv exchange
-            fused = False
-            fused_error = f"{type(e).__name__}: {e}"
-    if fused:
-        runner.run(warmup)
-    elif graph:
-        loop.capture()            # two eager iterations, then the capture of two more (not executed)
-        loop.run_graph(warmup - 2)
+            runner = (FusedHaloLoop if world > 1 else LocalLoop)(loop, shard.plan, flags)
+        except Exception as e:  # no peer path / IPC unavailable: keep the NCCL exchange
+            native, note = False, f"{type(e).__name__}: {e}"
+    use_graph = False
+    if native:
+        run = runner.run
     else:
-        loop.run(warmup)
+        if world > 1 and mode.startswith("fused"):
+            note = note or f"the halo is not sparse for this matrix (exchange = {loop.mode}): NCCL exchange used"
+        try:
+            iters += iters % 2  # the captured unit is a pair of iterations (one ping-pong period of the buffers)
+            warmup += warmup % 2
+            loop.capture()  # two eager iterations, then the capture of two more (not executed)
+            use_graph = True
+            run = lambda k: loop.run_graph(k)  # noqa: E731
+            warmup = max(2, warmup - 2)
+        except Exception as e:
+            note = (note + "; " if note else "") + f"graph capture failed ({type(e).__name__}: {e}); eager launches"
+            run = lambda k: loop.run(k, finish=False)  # noqa: E731
+    run(warmup)
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.start()
     e0.record()
-    if fused:
-        runner.run(iters)
-    elif graph:
-        loop.run_graph(iters)
-    else:
-        loop.run(iters)
+    run(iters)
     e1.record()
     e1.synchronize()
+    if sampler:
+        sampler.stop()
     sync()
     ms = e0.elapsed_time(e1)
-    stats = torch.tensor([ms, float(nnz_local)], dtype=torch.float64, device="cuda")
     if world > 1:
-        mx = stats.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-        ms, nnz_total = float(mx[0]), float(stats[1])
-    else:
-        nnz_total = float(nnz_local)
-    n = N ** 3
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    n, nnz_total = shard.n, float(shard.nnz_total)
     sec_iter = ms * 1e-3 / iters
-    lo, hi = int(loop.bounds[rank]), int(loop.bounds[rank + 1])
+    lo, hi = int(shard.bounds[rank]), int(shard.bounds[rank + 1])
+    x = runner.x if native else loop.x
     out = {
-        "workload": f"C5: 27-point stencil {N}^3 ({n} rows, {int(nnz_total)} nnz), x <- A*x, {iters} iterations, "
-                    f"alpha=1, beta=0",
-        "scaling": "strong", "n_gpus": world, "iters": iters, "ms_per_iter": sec_iter * 1e3,
-        "value": 2.0 * nnz_total / sec_iter / 1e9, "unit": "GFLOP/s",
+        "mode": mode, "scaling": "strong", "n_gpus": world, "iters": iters, "warmup_iters": warmup + (2 if use_graph else 0),
+        "ms_per_iter": sec_iter * 1e3, "value": 2.0 * nnz_total / sec_iter / 1e9, "unit": "GFLOP/s",
         "effective_gbs": (12 * nnz_total + 4 * (n + 1) + 8 * n + 16 * n) / sec_iter / 1e9,
-        "exchange": ("halo, pushed by the SpMV kernels into peer memory (NVLink stores) + stream-ordered flags"
-                     if fused else loop.mode), "exchange_bytes_in_per_iter_rank0": loop.bytes_in_per_iter,
-        "cuda_graph": bool(graph),
-        "exchange_overlapped_with_interior_rows": bool(getattr(loop, "overlapped", False)),
+        "exchange": ("none (one rank)" if world == 1 else
+                     "halo rows pushed by the SpMV kernels into peer memory (NVLink stores), flags waited for and "
+                     "raised inside the kernel" if native else f"NCCL {loop.mode}"),
+        "exchange_bytes_in_per_iter_rank0": loop.bytes_in_per_iter,
+        "exchange_overlapped_with_local_rows": bool(getattr(loop, "overlapped", False)),
         "boundary_row_blocks_rank0": int(sum(b - a for a, b in loop.boundary)),
-        # bit pattern checksum of x[0 : n/16] after the last iteration: that range belongs to rank 0 for every
-        # world size <= 8, so equal values across runs with 1/2/4/8 GPUs prove bitwise-identical results
-        "x_checksum_first_16th": bits_checksum(runner.x[0:n // 16]),
-        "halo_fused_into_kernel": bool(fused),
-        "fused_boundary_first": bool(fused and getattr(runner, "split", False)),
-        "loop_enqueued_natively": bool(fused and getattr(runner, "desc", None) is not None),
+        # bit pattern checksum of this rank-0-owned range after the last iteration: equal values across runs with
+        # 1/2/4/8 GPUs and across modes prove bitwise-identical results (n/16 rows belong to rank 0 for <= 8 ranks)
+        "x_checksum_first_16th": bits_checksum(x[0:n // 16]),
         "total_timed_ms": ms,
     }
-    if fused:
+    if native:
+        info = runner.loop.info()
+        out.update({"launches_per_iteration": int(info.launches_per_iteration),
+                    "iterations_per_graph_launch": int(info.uses_graph),
+                    "single_launch_kernel": bool(info.single_launch),
+                    "boundary_first": bool(getattr(runner, "split", False))})
         runner.close()
-    elif fused_error:
-        out["halo_fused_error"] = fused_error
-    plan.destroy()
+    else:
+        out["cuda_graph"] = use_graph
+    if note:
+        out["note"] = note
     return out
+
+
+def bench_power_loop(N: int = 384, iters: int = 100, mode: str = "fused", warmup: int = 4) -> dict:
+    """One-call form: builds the C5 shard of this rank, times one mode, frees everything."""
+    shard = build_shard("stencil3d", N=N)
+    try:
+        out = time_power_loop(shard, mode, iters, warmup)
+        out["workload"] = f"C5: {shard.name} ({shard.n} rows, {shard.nnz_total} nnz), x <- A*x, alpha=1, beta=0"
+        return out
+    finally:
+        shard.destroy()

@@ -41,10 +41,22 @@ void cuda_b200_sparse_spmv_profile(SpMVAccHanele *handle, int trans, const doubl
   if (trans != 0) {
     throw std::runtime_error("cuda-b200: only operation_none is supported");
   }
-  cudaEvent_t e[4];
-  for (auto &ev : e) {
-    cudaEventCreate(&ev);
-  }
+  struct Events { // destroyed on every path out of this function, plan_create may throw
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    Events() {
+      for (auto &ev : e) {
+        cudaEventCreate(&ev);
+      }
+    }
+    ~Events() {
+      for (auto &ev : e) {
+        if (ev != nullptr) {
+          cudaEventDestroy(ev);
+        }
+      }
+    }
+  } events;
+  cudaEvent_t *e = events.e;
   spmv_b200_plan *plan = nullptr;
   cudaEventRecord(e[0], nullptr);
   check(spmv_b200_plan_create(&plan, d_csr_desc.rows, d_csr_desc.cols, d_csr_desc.nnz, d_csr_desc.row_ptr,
@@ -59,9 +71,6 @@ void cuda_b200_sparse_spmv_profile(SpMVAccHanele *handle, int trans, const doubl
     handle->profile_analyze_time = elapsed_ms(e[0], e[1]) * 1e3; // harness times are in microseconds
     handle->profile_kernel_time = elapsed_ms(e[1], e[2]) * 1e3;
     handle->profile_destroy_time = elapsed_ms(e[2], e[3]) * 1e3;
-  }
-  for (auto &ev : e) {
-    cudaEventDestroy(ev);
   }
   check(rc, "execute");
 }

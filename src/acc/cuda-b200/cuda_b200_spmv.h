@@ -23,14 +23,15 @@ void cuda_b200_sparse_spmv(int trans, const double alpha, const double beta, con
                            const csr_desc<int, double> d_csr_desc, const double *x, double *y);
 
 /**
- * Same computation with the analyse / kernel / destroy phases timed separately (milliseconds, CUDA events) into the
+ * Same computation with the analyse / kernel / destroy phases timed separately (microseconds, CUDA events) into the
  * handle, like csr_adaptive_plus_sparse_spmv<true> (src/acc/hip-csr-adaptive-plus/csr_adaptive_plus_spmv.cpp:92-129).
  */
 void cuda_b200_sparse_spmv_profile(SpMVAccHanele *handle, int trans, const double alpha, const double beta,
                                    const csr_desc<int, double> h_csr_desc, const csr_desc<int, double> d_csr_desc,
                                    const double *x, double *y);
 
-/** Drops the cached analysis of every matrix (call after a matrix was rewritten in place at the same address). */
+/** Drops the cached analysis of every matrix. The cache re-validates a fingerprint of the row pointers on every call
+ *  (include/spmv_b200.h); this is for callers that rewrite row pointers in place between calls. */
 void cuda_b200_invalidate_plans();
 
 #endif // SPMV_ACC_CUDA_B200_SPMV_H

@@ -10,7 +10,8 @@ import oracle
 from conftest import GOLDEN_CASES, load_golden
 from gpu_helpers import assert_parity, desc_of, gpu_spmv
 from spmv_acc_b200 import (FLAG_BETA0_SKIP_Y, FLAG_DIRECT, FLAG_NO_DIRECT, FLAG_NO_TMA, CsrDesc, HostMatrix, SpmvB200Error, SpmvPlan,
-                           cache_invalidate, cache_size, host_spmv, make_options, sparse_csr_spmv, sparse_spmv, synth)
+                           cache_invalidate, cache_revalidations, cache_size, host_spmv, make_options, sparse_csr_spmv,
+                           sparse_spmv, synth)
 
 pytestmark = pytest.mark.gpu
 
@@ -25,7 +26,7 @@ OPTS = {
     "tiled_only": make_options(flags=FLAG_NO_DIRECT),
     "direct": make_options(flags=FLAG_DIRECT),
     "direct_scalar_loads": make_options(flags=FLAG_DIRECT | FLAG_NO_TMA),
-    "direct_two_windows": make_options(flags=FLAG_DIRECT | (1 << 23)),
+    "direct_40_registers": make_options(flags=FLAG_DIRECT | (1 << 23)),
     "direct_T512_L64": make_options(512, 8, 64, flags=FLAG_DIRECT),
     "mixed_segmented": make_options(flags=(1 << 22) | FLAG_NO_DIRECT),
     "mixed_segmented_small": make_options(256, 4, 16, 2, flags=(1 << 22) | FLAG_NO_DIRECT),
@@ -195,6 +196,63 @@ def test_reference_shaped_entry_points_and_plan_cache():
     assert cache_size() == 0
 
 
+def test_plan_cache_detects_a_new_matrix_at_the_same_addresses():
+    """A caching allocator hands the same addresses to the next matrix of the same shape: the stateless entry points
+    must notice (fingerprint of the row pointers, re-read on the device on every call) and analyse again."""
+    import torch
+    cache_invalidate()
+    m, n = 6000, 4000
+    a = _ragged(21, m, n, [0, 1, 2, 3, 5, 9, 17, 40, 300, 2500])
+    # a second matrix with the same number of rows AND non-zeros, other row lengths: reverse the row order
+    lens = np.diff(a.rowptr)[::-1]
+    rp = np.zeros(m + 1, np.int32)
+    rp[1:] = np.cumsum(lens)
+    rng = np.random.default_rng(22)
+    b = synth.Csr(m, n, rp, rng.integers(0, n, a.nnz).astype(np.int32), rng.standard_normal(a.nnz))
+    assert b.nnz == a.nnz and not np.array_equal(a.rowptr, b.rowptr)
+    d = synth.to_device(a)
+    desc = desc_of(d)
+    x, y0 = synth.vector_numpy(n, 2), synth.vector_numpy(m, 3)
+    dx = torch.from_numpy(x).cuda()
+    before = cache_revalidations()
+    for h in (a, b, b, a):
+        d.rowptr.copy_(torch.from_numpy(h.rowptr))   # same device arrays, new contents
+        d.col.copy_(torch.from_numpy(h.col))
+        d.val.copy_(torch.from_numpy(h.val))
+        dy = torch.from_numpy(y0).cuda()
+        sparse_csr_spmv(0, 0.75, -0.5, desc, desc, dx, dy)
+        torch.cuda.synchronize()
+        assert_parity(h, x, y0, 0.75, -0.5, dy.cpu().numpy(), what="same address, new contents")
+        dy = torch.from_numpy(y0).cuda()
+        sparse_spmv(0, 1.0, 1.0, m, n, d.rowptr, d.col, d.val, dx, dy)  # nnz read on the device
+        torch.cuda.synchronize()
+        assert_parity(h, x, y0, 1.0, 1.0, dy.cpu().numpy(), what="same address, new contents (sparse_spmv)")
+        assert cache_size() == 1
+    assert cache_revalidations() - before == 2   # a -> b and b -> a; the repeated b is a plain hit
+    cache_invalidate()
+
+
+def test_host_buffer_path_on_a_device_resident_matrix():
+    """spmv_b200_hostmat_create_device: the matrix already lives on the device (cli/utils.hpp:94-116 done by the caller),
+    x / y travel per call; with beta == 0 and BETA0_SKIP_Y the y0 copy is skipped and NaN in h_y does not propagate."""
+    h = synth.stencil3d_numpy(40)
+    d = synth.to_device(h)
+    x, y0 = synth.vector_numpy(h.cols, 2), synth.vector_numpy(h.rows, 3)
+    hm = HostMatrix(h.rows, h.cols, d.rowptr, d.col, d.val)
+    for a, b in AB[:3]:
+        y = y0.copy()
+        hm.spmv(a, b, x, y)
+        assert_parity(h, x, y0, a, b, y, what="hostmat on device arrays")
+    hm.destroy()
+    hm = HostMatrix(h.rows, h.cols, d.rowptr, d.col, d.val, make_options(flags=FLAG_BETA0_SKIP_Y))
+    y = np.full(h.rows, np.nan)
+    hm.spmv(1.0, 0.0, x, y)
+    assert_parity(h, x, np.zeros(h.rows), 1.0, 0.0, y, what="hostmat, y0 not sent")
+    hm.destroy()
+    with pytest.raises(SpmvB200Error):
+        HostMatrix(h.rows, h.cols, h.rowptr, d.col, d.val)  # mixed host / device arrays
+
+
 def test_host_buffer_path():
     g = load_golden("c4_rmat_s11")
     h = _golden_csr(g)
@@ -317,6 +375,97 @@ def test_full_size_c4_rmat_row_sums():
     # index_add_ is itself a floating-point reduction in another order: allow its error as well
     assert bool(((y - ref).abs() <= 2e-12 * absum + 1e-300).all())
     assert int((lens == 0).sum()) > 0 and float(y[lens == 0].abs().max()) == 0.0
+    p.destroy()
+
+
+def _check_sample(d, plan, x, alpha, beta, rows, what):
+    """One SpMV at full size; the sampled rows against the reference's CPU SpMV (oracle/sampled.py); run twice."""
+    import torch
+    from oracle import sampled
+    y0 = synth.vector_device(d.rows, 5)
+    y = y0.clone()
+    plan.execute(alpha, beta, x, y)
+    y2 = y0.clone()
+    plan.execute(alpha, beta, x, y2)
+    torch.cuda.synchronize()
+    assert torch.equal(y.view(torch.int64), y2.view(torch.int64)), f"{what}: run-to-run results differ bitwise"
+    res = sampled.check_sampled_rows(d.rowptr, d.col, d.val, x, y0, y, alpha, beta, rows)
+    assert res["ok"], f"{what}: {res}"
+    return res, y
+
+
+def test_full_size_c3_sampled_rows_against_oracle():
+    """C3: uniform random 10^7 x 10^7, 32 nnz per row (3.2e8 nnz): random x, 20 000 sampled rows + the ends."""
+    from oracle import sampled
+    d = synth.uniform_device(10_000_000, 10_000_000, 32, seed=1)
+    p = SpmvPlan(desc_of(d))
+    x = synth.vector_device(d.cols, 2)
+    rows = sampled.sample_rows(d.rows, 20000, seed=11)
+    for a, b in ((0.75, -0.5), (1.0, 1.0)):
+        res, _ = _check_sample(d, p, x, a, b, rows, f"C3 a={a} b={b}")
+        assert res["rows_checked"] >= 20000 and res["nnz_checked"] == 32 * res["rows_checked"]
+    p.destroy()
+
+
+def test_full_size_c4_sampled_rows_against_oracle():
+    """C4: R-MAT scale 24 (2^28 nnz): random x; the sample holds the longest row, >= 100 rows that are split across
+    row blocks (their partial sums are combined by the fix-up pass) and 20 000 random rows."""
+    import torch
+    from oracle import sampled
+    d = synth.rmat_device(24, 16, seed=1)
+    p = SpmvPlan(desc_of(d))
+    info = p.info()
+    assert info.direct == 1 and info.nsplit_rows >= 100
+    split = p.export("split_rows")[:info.nsplit_rows]
+    lens = (d.rowptr[1:] - d.rowptr[:-1])
+    longest = int(torch.argmax(lens).item())
+    assert longest in set(split.tolist())
+    pick = np.unique(np.concatenate([split[:: max(1, split.size // 400)], [longest]]))
+    rows = sampled.sample_rows(d.rows, 20000, seed=12, must_include=pick.tolist())
+    x = synth.vector_device(d.cols, 2)
+    res, y = _check_sample(d, p, x, 0.75, -0.5, rows, "C4")
+    assert res["longest_row_checked"] == int(lens[longest].item()) and res["longest_row_checked"] > 100000
+    # rows without elements: y = beta * y0 exactly
+    y0 = synth.vector_device(d.rows, 5)
+    empty = lens == 0
+    assert int(empty.sum()) > 0 and torch.equal(y[empty], -0.5 * y0[empty])
+    p.destroy()
+    # the tiled (shared-memory) form on the same matrix
+    p = SpmvPlan(desc_of(d), make_options(flags=FLAG_NO_DIRECT))
+    assert p.info().direct == 0
+    _check_sample(d, p, x, 1.0, 1.0, rows, "C4 tiled")
+    p.destroy()
+
+
+def test_full_size_c5_known_answer_and_sampled_rows():
+    """C5: 27-point averaging stencil on 384^3 (56.6M rows, 1.52e9 nnz = 71 % of int32): A*1 = 1 on interior rows
+    within the bound and (neighbours)/27 on the boundary; random x on 20 000 sampled rows and around z-plane
+    boundaries and the very end of the arrays (where 32-bit byte offsets would have wrapped)."""
+    import torch
+    from oracle import sampled
+    N = 384
+    d = synth.stencil3d_device(N)
+    assert d.nnz == (3 * N - 2) ** 3
+    p = SpmvPlan(desc_of(d), make_options(flags=FLAG_BETA0_SKIP_Y))
+    ones = torch.ones(d.cols, dtype=torch.float64, device="cuda")
+    y = torch.full((d.rows,), float("nan"), dtype=torch.float64, device="cuda")
+    p.execute(1.0, 0.0, ones, y)
+    yy = y.view(N, N, N)
+    assert float((yy[1:-1, 1:-1, 1:-1] - 1.0).abs().max()) <= 27 * 2.3e-16
+    assert abs(float(yy[0, 0, 0]) - 8.0 / 27.0) <= 1e-15 and abs(float(yy[-1, -1, -1]) - 8.0 / 27.0) <= 1e-15
+    assert abs(float(yy[0, 5, 5]) - 18.0 / 27.0) <= 1e-15 and abs(float(yy[-1, 0, 7]) - 12.0 / 27.0) <= 1e-15
+    # the sum of all row sums = nnz / 27 (sum of pairwise sums on the device: allow its rounding)
+    assert abs(float(y.sum()) - d.nnz / 27.0) <= 1e-9 * d.nnz / 27.0
+    del ones, yy
+    plane = N * N
+    edge = [r for z in (1, 191, 192, 383) for r in range(z * plane - 40, z * plane + 40)]
+    rows = sampled.sample_rows(d.rows, 20000, seed=13, must_include=edge)
+    x = synth.vector_device(d.cols, 2)
+    res, _ = _check_sample(d, p, x, 1.0, 0.0, rows, "C5")
+    assert res["rows_checked"] >= 20000
+    p.destroy()
+    p = SpmvPlan(desc_of(d))      # default semantics (y read even when beta == 0), general alpha / beta
+    _check_sample(d, p, x, 0.75, -0.5, rows, "C5 a=0.75 b=-0.5")
     p.destroy()
 
 
