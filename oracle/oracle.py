@@ -39,7 +39,7 @@ def build(with_ref: bool = True) -> None:
     if with_ref and REFERENCE.exists():
         targets += ["ref", "ref-gpu"]
         if (HERE.parent / "spmv_acc_b200" / "lib" / "libspmv_b200.so").exists():
-            targets += ["ref-cli"]
+            targets += ["ref-cli", "ref-harness"]
     res = subprocess.run(["make", "-s", "-C", str(HERE), *targets], capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"oracle build failed:\n{res.stdout}\n{res.stderr}")

@@ -16,4 +16,5 @@ if (NOT DEFINED SPMV_B200_ROOT)
 endif ()
 include_directories(${SPMV_B200_ROOT}/include)
 find_package(CUDAToolkit REQUIRED)
-set(ACC_LIBS ${ACC_LIBS} ${SPMV_B200_ROOT}/spmv_acc_b200/lib/libspmv_b200.so CUDA::cudart)
+# linked PUBLIC by the kernel library (src/acc/CMakeLists.txt), so the CLI and the benchmark get them transitively
+set(SPMV_B200_LINK_LIBS ${SPMV_B200_ROOT}/spmv_acc_b200/lib/libspmv_b200.so CUDA::cudart)
