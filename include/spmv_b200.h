@@ -43,7 +43,8 @@ extern "C" {
 #define SPMV_B200_FLAG_BETA0_SKIP_Y 2u /* beta==0: do not read y (cuSPARSE semantics); default reads y so   */
                                        /* that NaN/Inf in y propagate exactly like cli/verification.cpp:64  */
 #define SPMV_B200_FLAG_GATHER_NO_L1 8u /* gather x with L1::no_allocate                                             */
-#define SPMV_B200_FLAG_PERSISTENT 0x20000u /* row kernels as persistent CTAs with a two-stage TMA ring              */
+#define SPMV_B200_FLAG_NO_XSTAGE 0x40000u /* never use the staged-x form (x segments of a row block in shared memory  */
+                                          /* + 16-bit local column indices; automatic for stencil / banded matrices) */
 #define SPMV_B200_FLAG_DIRECT 0x40u    /* force the direct form: one warp per row block, value / colindex              */
                                        /* streamed straight into registers, no shared memory (all of the unified      */
                                        /* L1/shared array stays L1 for the x gathers); automatic for irregular gathers */
@@ -79,6 +80,8 @@ typedef struct spmv_b200_plan_info {
   int64_t gather_lines;      /* distinct 128-byte lines of x those gathers touch                */
   int64_t smem_bytes;        /* dynamic shared memory per CTA of the streaming kernels          */
   int64_t workspace_bytes;   /* device memory owned by the plan                                 */
+  int32_t xstage;            /* 1 if the staged-x form is used (x segments in shared memory, 16-bit local indices) */
+  int32_t xstage_lines;      /* largest number of 128-byte lines of x any row block stages      */
 } spmv_b200_plan_info;
 
 /* arrays that spmv_b200_plan_export can copy to the host (for bit-exact analysis checks) */
@@ -94,7 +97,12 @@ enum {
   /* direct form only (empty otherwise): */
   SPMV_B200_EXPORT_ROW_START_BITS = 8, /* uint32 [ceil(rowptr[m]/32)] bit k set iff element k is the first of its row */
   SPMV_B200_EXPORT_NZ_ROWS = 9,        /* int32 [non-empty rows]      their ids, ascending                           */
-  SPMV_B200_EXPORT_TILE_NZBASE = 10    /* int32 [ntiles]              number of non-empty rows in front of each tile  */
+  SPMV_B200_EXPORT_TILE_NZBASE = 10,   /* int32 [ntiles]              number of non-empty rows in front of each tile  */
+  /* staged-x form only (empty otherwise): */
+  SPMV_B200_EXPORT_LCOL = 11,  /* uint16 [nnz]      (rank of the 128-byte line of x among the lines the element's row block
+                                                     references) * 16 + (colindex & 15)                                   */
+  SPMV_B200_EXPORT_XDESC = 12  /* int32 [32*ntiles] per row block: nseg, nlines, first line of each of <= 16 runs of
+                                                     consecutive lines, then their ranks as uint16 pairs, padding           */
 };
 
 /* Fused halo push: rows [row_lo[j], row_hi[j]) of y are also stored to dst[j][row] (device pointers, typically

@@ -18,6 +18,7 @@
  * and rows: row r starts at merged position f(r) = rowptr[r] - base + r).
  */
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 static int lower_bound_rowptr(const int *rowptr, int m, long long target) {
@@ -325,4 +326,81 @@ int port_adaptive_choice(const int *rowptr, int m) {
   if (bp_3 > (1 << 23))
     return 3;
   return 4;
+}
+
+/* Staged-x form of the row kernels (spmv_acc_b200/csrc/analysis.cu:k_xstage_build), restated serially. For every row
+ * block t with elements [tile_elem[t], tile_elem[t+1]): the sorted set of 128-byte lines of x it references
+ * (line = colindex >> 4), the maximal runs of consecutive lines ("segments": first line and rank of that line in the
+ * set), and for every element the 16-bit offset (rank of its line << 4) | (colindex & 15) into the staged copy of x.
+ * This plays the role of the reference's x-remap kernels (src/acc/hip-thread-row/thread_row_block_x_remap.hpp:148-265,
+ * which stage column indices and then x per block in LDS), decided once per matrix instead of per launch.
+ * xdesc is 32 int32 per tile with the layout of struct XDesc: [0] nseg, [1] nlines, [2..17] first lines, [18..25] the
+ * ranks as 16 uint16 packed little-endian, [26..31] zero. Returns the number of tiles that do not qualify (span of
+ * lines >= span_max, more than lines_max lines, more than seg_max runs, or no elements); their xdesc[0] is -1 and
+ * their lcol entries are left untouched. *max_lines receives the largest line count of the qualifying tiles. */
+static int cmp_int(const void *a, const void *b) {
+  const int x = *(const int *)a, y = *(const int *)b;
+  return (x > y) - (x < y);
+}
+
+int port_xstage(const int *colindex, const int *tile_elem, int ntiles, int elem_base, int span_max, int lines_max,
+                int seg_max, unsigned short *lcol, int *xdesc, int *max_lines) {
+  int failed = 0, best = 0;
+  for (int t = 0; t < ntiles; t++) {
+    int *xd = xdesc + 32 * (long long)t;
+    for (int i = 0; i < 32; i++)
+      xd[i] = 0;
+    const int e0 = tile_elem[t], e1 = tile_elem[t + 1];
+    const int cnt = e1 - e0;
+    int ok = cnt > 0;
+    int *lines = NULL;
+    int nlines = 0, nseg = 0;
+    if (ok) {
+      lines = (int *)malloc(sizeof(int) * (size_t)cnt);
+      for (int k = 0; k < cnt; k++)
+        lines[k] = colindex[e0 + k] >> 4;
+      qsort(lines, (size_t)cnt, sizeof(int), cmp_int);
+      for (int k = 0; k < cnt; k++)
+        if (k == 0 || lines[k] != lines[k - 1])
+          lines[nlines++] = lines[k];
+      for (int i = 0; i < nlines; i++)
+        if (i == 0 || lines[i] != lines[i - 1] + 1)
+          nseg++;
+      ok = (lines[nlines - 1] - lines[0]) < span_max && nlines <= lines_max && nseg <= seg_max;
+    }
+    if (!ok) {
+      xd[0] = -1;
+      failed++;
+      free(lines);
+      continue;
+    }
+    unsigned short *off = (unsigned short *)(xd + 18);
+    int s = 0;
+    for (int i = 0; i < nlines; i++)
+      if (i == 0 || lines[i] != lines[i - 1] + 1) {
+        xd[2 + s] = lines[i];
+        off[s] = (unsigned short)i;
+        s++;
+      }
+    xd[0] = nseg;
+    xd[1] = nlines;
+    if (nlines > best)
+      best = nlines;
+    for (int k = 0; k < cnt; k++) {
+      const int c = colindex[e0 + k], l = c >> 4;
+      int lo = 0, hi = nlines - 1; /* rank of l in the sorted set */
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (lines[mid] < l)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      lcol[(long long)e0 + k - elem_base] = (unsigned short)((lo << 4) | (c & 15));
+    }
+    free(lines);
+  }
+  if (max_lines)
+    *max_lines = best;
+  return failed;
 }

@@ -17,7 +17,7 @@ REFERENCE = Path("/root/reference")
 __all__ = [
     "build", "have_ref", "port_host_spmv", "port_host_spmv_ax", "port_verify_y", "port_verify", "port_row_bound",
     "port_generate_vector", "port_merge_path_partition", "port_flat_break_points_v2", "port_analysis",
-    "port_shard_bounds", "port_gather_stat", "port_tiled_spmv", "port_direct_arrays", "port_adaptive_choice", "ref_host_spmv", "ref_host_spmv_ax", "ref_verify_y",
+    "port_shard_bounds", "port_gather_stat", "port_tiled_spmv", "port_direct_arrays", "port_adaptive_choice", "port_xstage", "ref_host_spmv", "ref_host_spmv_ax", "ref_verify_y",
     "ref_adaptive_plus_analyze", "ref_read", "ref_generate_vector", "best_host_spmv", "check_rows",
 ]
 
@@ -253,6 +253,22 @@ def port_direct_arrays(rowptr, tile_row):
     tile_row = np.asarray(tile_row, dtype=np.int64)
     nzbase = np.searchsorted(nz_rows, tile_row[:-1], side="left").astype(_i32)
     return {"row_start_bits": bits, "nz_rows": nz_rows, "tile_nzbase": nzbase}
+
+
+def port_xstage(col, tile_elem, span_max=65536, lines_max=256, seg_max=16):
+    """CPU restatement of the staged-x analysis (spmv_acc_b200/csrc/analysis.cu:k_xstage_build): returns
+    dict(failed, max_lines, lcol uint16 [nnz], xdesc int32 [32*ntiles]) with the export layout."""
+    col, tile_elem = _c(col, _i32), _c(tile_elem, _i32)
+    nt = tile_elem.size - 1
+    base = int(tile_elem[0]) if tile_elem.size else 0
+    nnz = int(tile_elem[-1]) - base if tile_elem.size else 0
+    lcol = np.zeros(max(nnz, 1), np.uint16)
+    xdesc = np.zeros(32 * max(nt, 1), _i32)
+    best = C.c_int(0)
+    failed = _port_lib().port_xstage(_p(col, C.c_int), _p(tile_elem, C.c_int), C.c_int(nt), C.c_int(base),
+                                     C.c_int(span_max), C.c_int(lines_max), C.c_int(seg_max),
+                                     lcol.ctypes.data_as(C.POINTER(C.c_ushort)), _p(xdesc, C.c_int), C.byref(best))
+    return {"failed": int(failed), "max_lines": int(best.value), "lcol": lcol[:nnz], "xdesc": xdesc[:32 * nt]}
 
 
 ADAPTIVE_CHOICES = ["vector-row, two data blocks", "adaptive line", "adaptive line-enhance", "adaptive flat",

@@ -7,6 +7,6 @@ package does not load the CUDA library; the first call does, and fails loudly if
 """
 from .api import (CsrDesc, HostMatrix, PeerBuffer, SpmvB200Error, SpmvPlan, cache_invalidate, cache_size, col_block_bitmap, coo_to_csr,  # noqa: F401
                   host_spmv, make_options, HaloLoop, cache_revalidations, enable_peer_access, operation_none, operation_transpose, shard_bounds, sparse_csr_spmv,
-                  sparse_spmv, FLAG_BETA0_SKIP_Y, FLAG_DIRECT, FLAG_L2_PERSIST_X, FLAG_NO_DIRECT, FLAG_NO_TMA)
+                  sparse_spmv, FLAG_BETA0_SKIP_Y, FLAG_DIRECT, FLAG_L2_PERSIST_X, FLAG_NO_DIRECT, FLAG_NO_TMA, FLAG_NO_XSTAGE)
 
 __version__ = "0.1.0"

@@ -66,7 +66,8 @@ class PlanInfo(C.Structure):
                 ("uses_tma", C.c_int32), ("ntiles", C.c_int32), ("tiles_per_kind", C.c_int32 * 3),
                 ("nsplit_rows", C.c_int32), ("launches_per_execute", C.c_int32), ("direct", C.c_int32), ("bin_rows", C.c_int64 * 4),
                 ("bin_nnz", C.c_int64 * 4), ("gather_active", C.c_int64), ("gather_lines", C.c_int64),
-                ("smem_bytes", C.c_int64), ("workspace_bytes", C.c_int64)]
+                ("smem_bytes", C.c_int64), ("workspace_bytes", C.c_int64), ("xstage", C.c_int32),
+                ("xstage_lines", C.c_int32)]
 
 
 FLAG_NO_TMA = 1
@@ -74,12 +75,15 @@ FLAG_BETA0_SKIP_Y = 2
 FLAG_L2_PERSIST_X = 4
 FLAG_DIRECT = 0x40
 FLAG_NO_DIRECT = 0x80
+FLAG_NO_XSTAGE = 0x40000
 
 EXPORT_IDS = {"tile_row": 0, "tile_elem": 1, "tile_split": 2, "tile_kind": 3, "tile_part": 4, "row_bin": 5,
-              "split_rows": 6, "tile_maxlen": 7, "row_start_bits": 8, "nz_rows": 9, "tile_nzbase": 10}
+              "split_rows": 6, "tile_maxlen": 7, "row_start_bits": 8, "nz_rows": 9, "tile_nzbase": 10, "lcol": 11,
+              "xdesc": 12}
 EXPORT_DTYPES = {"tile_row": "int32", "tile_elem": "int32", "tile_split": "uint8", "tile_kind": "uint8",
                  "tile_part": "int32", "row_bin": "uint8", "split_rows": "int32", "tile_maxlen": "int32",
-                 "row_start_bits": "uint32", "nz_rows": "int32", "tile_nzbase": "int32"}
+                 "row_start_bits": "uint32", "nz_rows": "int32", "tile_nzbase": "int32", "lcol": "uint16",
+                 "xdesc": "int32"}
 
 _lib = None
 _gen = None

@@ -22,7 +22,7 @@ from typing import Any, Optional
 import numpy as np
 
 from . import _lib
-from ._lib import FLAG_BETA0_SKIP_Y, FLAG_DIRECT, FLAG_L2_PERSIST_X, FLAG_NO_DIRECT, FLAG_NO_TMA, Options, PlanInfo, SpmvB200Error, check  # noqa: F401
+from ._lib import FLAG_BETA0_SKIP_Y, FLAG_DIRECT, FLAG_L2_PERSIST_X, FLAG_NO_DIRECT, FLAG_NO_TMA, FLAG_NO_XSTAGE, Options, PlanInfo, SpmvB200Error, check  # noqa: F401
 
 operation_none = 0       # src/acc/api/types.h:8
 operation_transpose = 1

@@ -533,6 +533,196 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
   return SPMV_B200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// staged-x form: per row block, the 128-byte lines of x it references, their runs, and 16-bit local column indices
+// ---------------------------------------------------------------------------------------------------------------
+// Specification (bit-exact restatement: oracle/analysis_port.c:port_xstage). For tile t with elements [e0, e1):
+//   lines(t)   = sorted set of { col[k] >> 4 : e0 <= k < e1 }            (a line = 16 consecutive entries of x)
+//   rank(l)    = number of lines of the set smaller than l
+//   segments   = maximal runs of consecutive line numbers; segment s = (first line, rank of its first line)
+//   lcol[k]    = (rank(col[k] >> 4) << 4) | (col[k] & 15)                (offset into the staged copy, in doubles)
+//   the tile qualifies iff it has elements, last line - first line < kXspanLinesMax, |lines| <= kXlinesMax and
+//   #segments <= kXsegMax; the plan takes the form iff every tile qualifies.
+// One CTA per tile: a bitmap of the line span in shared memory (integer OR), a scan of its popcounts for the ranks.
+__global__ void __launch_bounds__(256)
+    k_xstage_build(const int *__restrict__ col, const TileDesc *__restrict__ desc, int ntiles, long long lcol_base,
+                   unsigned short *__restrict__ lcol, XDesc *__restrict__ xdesc, int *__restrict__ status /* [2]: failed, max lines */) {
+  extern __shared__ unsigned int xs_smem[];
+  unsigned int *bitmap = xs_smem;                                          // [kXspanLinesMax / 32]
+  int *prefix = reinterpret_cast<int *>(xs_smem + kXspanLinesMax / 32);    // lines in front of each word
+  __shared__ int s_red[2][8];
+  __shared__ int s_scan[9], s_runs[9];
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (t >= ntiles)
+    return;
+  XDesc *xd = xdesc + t;
+  __shared__ int s_abort;
+  if (tid == 0)
+    s_abort = *reinterpret_cast<volatile int *>(status); // another tile has already failed: the plan will not use the form
+  __syncthreads();
+  if (s_abort != 0)
+    return;
+  const int e0 = desc[t].e0, e1 = desc[t].e1;
+  // span of lines
+  int lo = 0x7fffffff, hi = -1;
+  for (int k = e0 + tid; k < e1; k += 256) {
+    const int l = __ldg(col + k) >> 4;
+    lo = l < lo ? l : lo;
+    hi = l > hi ? l : hi;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const int l2 = __shfl_xor_sync(0xffffffffu, lo, off), h2 = __shfl_xor_sync(0xffffffffu, hi, off);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+  }
+  if (lane == 0) {
+    s_red[0][warp] = lo;
+    s_red[1][warp] = hi;
+  }
+  __syncthreads();
+  lo = s_red[0][0];
+  hi = s_red[1][0];
+  for (int w = 1; w < 8; ++w) {
+    lo = s_red[0][w] < lo ? s_red[0][w] : lo;
+    hi = s_red[1][w] > hi ? s_red[1][w] : hi;
+  }
+  bool ok = e1 > e0 && hi >= lo && (hi - lo) < kXspanLinesMax;
+  int nwords = ok ? ((hi - lo) >> 5) + 1 : 0;
+  if (ok) {
+    for (int w = tid; w < nwords; w += 256)
+      bitmap[w] = 0u;
+    __syncthreads();
+    for (int k = e0 + tid; k < e1; k += 256) {
+      const int l = (__ldg(col + k) >> 4) - lo;
+      atomicOr(bitmap + (l >> 5), 1u << (l & 31));
+    }
+    __syncthreads();
+    // ranks: exclusive scan of the popcounts of the words; runs: set bits whose predecessor bit is clear
+    const int per = (nwords + 255) / 256; // consecutive words per thread
+    int cnt = 0, runs = 0;
+    for (int j = 0; j < per; ++j) {
+      const int w = tid * per + j;
+      if (w < nwords) {
+        const unsigned b = bitmap[w];
+        const unsigned prev = w > 0 ? bitmap[w - 1] >> 31 : 0u;
+        cnt += __popc(b);
+        runs += __popc(b & ~((b << 1) | prev));
+      }
+    }
+    int icnt = cnt, iruns = runs;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int c2 = __shfl_up_sync(0xffffffffu, icnt, off), r2 = __shfl_up_sync(0xffffffffu, iruns, off);
+      if (lane >= off) {
+        icnt += c2;
+        iruns += r2;
+      }
+    }
+    if (lane == 31) {
+      s_scan[warp + 1] = icnt;
+      s_runs[warp + 1] = iruns;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      s_scan[0] = 0;
+      s_runs[0] = 0;
+      for (int w = 1; w <= 8; ++w) {
+        s_scan[w] += s_scan[w - 1];
+        s_runs[w] += s_runs[w - 1];
+      }
+    }
+    __syncthreads();
+    const int nlines = s_scan[8], nruns = s_runs[8];
+    ok = nlines <= kXlinesMax && nruns <= kXsegMax;
+    if (ok) {
+      int base = s_scan[warp] + icnt - cnt, rbase = s_runs[warp] + iruns - runs; // exclusive prefixes of this thread
+      for (int j = 0; j < per; ++j) {
+        const int w = tid * per + j;
+        if (w < nwords) {
+          const unsigned b = bitmap[w];
+          const unsigned prev = w > 0 ? bitmap[w - 1] >> 31 : 0u;
+          prefix[w] = base;
+          unsigned starts = b & ~((b << 1) | prev);
+          while (starts) { // segment table: first line and rank of every run
+            const int bit = __ffs(starts) - 1;
+            starts &= starts - 1;
+            xd->line[rbase] = lo + 32 * w + bit;
+            xd->off[rbase] = (unsigned short)(base + __popc(b & ((1u << bit) - 1u)));
+            ++rbase;
+          }
+          base += __popc(b);
+        }
+      }
+      if (tid == 0) {
+        xd->nseg = nruns;
+        xd->nlines = nlines;
+        atomicMax(status + 1, nlines);
+      }
+      for (int s = nruns + tid; s < kXsegMax; s += 256) {
+        xd->line[s] = 0;
+        xd->off[s] = 0;
+      }
+      if (tid < 6)
+        xd->pad[tid] = 0;
+      __syncthreads();
+      for (int k = e0 + tid; k < e1; k += 256) {
+        const int c = __ldg(col + k);
+        const int l = (c >> 4) - lo;
+        const int rank = prefix[l >> 5] + __popc(bitmap[l >> 5] & ((1u << (l & 31)) - 1u));
+        lcol[(long long)k - lcol_base] = (unsigned short)((rank << 4) | (c & 15));
+      }
+    }
+  }
+  if (!ok && tid == 0) {
+    xd->nseg = -1;
+    atomicExch(status, 1);
+  }
+}
+
+int analysis_xstage(spmv_b200_plan *p, cudaStream_t stream) {
+  p->xstage = false;
+  // regular matrices only: one row-kernel kind owns every row block, nothing is split, TMA is usable
+  const bool one_kind = p->ntiles > 0 && (p->count[SPMV_B200_KIND_SHORT] == p->ntiles ||
+                                           p->count[SPMV_B200_KIND_MEDIUM] == p->ntiles);
+  if (!one_kind || p->direct || p->nsplit > 0 || !p->uses_tma || p->irregular || p->nnz == 0 ||
+      (p->flags & SPMV_B200_FLAG_NO_XSTAGE))
+    return SPMV_B200_OK;
+  p->lcol_base = p->elem_base & ~7LL; // keeps lcol + (a0 - base) 16-byte aligned for a0 multiple of 8
+  const size_t n16 = (size_t)(p->elem_end - p->lcol_base) + 16;
+  DeviceScratch status;
+  B200_CUDA(status.alloc(2 * sizeof(int)));
+  B200_CUDA(cudaMemsetAsync(status.p, 0, 2 * sizeof(int), stream));
+  cudaError_t e = cudaMalloc(&p->lcol, sizeof(unsigned short) * n16);
+  if (e == cudaSuccess)
+    e = cudaMalloc(&p->xdesc, sizeof(XDesc) * (size_t)p->ntiles);
+  if (e == cudaSuccess)
+    e = cudaMemsetAsync(p->lcol, 0, sizeof(unsigned short) * n16, stream);
+  int h_status[2] = {1, 0};
+  if (e == cudaSuccess) {
+    const size_t smem = sizeof(unsigned int) * (kXspanLinesMax / 32) * 2;
+    k_xstage_build<<<p->ntiles, 256, smem, stream>>>(p->col, p->desc_all, p->ntiles, p->lcol_base, p->lcol, p->xdesc,
+                                                     status.as<int>());
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(h_status, status.p, sizeof(h_status), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess || h_status[0] != 0) { // some row block does not qualify: the plan keeps the gather kernels
+    cudaFree(p->lcol);
+    cudaFree(p->xdesc);
+    p->lcol = nullptr;
+    p->xdesc = nullptr;
+    B200_CUDA(e);
+    return SPMV_B200_OK;
+  }
+  p->xstage = true;
+  p->xlines = h_status[1];
+  p->workspace_bytes += sizeof(unsigned short) * n16 + sizeof(XDesc) * (size_t)p->ntiles;
+  return SPMV_B200_OK;
+}
+
 // descriptors in a caller-given tile order (the fused halo loop walks boundary row blocks first)
 int analysis_gather_descs(const TileDesc *d_all, const int *h_order, int n, TileDesc **d_out, cudaStream_t stream) {
   *d_out = nullptr;

@@ -77,7 +77,7 @@ static int free_plan_arrays(spmv_b200_plan *p) {
       p->desc[k] = nullptr; // alias, freed once below
   void *ptrs[] = {p->tile_row, p->tile_elem, p->tile_split, p->tile_part,  p->tile_maxlen, p->tile_kind, p->list[0],
                   p->list[1],  p->list[2],   p->split_rows, p->partials,   p->desc_all,    p->desc[0],   p->desc[1],
-                  p->desc[2],  p->row_start_bits, p->nz_rows, p->desc_direct};
+                  p->desc[2],  p->row_start_bits, p->nz_rows, p->desc_direct, p->lcol, p->xdesc};
   int rc = SPMV_B200_OK;
   for (void *q : ptrs)
     if (q && cudaFree(q) != cudaSuccess)
@@ -99,6 +99,10 @@ static void reset_plan_arrays(spmv_b200_plan *p) {
   p->partials = nullptr;
   p->row_start_bits = nullptr;
   p->nz_rows = nullptr;
+  p->lcol = nullptr;
+  p->xdesc = nullptr;
+  p->xstage = false;
+  p->xlines = 0;
   p->nsplit = 0;
   p->n_nz_rows = 0;
   p->h_tile_row.clear();
@@ -199,7 +203,13 @@ int spmv_b200_plan_create(spmv_b200_plan **out, int32_t m, int32_t n, int64_t nn
         rc = analysis_run(p, static_cast<cudaStream_t>(stream));
     }
   }
+  // staged-x form for regular matrices (x segments of every row block in shared memory, 16-bit local column indices)
+  if (rc == SPMV_B200_OK && p->nnz > 0 && d_colidx)
+    rc = analysis_xstage(p, static_cast<cudaStream_t>(stream));
+  if (rc == SPMV_B200_OK)
+    rc = kernels_configure_xs(p);
   if (rc != SPMV_B200_OK) {
+    kernels_release(p);
     free_plan_arrays(p);
     delete p;
     return rc;
@@ -638,6 +648,7 @@ int spmv_b200_peer_free(void *d_ptr) {
 int spmv_b200_plan_destroy(spmv_b200_plan *plan) {
   if (!plan)
     return SPMV_B200_OK;
+  kernels_release(plan);
   const int rc = free_plan_arrays(plan);
   delete plan;
   if (rc != SPMV_B200_OK)
@@ -680,6 +691,8 @@ int spmv_b200_plan_get_info(const spmv_b200_plan *p, spmv_b200_plan_info *info) 
   info->gather_lines = p->gather_lines;
   info->smem_bytes = (int64_t)p->smem_bytes;
   info->workspace_bytes = (int64_t)p->workspace_bytes;
+  info->xstage = p->xstage ? 1 : 0;
+  info->xstage_lines = p->xstage ? p->xlines : 0;
   return SPMV_B200_OK;
 }
 
@@ -733,6 +746,14 @@ int spmv_b200_plan_export(spmv_b200_plan *p, int32_t what, void *h_dst, int64_t 
     break;
   case SPMV_B200_EXPORT_TILE_NZBASE:
     bytes = p->direct ? 4 * nt : 0;
+    break;
+  case SPMV_B200_EXPORT_LCOL:
+    src = p->xstage ? p->lcol + (p->elem_base - p->lcol_base) : nullptr;
+    bytes = p->xstage ? 2 * p->nnz : 0;
+    break;
+  case SPMV_B200_EXPORT_XDESC:
+    src = p->xdesc;
+    bytes = p->xstage ? 128 * nt : 0;
     break;
   default:
     set_error("plan_export: unknown array id");

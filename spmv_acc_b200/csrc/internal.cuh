@@ -57,6 +57,23 @@ struct __align__(16) TileDesc {
   int flags;      // bit 0: leading boundary split, bit 1: trailing boundary split
 };
 
+// Staged-x form ("XS") of the row kernels: the entries of x a row block references are brought into shared memory as
+// whole 128-byte lines by TMA, and the block's column indices are stored a second time as 16-bit offsets into that
+// staged copy (plan array `lcol`, 2 bytes per non-zero instead of 4). XDesc lists the runs of consecutive lines
+// ("segments") of one row block: segment s covers lines [line[s], line[s] + off[s+1] - off[s]) of x and lands at line
+// off[s] of the staged copy (off[nseg] = nlines). 128 bytes, one per row block.
+constexpr int kXsegMax = 16;          // segments per row block (a 27-point stencil has 9, a 5-point stencil 3)
+constexpr int kXlinesMax = 256;       // staged lines per row block (32 KB), upper limit
+constexpr int kXspanLinesMax = 65536; // lines between the smallest and the largest column of a row block (bitmap size)
+struct __align__(16) XDesc {
+  int nseg;   // -1: the row block does not qualify
+  int nlines; // staged lines
+  int line[kXsegMax];
+  unsigned short off[kXsegMax];
+  int pad[6];
+};
+static_assert(sizeof(XDesc) == 128, "XDesc is one 128-byte line");
+
 // Rows whose result is also stored into other GPUs' memory (fused halo push of the iterated multi-GPU loop):
 // for row in [row_lo[j], row_hi[j]) the epilogue stores y to dst[j][row] as well (dst is a peer-mapped pointer,
 // already offset so that it is indexed by the shard-local row).
@@ -85,7 +102,12 @@ struct SpmvArgs {
   const int *__restrict__ nz_rows;                 // direct form only
   int read_y;   // 0: beta == 0 and SPMV_B200_FLAG_BETA0_SKIP_Y
   int gather_na; // 1: x gathers use L1::no_allocate
-  int rotate_slots; // MEDIUM kernel: lane groups walk the slots of a round in rotated order (bank conflicts)
+  // staged-x form only
+  const unsigned short *__restrict__ lcol; // 16-bit offsets into the staged x, indexed like col minus lcol_base
+  const XDesc *__restrict__ xdesc;         // by tile id
+  long long lcol_base;
+  int n;        // entries of x (the last line of x may be short)
+  int xcap;     // doubles of shared memory reserved for the staged x
   PushArgs push;
 };
 
@@ -135,10 +157,14 @@ struct spmv_b200_plan {
   int cap = 0;
   size_t smem_bytes = 0;
   size_t persist_bytes = 0, max_window_bytes = 0; // L2 persistence for x (SPMV_B200_FLAG_L2_PERSIST_X)
-  int persistent_grid[3] = {0, 0, 0}; // CTAs of the persistent kernels per tile kind
   int variant_short = 0, variant_medium = 0; // kernel variants (option flag bits 8-11 / 12-15)
-  bool mixed_queue_form = true;              // option flag bit 22 selects the segmented-sum form instead (A-B runs)
   int mixed_threads = 256;                   // CTA size of the MIXED kernel (option flag bits 20-21 override)
+  // staged-x form (regular matrices: every row block references few runs of consecutive entries of x)
+  bool xstage = false;
+  unsigned short *lcol = nullptr;
+  b200::XDesc *xdesc = nullptr;
+  long long lcol_base = 0;
+  int xlines = 0; // largest number of staged lines of any row block
   // device arrays owned by the plan
   int *tile_row = nullptr;
   int *tile_elem = nullptr;
@@ -174,6 +200,7 @@ namespace b200 {
 int analysis_gather_descs(const TileDesc *d_all, const int *h_order, int n, TileDesc **d_out, cudaStream_t stream);
 int analysis_prepare(spmv_b200_plan *p, cudaStream_t stream); // reads rowptr[0], rowptr[m]
 int analysis_run(spmv_b200_plan *p, cudaStream_t stream);
+int analysis_xstage(spmv_b200_plan *p, cudaStream_t stream); // sets p->xstage (and lcol / xdesc / xlines) if it qualifies
 int analysis_row_bins(const spmv_b200_plan *p, unsigned char *d_out, cudaStream_t stream);
 int analysis_tile_col_range(const spmv_b200_plan *p, int *h_min, int *h_max, cudaStream_t stream);
 int shard_bounds_run(int m, long long nnz, const int *d_rowptr, int nshards, int *h_bounds, cudaStream_t stream);
@@ -186,6 +213,8 @@ int coo_to_csr_run(int m, int n, long long nnz, const int *d_row, const int *d_c
 
 // kernels.cu
 int kernels_configure(spmv_b200_plan *p);
+int kernels_configure_xs(spmv_b200_plan *p); // after analysis_xstage
+void kernels_release(spmv_b200_plan *p);     // device-wide state a plan took (L2 carve-out)
 int kernels_launch(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y,
                    cudaStream_t stream, const PushArgs *push = nullptr);
 // tiles [tile_lo, tile_hi) only; the plan must have no split rows (their partial sums cross tile ranges)

@@ -9,6 +9,10 @@
 //                                           consecutive rows, so for banded/stencil matrices the x gathers of a
 //                                           warp fall into 2-3 cache lines.
 //   k_spmv_rows<TMA, true>   MEDIUM tiles : 2^k lanes per row, warp-shuffle segmented sum.
+//   k_spmv_rows<.., XS>      staged-x form of both: the runs of x a row block references are brought into shared memory
+//                                           by TMA as well and addressed through 16-bit local column indices (10 bytes
+//                                           per non-zero from HBM instead of 12, no gathers through L1); regular
+//                                           matrices (stencils, banded) only, decided by the analysis.
 //   k_spmv_mixed<TMA>        MIXED tiles  : rows of any length plus fragments of rows that are split across tiles:
 //                                           products are formed in place in shared memory (one nnz per thread and
 //                                           step), short rows are summed by one thread, long rows by one warp, row
@@ -76,6 +80,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_sr
                : "memory");
 }
 
+__device__ __forceinline__ void tma_bulk_g2s_nohint(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                                    unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __device__ __forceinline__ double ld_stream_f64(const double *p) {
   double v;
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
@@ -89,9 +101,20 @@ __device__ __forceinline__ int ld_stream_s32(const int *p) {
 }
 
 // x gather through the read-only path; `na` selects L1::no_allocate (the line is not kept in L1)
+// x gather that asks L2 to keep the line (evict_last): tuning bit 27, for matrices whose x does not quite fit the L2
+__device__ __forceinline__ double ld_x_evict_last(const double *p) {
+  unsigned long long pol;
+  double v;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 __device__ __forceinline__ double gather_x(const double *__restrict__ x, int c, int na) {
   if (na == 2) // experiment: no gather at all (wrong results; isolates the cost of the x traffic)
     return 1.0;
+  if (na == 3)
+    return ld_x_evict_last(x + c);
   if (na)
     return ld_stream_f64(x + c);
   return __ldg(x + c);
@@ -152,27 +175,62 @@ __device__ __forceinline__ void tile_issue_loads(const SpmvArgs &a, int a0, int 
   }
 }
 
-// TMA part of tile_issue_loads for an already initialised barrier (persistent kernels)
-__device__ __forceinline__ void tile_issue_tma(const SpmvArgs &a, int a0, int e1, double *sval, int *scol,
-                                               unsigned long long *bar, int tid) {
+// Staged-x form: value, the 16-bit local column indices and the segments of x the tile references, all by TMA
+// (a0 = elem_begin & ~7: 16-byte alignment of the 2-byte index stream). Warp 0 issues the copies: lane s brings
+// segment s of x (whole 128-byte lines; only the very last line of x can be short), lane 0 the two streams. The
+// transaction count is posted by lane 0 in the same operation as the barrier's only arrival, so the phase cannot
+// complete before every copy has been accounted for, whatever the order in which the lanes issue.
+__device__ __forceinline__ void tile_issue_loads_xs(const SpmvArgs &a, int tile, int a0, int e1, double *sval,
+                                                    unsigned short *slcol, double *sx, unsigned long long *bar,
+                                                    int tid) {
   const int span = e1 - a0;
+  if (tid == 0)
+    mbar_init(bar, 1);
+  __syncthreads();
   const long long avail = a.nnz - (long long)a0;
-  int cnt = (span + 3) & ~3;
+  int cnt = (span + 7) & ~7;
   if ((long long)cnt > avail)
-    cnt = (int)(avail & ~3LL);
-  if (tid == 0) {
-    if (cnt > 0) {
-      const unsigned long long pol = policy_evict_first();
-      mbar_arrive_expect_tx(bar, (uint32_t)cnt * 12u);
-      tma_bulk_g2s(sval, a.val + a0, (uint32_t)cnt * 8u, bar, pol);
-      tma_bulk_g2s(scol, a.col + a0, (uint32_t)cnt * 4u, bar, pol);
-    } else {
-      mbar_arrive(bar);
+    cnt = (int)(avail & ~7LL);
+  if (tid < 32) {
+    const XDesc *__restrict__ xd = a.xdesc + tile;
+    const int nseg = __ldg(&xd->nseg);
+    unsigned int xbytes = 0;
+    int line = 0, off = 0;
+    if (tid < nseg) {
+      line = __ldg(&xd->line[tid]);
+      off = (int)__ldg(&xd->off[tid]);
+      const int end = tid + 1 < nseg ? (int)__ldg(&xd->off[tid + 1]) : __ldg(&xd->nlines);
+      long long elems = (long long)(end - off) * 16;
+      const long long left = (long long)a.n - (long long)line * 16;
+      if (elems > left)
+        elems = left;
+      xbytes = (unsigned int)(elems & ~1LL) * 8u;
+      if (elems & 1) // n is odd and this is the last entry of x: a 16-byte copy would read past the vector
+        sx[(long long)off * 16 + elems - 1] = __ldg(a.x + (long long)line * 16 + elems - 1);
     }
+    unsigned int total = xbytes;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      total += __shfl_xor_sync(0xffffffffu, total, o);
+    total += (unsigned int)cnt * 10u;
+    if (tid == 0) {
+      if (total > 0)
+        mbar_arrive_expect_tx(bar, total);
+      else
+        mbar_arrive(bar);
+    }
+    __syncwarp();
+    if (tid == 0 && cnt > 0) {
+      const unsigned long long pol = policy_evict_first(); // the streams are read exactly once
+      tma_bulk_g2s(sval, a.val + a0, (uint32_t)cnt * 8u, bar, pol);
+      tma_bulk_g2s(slcol, a.lcol + ((long long)a0 - a.lcol_base), (uint32_t)cnt * 2u, bar, pol);
+    }
+    if (xbytes > 0) // x is what neighbouring row blocks read again: default L2 policy
+      tma_bulk_g2s_nohint(sx + (long long)off * 16, a.x + (long long)line * 16, xbytes, bar);
   }
   for (int i = cnt + tid; i < span; i += kThreads) {
     sval[i] = ld_stream_f64(a.val + a0 + i);
-    scol[i] = ld_stream_s32(a.col + a0 + i);
+    slcol[i] = __ldg(a.lcol + ((long long)a0 - a.lcol_base) + i);
   }
 }
 
@@ -190,13 +248,15 @@ __device__ __forceinline__ void emit_y(double *__restrict__ y, const PushArgs &p
 // ---------------------------------------------------------------------------------------------------------------
 // SHORT (VEC = false) and MEDIUM (VEC = true) tiles: every owned row lies completely inside the tile
 // ---------------------------------------------------------------------------------------------------------------
-// W = x gathers issued back to back per row and round, R = rows handled by one lane group at a time. All W*R gathers
-// of a round are in flight before the first FMA, and y is fetched before the tile has landed, so that a CTA exposes
-// one round trip to memory per phase (tile, gathers) instead of one per batch of four elements.
-// Rows of one tile whose value / colindex are (being) staged in sval / scol; waits for the TMA phase `parity` of `bar`.
-template <bool TMA, bool VEC, int W, int R, bool ROT = false>
+// W = x gathers issued back to back per row and round. All W gathers of a round are in flight before the first FMA,
+// and y is fetched before the tile has landed, so that a CTA exposes one round trip to memory per phase (tile,
+// gathers) instead of one per batch of four elements. XS: x comes from the staged copy in shared memory (sx) through
+// the 16-bit local indices (slcol) instead of being gathered through L1.
+// Rows of one tile whose value / colindex are (being) staged in shared memory; waits for the TMA phase `parity` of `bar`.
+template <bool TMA, bool VEC, int W, bool ROT, bool XS>
 __device__ __forceinline__ void rows_tile(const SpmvArgs &a, const double *__restrict__ sval,
-                                          const int *__restrict__ scol, int *__restrict__ srow,
+                                          const int *__restrict__ scol, const unsigned short *__restrict__ slcol,
+                                          const double *__restrict__ sx, int *__restrict__ srow,
                                           unsigned long long *bar, uint32_t parity, int r0, int nrows, int a0, int e0,
                                           int e1, int tid) {
   int lv = 0; // log2(lanes per row)
@@ -212,12 +272,7 @@ __device__ __forceinline__ void rows_tile(const SpmvArgs &a, const double *__res
   const int l = tid & (V - 1);
 
   // y of the first pass, requested while the tile is still in flight
-  double ypre[R];
-#pragma unroll
-  for (int q = 0; q < R; ++q) {
-    const int r = q * G + g;
-    ypre[q] = (a.read_y && l == 0 && r < nrows && r < kRowChunk) ? a.y[r0 + r] : 0.0;
-  }
+  const double ypre = (a.read_y && l == 0 && g < nrows && g < kRowChunk) ? a.y[r0 + g] : 0.0;
 
   for (int cb = 0;; cb += kRowChunk) {
     int nr = nrows - cb;
@@ -231,95 +286,92 @@ __device__ __forceinline__ void rows_tile(const SpmvArgs &a, const double *__res
     if (TMA && cb == 0)
       mbar_wait(bar, parity);
 
-    for (int rb = 0; rb < nr; rb += R * G) {
-      int k[R], e[R];
-      double sum[R], yv[R];
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        const int r = rb + q * G + g;
-        const bool act = r < nr;
-        k[q] = act ? srow[r] - a0 + l : 0;
-        e[q] = act ? srow[r + 1] - a0 : 0;
-        sum[q] = 0.0;
-        if (cb == 0 && rb == 0)
-          yv[q] = ypre[q];
-        else
-          yv[q] = (a.read_y && act && l == 0) ? a.y[r0 + cb + r] : 0.0;
-      }
+    for (int rb = 0; rb < nr; rb += G) {
+      const int r = rb + g;
+      const bool act = r < nr;
+      int k = act ? srow[r] - a0 + l : 0;
+      const int e = act ? srow[r + 1] - a0 : 0;
+      double sum = 0.0;
+      const double yv = (cb == 0 && rb == 0) ? ypre : ((a.read_y && act && l == 0) ? a.y[r0 + cb + r] : 0.0);
       // Irregular-gather plans: lane groups of a warp walk the W slots of a round in rotated order. With rows whose
       // length is a multiple of 16 (32 nnz per row in C3) every group would otherwise read the same shared-memory banks
       // in the same step (ncu: 8-way conflicts, 130 M extra wavefronts on C3). The rotation depends only on the
       // group's position in the tile.
       int rot = ROT ? (g % W) * V : 0; // offset of the first slot this group reads in a round
-      for (;;) {
-        double xv[R][W];
+      while (k < e) {
+        double xv[W];
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-#pragma unroll
-          for (int j = 0; j < W; ++j) {
-            int kk = k[q] + j * V;
-            if (ROT) {
-              kk += rot;
-              kk -= (kk >= k[q] + W * V) ? W * V : 0; // wrap around inside the round
-            }
-            xv[q][j] = (kk < e[q]) ? gather_x(a.x, scol[kk], a.gather_na) : 0.0;
+        for (int j = 0; j < W; ++j) {
+          int kk = k + j * V;
+          if (ROT) {
+            kk += rot;
+            kk -= (kk >= k + W * V) ? W * V : 0; // wrap around inside the round
           }
+          if (XS)
+            xv[j] = (kk < e) ? sx[slcol[kk]] : 0.0;
+          else
+            xv[j] = (kk < e) ? gather_x(a.x, scol[kk], a.gather_na) : 0.0;
         }
         if (ROT)
           asm volatile("" : "+r"(rot)); // recompute the indices below instead of keeping W of them in registers
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-#pragma unroll
-          for (int j = 0; j < W; ++j) {
-            int kk = k[q] + j * V;
-            if (ROT) {
-              kk += rot;
-              kk -= (kk >= k[q] + W * V) ? W * V : 0;
-            }
-            if (kk < e[q])
-              sum[q] = fma(sval[kk], xv[q][j], sum[q]);
+        for (int j = 0; j < W; ++j) {
+          int kk = k + j * V;
+          if (ROT) {
+            kk += rot;
+            kk -= (kk >= k + W * V) ? W * V : 0;
           }
+          if (kk < e)
+            sum = fma(sval[kk], xv[j], sum);
         }
-        bool more = false;
-#pragma unroll
-        for (int q = 0; q < R; ++q) {
-          k[q] += W * V;
-          more |= k[q] < e[q];
-        }
-        if (!more)
-          break;
+        k += W * V;
       }
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        if (VEC) {
-          for (int off = V >> 1; off > 0; off >>= 1)
-            sum[q] += __shfl_down_sync(0xffffffffu, sum[q], off, V);
-        }
-        const int r = rb + q * G + g;
-        if (r < nr && l == 0) // cli/verification.cpp:64  y[i] = alpha * y0 + beta * y[i]
-          emit_y(a.y, a.push, r0 + cb + r, a.alpha * sum[q] + a.beta * yv[q]);
+      if (VEC) {
+        for (int off = V >> 1; off > 0; off >>= 1)
+          sum += __shfl_down_sync(0xffffffffu, sum, off, V);
       }
+      if (act && l == 0) // cli/verification.cpp:64  y[i] = alpha * y0 + beta * y[i]
+        emit_y(a.y, a.push, r0 + cb + r, a.alpha * sum + a.beta * yv);
     }
     if (cb + kRowChunk >= nrows)
       break;
   }
 }
 
-template <bool TMA, bool VEC, int W, int R, bool ROT = false>
-__global__ void __launch_bounds__(kThreads) k_spmv_rows(const SpmvArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long bar;
-  double *sval = reinterpret_cast<double *>(smem_raw);
-  int *scol = reinterpret_cast<int *>(sval + a.cap);
-  int *srow = scol + a.cap;
-
+// one CTA = one tile: shared-memory layout, loads, rows
+//   gather form: sval[cap] | scol[cap] (int32) | srow[kRowChunk + 1]
+//   staged-x   : sval[cap] | sx[xcap] | srow[kRowChunk + 1] | slcol[cap] (uint16)
+template <bool TMA, bool VEC, int W, bool ROT, bool XS>
+__device__ __forceinline__ void rows_cta(const SpmvArgs &a, unsigned char *smem_raw, unsigned long long *bar) {
   const int tid = threadIdx.x;
   const TileDesc d = load_desc(a.desc, blockIdx.x);
-  const int r0 = d.r0, r1 = d.r1, e0 = d.e0, e1 = d.e1;
-  const int a0 = e0 & ~3;
+  double *sval = reinterpret_cast<double *>(smem_raw);
+  if (XS) {
+    double *sx = sval + a.cap;
+    int *srow = reinterpret_cast<int *>(sx + a.xcap);
+    unsigned short *slcol = reinterpret_cast<unsigned short *>(srow + (kRowChunk + 4));
+    const int a0 = d.e0 & ~7;
+    tile_issue_loads_xs(a, d.tile, a0, d.e1, sval, slcol, sx, bar, tid);
+    rows_tile<true, VEC, W, false, true>(a, sval, nullptr, slcol, sx, srow, bar, 0u, d.r0, d.r1 - d.r0, a0, d.e0, d.e1,
+                                         tid);
+  } else {
+    int *scol = reinterpret_cast<int *>(sval + a.cap);
+    int *srow = scol + a.cap;
+    const int a0 = d.e0 & ~3;
+    tile_issue_loads<TMA>(a, a0, d.e0, d.e1, sval, scol, bar, tid);
+    rows_tile<TMA, VEC, W, ROT, false>(a, sval, scol, nullptr, nullptr, srow, bar, 0u, d.r0, d.r1 - d.r0, a0, d.e0, d.e1,
+                                       tid);
+  }
+}
 
-  tile_issue_loads<TMA>(a, a0, e0, e1, sval, scol, &bar, tid);
-  rows_tile<TMA, VEC, W, R, ROT>(a, sval, scol, srow, &bar, 0u, r0, r1 - r0, a0, e0, e1, tid);
+// register budgets: 40 for MEDIUM and for SHORT with 8 gathers per round, 32 for SHORT with <= 6; the staged-x MEDIUM
+// kernel is limited to 4-5 resident CTAs by its shared memory and takes 48 (RB = 5) unless tuning bit 24 asks for 40
+constexpr int rows_min_blocks(bool vec, int w, bool xs, int rb) { return rb ? rb : ((xs && vec) ? 5 : ((vec || w > 6) ? 6 : 8)); }
+template <bool TMA, bool VEC, int W, bool ROT = false, bool XS = false, int RB = 0>
+__global__ void __launch_bounds__(kThreads, rows_min_blocks(VEC, W, XS, RB)) k_spmv_rows(const SpmvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bar;
+  rows_cta<TMA, VEC, W, ROT, XS>(a, smem_raw, &bar);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -339,30 +391,30 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
-// one thread: blocks until every neighbour's flag has reached the epoch; returns the epoch
-__device__ __forceinline__ unsigned int halo_wait(const HaloSync &h) {
+// one thread: blocks until every neighbour's flag has reached the epoch
+__device__ __forceinline__ void halo_wait(const HaloSync &h) {
   const unsigned int k = ld_volatile_u32(h.state);
   if (k == 0u)
-    return k;
+    return;
   const unsigned long long t0 = global_timer_ns();
   for (int j = 0; j < h.n_neigh; ++j) {
     while (ld_volatile_u32(h.wait[j]) < k) {
       if (ld_volatile_u32(h.state + 2) != 0u)
-        return k; // another CTA has already given up
+        return; // another CTA has already given up
       if (h.timeout_ns != 0ull && global_timer_ns() - t0 > h.timeout_ns) {
         atomicCAS(h.state + 2, 0u, 0x80000000u | k); // sticky: the host reads it in spmv_b200_halo_loop_sync
-        return k;
+        return;
       }
       __nanosleep(64);
     }
   }
   __threadfence_system(); // the neighbours' pushed rows are ordered before their flag
-  return k;
 }
 
 // one thread, after all stores of the boundary row blocks: publish epoch + 1 to the neighbours (never after a timeout:
 // a rank that multiplied a stale halo must not hand its rows on as if they were good; its neighbours then time out too)
-__device__ __forceinline__ void halo_signal(const HaloSync &h, unsigned int k) {
+__device__ __forceinline__ void halo_signal(const HaloSync &h) {
+  const unsigned int k = ld_volatile_u32(h.state); // the epoch only changes here
   __threadfence_system();
   st_volatile_u32(h.state, k + 1u);
   if (ld_volatile_u32(h.state + 2) == 0u)
@@ -370,87 +422,36 @@ __device__ __forceinline__ void halo_signal(const HaloSync &h, unsigned int k) {
       st_volatile_u32(h.signal[j], k + 1u);
 }
 
-template <bool VEC, int W, int R>
-__global__ void __launch_bounds__(kThreads) k_spmv_rows_halo(const SpmvArgs a, const HaloSync h) {
+// The flag protocol sits in front of and behind the row kernel proper, where nothing of it is live, so the body keeps
+// the register budget of k_spmv_rows (without that the compiler spent 55 registers and cost the kernel a resident
+// CTA per SM: 3.63 ms against 3.30 ms per iteration on C5). The wait is satisfied long before it is reached in the
+// steady state (the neighbour raised its flag early in ITS previous iteration), so waiting before the TMA copies are
+// issued costs the boundary row blocks (a few percent of the CTAs) a few L2 round trips. In the staged-x form the wait
+// has to come first anyway: the x segments the TMA copies read include the halo entries.
+template <bool VEC, int W, bool XS>
+__global__ void __launch_bounds__(kThreads, rows_min_blocks(VEC, W, XS, 0)) k_spmv_rows_halo(const SpmvArgs a, const HaloSync h) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
-  __shared__ unsigned int s_epoch;
-  double *sval = reinterpret_cast<double *>(smem_raw);
-  int *scol = reinterpret_cast<int *>(sval + a.cap);
-  int *srow = scol + a.cap;
-
-  const int tid = threadIdx.x;
-  const TileDesc d = load_desc(a.desc, blockIdx.x);
-  const int a0 = d.e0 & ~3;
-  const bool boundary = (int)blockIdx.x < h.n_boundary;
-
-  tile_issue_loads<true>(a, a0, d.e0, d.e1, sval, scol, &bar, tid); // value / colindex do not depend on the halo
-  if (boundary && tid == 0)
-    s_epoch = halo_wait(h); // rows_tile starts with a CTA barrier, in front of the first gather of x
-  rows_tile<true, VEC, W, R>(a, sval, scol, srow, &bar, 0u, d.r0, d.r1 - d.r0, a0, d.e0, d.e1, tid);
-  if (boundary) {
+  if ((int)blockIdx.x < h.n_boundary) {
+    if (threadIdx.x == 0)
+      halo_wait(h);
+    __syncthreads();
+  }
+  rows_cta<true, VEC, W, false, XS>(a, smem_raw, &bar);
+  if ((int)blockIdx.x < h.n_boundary) {
     __syncthreads(); // every row of this block has been stored (locally and into the neighbours' buffers)
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
       __threadfence_system();
       if (atomicAdd(h.state + 1, 1u) == (unsigned int)h.n_boundary - 1u) { // last boundary row block of the iteration
         st_volatile_u32(h.state + 1, 0u);
-        halo_signal(h, s_epoch);
+        halo_signal(h);
       }
     }
   }
 }
 
-__global__ void k_halo_wait(const HaloSync h) { (void)halo_wait(h); }
-__global__ void k_halo_signal(const HaloSync h) { halo_signal(h, ld_volatile_u32(h.state)); }
-
-// Persistent form: gridDim.x CTAs walk the tile list with a two-stage ring of shared-memory tiles. The TMA copies
-// of tile i+1 are issued before tile i is processed, so the stream of value / colindex keeps flowing while the CTA
-// gathers x (the gather phase is bound by L1 wavefronts, the stream by HBM: the two overlap instead of alternating).
-template <bool VEC, int W, int R>
-__global__ void __launch_bounds__(kThreads) k_spmv_rows_persistent(const SpmvArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long bar[2];
-  double *sval0 = reinterpret_cast<double *>(smem_raw);
-  int *scol0 = reinterpret_cast<int *>(sval0 + a.cap);
-  double *sval1 = reinterpret_cast<double *>(scol0 + a.cap);
-  int *scol1 = reinterpret_cast<int *>(sval1 + a.cap);
-  int *srow = scol1 + a.cap;
-
-  const int tid = threadIdx.x;
-  int i = blockIdx.x;
-  if (i >= a.ntiles)
-    return;
-  if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-  }
-  __syncthreads();
-
-  TileDesc d = load_desc(a.desc, i);
-  int r0 = d.r0, r1 = d.r1, e0 = d.e0, e1 = d.e1;
-  tile_issue_tma(a, e0 & ~3, e1, sval0, scol0, &bar[0], tid);
-
-  for (int it = 0; i < a.ntiles; i += gridDim.x, ++it) {
-    const int stage = it & 1;
-    const int inext = i + (int)gridDim.x;
-    int r0n = 0, r1n = 0, e0n = 0, e1n = 0;
-    if (inext < a.ntiles) { // refill the other stage: every thread left it at the barrier that ended the last iteration
-      d = load_desc(a.desc, inext);
-      r0n = d.r0;
-      r1n = d.r1;
-      e0n = d.e0;
-      e1n = d.e1;
-      tile_issue_tma(a, e0n & ~3, e1n, stage ? sval0 : sval1, stage ? scol0 : scol1, &bar[stage ^ 1], tid);
-    }
-    rows_tile<true, VEC, W, R>(a, stage ? sval1 : sval0, stage ? scol1 : scol0, srow, &bar[stage],
-                               (uint32_t)((it >> 1) & 1), r0, r1 - r0, e0 & ~3, e0, e1, tid);
-    __syncthreads(); // the stage and srow may be overwritten from here on
-    r0 = r0n;
-    r1 = r1n;
-    e0 = e0n;
-    e1 = e1n;
-  }
-}
+__global__ void k_halo_wait(const HaloSync h) { halo_wait(h); }
+__global__ void k_halo_signal(const HaloSync h) { halo_signal(h); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // MIXED tiles
@@ -638,226 +639,6 @@ __global__ void __launch_bounds__(NT) k_spmv_mixed(const SpmvArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// MIXED tiles, segmented-sum form (option bit 22): cost per non-zero independent of the row-length distribution
-// ---------------------------------------------------------------------------------------------------------------
-// 1. products: thread `tid` forms the products of elements tid, tid + NT, ... (consecutive lanes gather for consecutive
-//    elements, all 8 gathers of a thread in flight before the first multiply) and writes them back in place with an
-//    XOR swizzle inside groups of 8, so that phase 2 reads 8 consecutive products per thread without bank conflicts.
-//    Elements of row fragments (rows split across tiles) are accumulated in registers instead and reduced CTA-wide
-//    into `partials` for the fix-up kernel.
-// 2. segmented sum: thread g owns the 8 consecutive products of group g. Rows that begin and end inside the group are
-//    finished by the thread alone; the piece in front of the first row end ("head") needs the sum of the open pieces
-//    of the preceding threads, which is a segmented scan (warp shuffles, then the 8 warp aggregates in order). The
-//    order of every addition is fixed by the tile geometry: results are bitwise reproducible.
-// 3. y: beta*y0 of the owned rows is staged in shared memory while the tile is in flight, each row's alpha*sum is
-//    added by the unique thread that finishes it, and the chunk is stored with coalesced writes.
-// Analogue of the reference's merge-path reduction (benchmark/merge-path/merge_path_reduction.h:80-136, block-wide
-// reduce-by-key) without its per-element binary search: one search per 8 elements.
-__device__ __forceinline__ int swz8(int i) { return i ^ ((i >> 4) & 7); }
-
-template <bool TMA, int NT>
-__global__ void __launch_bounds__(NT, 1536 / NT) k_spmv_seg(const SpmvArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long bar;
-  __shared__ double sfrag[2][NT / 32];
-  __shared__ double swv[NT / 32];
-  __shared__ int swf[NT / 32];
-  double *sval = reinterpret_cast<double *>(smem_raw);
-  double *sy = sval + a.cap;
-  int *scol = reinterpret_cast<int *>(sy + kRowChunk);
-  int *srow = scol + a.cap;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const TileDesc d = load_desc(a.desc, blockIdx.x);
-  const int t = d.tile;
-  const int r0 = d.r0, r1 = d.r1, e0 = d.e0, e1 = d.e1;
-  const int a0 = e0 & ~3;
-  const bool split_begin = (d.flags & 1) != 0;
-  const bool split_end = (d.flags & 2) != 0;
-  const bool has_tail = split_end && (r1 > r0); // the last owned row continues in the next tile
-  const int nrows = (r1 - r0) - (has_tail ? 1 : 0);
-
-  tile_issue_loads<TMA, NT>(a, a0, e0, e1, sval, scol, &bar, tid);
-  // while the tile is in flight: row pointers (as shared-memory indices) and beta*y0 of the first chunk of rows
-  {
-    const int nr0 = nrows < kRowChunk ? nrows : kRowChunk;
-    for (int i = tid; i <= nr0; i += NT)
-      srow[i] = __ldg(a.rowptr + r0 + i) - a0;
-    for (int i = tid; i < nr0; i += NT)
-      sy[i] = a.read_y ? a.beta * a.y[r0 + i] : 0.0; // cli/verification.cpp:64: y is read even when beta == 0
-  }
-  __syncthreads();
-  if (TMA)
-    mbar_wait(&bar, 0);
-
-  const int beg = e0 - a0, end = e1 - a0;
-  const int hend = split_begin ? d.head_end - a0 : beg; // head fragment [beg, hend): row r0-1 began in an earlier tile
-  const int tbeg = has_tail ? d.tail_start - a0 : end;  // tail fragment [tbeg, end): row r1-1 continues
-  double hacc = 0.0, tacc = 0.0;
-  for (int base = tid; base - lane < end; base += 8 * NT) { // warp-uniform trip count (there is a __syncwarp inside)
-    int c[8];
-    double xv[8], v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = base + j * NT;
-      c[j] = (i >= beg && i < end) ? scol[i] : -1;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      xv[j] = (c[j] >= 0) ? gather_x(a.x, c[j], a.gather_na) : 0.0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      v[j] = (c[j] >= 0) ? sval[base + j * NT] : 0.0;
-    __syncwarp(); // every lane has read its values before any lane overwrites a slot of the same group
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = base + j * NT;
-      if (c[j] >= 0) {
-        const double pr = v[j] * xv[j];
-        if (i < hend)
-          hacc += pr;
-        else if (i >= tbeg)
-          tacc += pr;
-        else
-          sval[swz8(i)] = pr; // the 8 slots of a group are read and written by the same warp instruction
-      }
-    }
-  }
-  if (split_begin || has_tail) { // CTA-uniform
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      hacc += __shfl_xor_sync(0xffffffffu, hacc, off);
-      tacc += __shfl_xor_sync(0xffffffffu, tacc, off);
-    }
-    if (lane == 0) {
-      sfrag[0][warp] = hacc;
-      sfrag[1][warp] = tacc;
-    }
-  }
-  __syncthreads();
-  if ((split_begin || has_tail) && tid == 0) {
-    double h = 0.0, tl = 0.0;
-#pragma unroll
-    for (int w = 0; w < NT / 32; ++w) {
-      h += sfrag[0][w];
-      tl += sfrag[1][w];
-    }
-    if (split_begin)
-      a.partials[2 * (size_t)t] = h;
-    if (has_tail)
-      a.partials[2 * (size_t)t + 1] = tl;
-  }
-
-  for (int cb = 0; cb < nrows; cb += kRowChunk) {
-    int nr = nrows - cb;
-    if (nr > kRowChunk)
-      nr = kRowChunk;
-    if (cb > 0) {
-      __syncthreads(); // the stores of the previous chunk have read sy
-      for (int i = tid; i <= nr; i += NT)
-        srow[i] = __ldg(a.rowptr + r0 + cb + i) - a0;
-      for (int i = tid; i < nr; i += NT)
-        sy[i] = a.read_y ? a.beta * a.y[r0 + cb + i] : 0.0;
-      __syncthreads();
-    }
-    const int lo = srow[0], hi = srow[nr]; // products of the complete rows of this chunk
-    const int g0 = lo >> 3;
-    const int ngroups = hi > lo ? ((hi + 7) >> 3) - g0 : 0;
-    double cv = 0.0; // open piece carried over from the previous round of groups
-    for (int gb = 0; gb < ngroups; gb += NT) {
-      const int g = g0 + gb + tid;
-      const int b = 8 * g > lo ? 8 * g : lo, e = 8 * g + 8 < hi ? 8 * g + 8 : hi;
-      bool f = false; // this group contains a row end
-      double head = 0.0, acc = 0.0;
-      int hrow = 0;
-      if (b < e) {
-        int r = 0, rh = nr; // row that owns element b: the last r with srow[r] <= b (empty rows in front are skipped)
-        while (rh - r > 1) {
-          const int mid = (r + rh) >> 1;
-          if (srow[mid] <= b)
-            r = mid;
-          else
-            rh = mid;
-        }
-        int rend = srow[r + 1];
-        const int sw = (g >> 1) & 7;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int idx = 8 * g + k;
-          if (idx >= b && idx < e) {
-            acc += sval[8 * g + (k ^ sw)];
-            if (idx + 1 == rend) {
-              if (!f) {
-                f = true;
-                head = acc;
-                hrow = r;
-              } else {
-                sy[r] = fma(a.alpha, acc, sy[r]); // the row began and ended inside this group
-              }
-              acc = 0.0;
-              if (++r < nr) {
-                rend = srow[r + 1];
-                if (rend == idx + 1) { // empty rows follow: continue with the last row that starts at idx + 1
-                  rh = nr;
-                  while (rh - r > 1) {
-                    const int mid = (r + rh) >> 1;
-                    if (srow[mid] <= idx + 1)
-                      r = mid;
-                    else
-                      rh = mid;
-                  }
-                  rend = srow[r + 1];
-                }
-              }
-            }
-          }
-        }
-      }
-      // segmented inclusive scan of (f, open piece) over the lanes; the piece of a lane with a row end restarts the sum
-      double v = acc;
-      int ff = f ? 1 : 0;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const double vv = __shfl_up_sync(0xffffffffu, v, off);
-        const int fo = __shfl_up_sync(0xffffffffu, ff, off);
-        if (lane >= off) {
-          if (!ff)
-            v = vv + v;
-          ff |= fo;
-        }
-      }
-      double ev = __shfl_up_sync(0xffffffffu, v, 1);
-      int ef = __shfl_up_sync(0xffffffffu, ff, 1);
-      if (lane == 0) {
-        ev = 0.0;
-        ef = 0;
-      }
-      if (lane == 31) {
-        swv[warp] = v;
-        swf[warp] = ff;
-      }
-      __syncthreads();
-      double wv = cv; // open piece in front of this warp: earlier rounds, then the aggregates of the warps before it
-      for (int w = 0; w < warp; ++w)
-        wv = swf[w] ? swv[w] : wv + swv[w];
-      if (f)
-        sy[hrow] = fma(a.alpha, (ef ? ev : wv + ev) + head, sy[hrow]);
-      if (gb + NT < ngroups) { // another round follows: carry the open piece of the whole CTA
-        double nv = cv;
-#pragma unroll
-        for (int w = 0; w < NT / 32; ++w)
-          nv = swf[w] ? swv[w] : nv + swv[w];
-        __syncthreads(); // swv / swf are rewritten by the next round
-        cv = nv;
-      }
-    }
-    __syncthreads();
-    for (int i = tid; i < nr; i += NT)
-      emit_y(a.y, a.push, r0 + cb + i, sy[i]);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // Direct form: one warp per row block, no shared memory (matrices whose x gathers do not coalesce across rows)
 // ---------------------------------------------------------------------------------------------------------------
 // A gather in flight holds a 128-byte line of L1, and L1 is what the shared-memory carve-out leaves of the 256 KB
@@ -970,9 +751,15 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmv_warp(const SpmvArgs a) 
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         c[j] = (unsigned)(i0 + 32 * j - e0) < span ? ld_cs_s32(a.col + i0 + 32 * j) : -1;
+      if (a.gather_na == 3) { // (uniform) tuning bit 27: L2 evict_last on the gathers
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        p[j] = c[j] >= 0 ? ld_nc_f64(a.x + c[j]) : 0.0;
+        for (int j = 0; j < 4; ++j)
+          p[j] = c[j] >= 0 ? ld_x_evict_last(a.x + c[j]) : 0.0;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          p[j] = c[j] >= 0 ? ld_nc_f64(a.x + c[j]) : 0.0;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -1082,58 +869,71 @@ static int cap_for(const spmv_b200_plan *p, int kind) {
   return p->T + (kind == SPMV_B200_KIND_SHORT ? ((p->short_max + 3) & ~3) : p->medium_max) + 8;
 }
 
-static size_t smem_for(const spmv_b200_plan *p, int kind, bool persistent = false) {
+static size_t smem_for(const spmv_b200_plan *p, int kind) {
   const int cap = cap_for(p, kind);
-  size_t b = (size_t)cap * 12 * (persistent ? 2 : 1) + sizeof(int) * (kRowChunk + 1);
-  if (kind == SPMV_B200_KIND_MIXED) { // segmented form: beta*y0 of a row chunk; queue form (tuning bit 22): two row queues
-    const size_t seg = sizeof(double) * kRowChunk, queues = 2 * sizeof(int) * ((size_t)cap / (kSerialMax + 1) + 8);
-    b += seg > queues ? seg : queues;
-  }
+  size_t b = (size_t)cap * 12 + sizeof(int) * (kRowChunk + 1);
+  if (kind == SPMV_B200_KIND_MIXED) // two row queues
+    b += 2 * sizeof(int) * ((size_t)cap / (kSerialMax + 1) + 8);
+  return (b + 15) & ~(size_t)15;
+}
+
+// staged-x form: the streams start at an element index that is a multiple of 8 (16-byte alignment of the 2-byte
+// indices), hence 8 more elements of slack; sx holds the plan's largest set of lines
+static int xs_cap_for(const spmv_b200_plan *p, int kind) { return cap_for(p, kind) + 8; }
+static int xs_xcap(const spmv_b200_plan *p) { return 16 * ((p->xlines + 7) & ~7); }
+static size_t xs_smem_for(const spmv_b200_plan *p, int kind) {
+  const size_t b = (size_t)xs_cap_for(p, kind) * 10 + sizeof(double) * (size_t)xs_xcap(p) + sizeof(int) * (kRowChunk + 4);
   return (b + 15) & ~(size_t)15;
 }
 
 typedef void (*RowsKernel)(const SpmvArgs);
+typedef void (*HaloKernel)(const SpmvArgs, const HaloSync);
 struct RowsVariant {
-  RowsKernel tma, plain, persistent;
+  RowsKernel tma, plain; // tiles by TMA / by plain loads (misaligned value / colindex)
+  RowsKernel xs;         // staged-x form (nullptr: not built for this variant)
+  RowsKernel xs40;       // the same with a 40-register budget (tuning bit 24; nullptr: same as xs)
+  HaloKernel halo, halo_xs;
   const char *name;
 };
-// variant tables (index = option bits, 0 = default); every entry is a separate instantiation of k_spmv_rows
+// variant tables (index = option bits, 0 = default); every entry is a separate instantiation of the row kernels
 static const RowsVariant kShortVariants[] = {
-    {k_spmv_rows<true, false, 6, 1>, k_spmv_rows<false, false, 6, 1>, k_spmv_rows_persistent<false, 6, 1>, "W6R1"},
-    {k_spmv_rows<true, false, 8, 1>, k_spmv_rows<false, false, 8, 1>, k_spmv_rows_persistent<false, 8, 1>, "W8R1"},
-    {k_spmv_rows<true, false, 4, 1>, k_spmv_rows<false, false, 4, 1>, k_spmv_rows_persistent<false, 4, 1>, "W4R1"},
-    {k_spmv_rows<true, false, 4, 2>, k_spmv_rows<false, false, 4, 2>, k_spmv_rows_persistent<false, 4, 2>, "W4R2"},
-    {k_spmv_rows<true, false, 8, 2>, k_spmv_rows<false, false, 8, 2>, k_spmv_rows_persistent<false, 8, 2>, "W8R2"},
+    {k_spmv_rows<true, false, 6>, k_spmv_rows<false, false, 6>, k_spmv_rows<true, false, 6, false, true>, nullptr,
+     k_spmv_rows_halo<false, 6, false>, k_spmv_rows_halo<false, 6, true>, "W6"},
+    {k_spmv_rows<true, false, 8>, k_spmv_rows<false, false, 8>, k_spmv_rows<true, false, 8, false, true>, nullptr,
+     k_spmv_rows_halo<false, 8, false>, k_spmv_rows_halo<false, 8, true>, "W8"},
+    {k_spmv_rows<true, false, 4>, k_spmv_rows<false, false, 4>, nullptr, nullptr, nullptr, nullptr, "W4"},
 };
 static const RowsVariant kMediumVariants[] = {
-    {k_spmv_rows<true, true, 8, 1>, k_spmv_rows<false, true, 8, 1>, k_spmv_rows_persistent<true, 8, 1>, "W8R1"},
-    {k_spmv_rows<true, true, 4, 1>, k_spmv_rows<false, true, 4, 1>, k_spmv_rows_persistent<true, 4, 1>, "W4R1"},
-    {k_spmv_rows<true, true, 4, 2>, k_spmv_rows<false, true, 4, 2>, k_spmv_rows_persistent<true, 4, 2>, "W4R2"},
-    {k_spmv_rows<true, true, 8, 2>, k_spmv_rows<false, true, 8, 2>, k_spmv_rows_persistent<true, 8, 2>, "W8R2"},
+    {k_spmv_rows<true, true, 8>, k_spmv_rows<false, true, 8>, k_spmv_rows<true, true, 8, false, true>,
+     k_spmv_rows<true, true, 8, false, true, 6>, k_spmv_rows_halo<true, 8, false>, k_spmv_rows_halo<true, 8, true>, "W8"},
+    {k_spmv_rows<true, true, 4>, k_spmv_rows<false, true, 4>, k_spmv_rows<true, true, 4, false, true>,
+     k_spmv_rows<true, true, 4, false, true, 6>, nullptr, nullptr, "W4"},
 };
 // MEDIUM kernels with the slot rotation (plans with irregular gathers); same order as kMediumVariants
 static const RowsVariant kMediumVariantsRot[] = {
-    {k_spmv_rows<true, true, 8, 1, true>, k_spmv_rows<false, true, 8, 1, true>, k_spmv_rows_persistent<true, 8, 1>, "W8R1r"},
-    {k_spmv_rows<true, true, 4, 1, true>, k_spmv_rows<false, true, 4, 1, true>, k_spmv_rows_persistent<true, 4, 1>, "W4R1r"},
-    {k_spmv_rows<true, true, 4, 2, true>, k_spmv_rows<false, true, 4, 2, true>, k_spmv_rows_persistent<true, 4, 2>, "W4R2r"},
-    {k_spmv_rows<true, true, 8, 2, true>, k_spmv_rows<false, true, 8, 2, true>, k_spmv_rows_persistent<true, 8, 2>, "W8R2r"},
+    {k_spmv_rows<true, true, 8, true>, k_spmv_rows<false, true, 8, true>, nullptr, nullptr, nullptr, nullptr, "W8r"},
+    {k_spmv_rows<true, true, 4, true>, k_spmv_rows<false, true, 4, true>, nullptr, nullptr, nullptr, nullptr, "W4r"},
 };
 constexpr int kNumShortVariants = sizeof(kShortVariants) / sizeof(kShortVariants[0]);
 constexpr int kNumMediumVariants = sizeof(kMediumVariants) / sizeof(kMediumVariants[0]);
 
-static RowsKernel mixed_kernel(bool tma, int threads, bool queue_form = false) {
-  if (!queue_form) {
-    switch (threads) {
-    case 64: return tma ? k_spmv_seg<true, 64> : k_spmv_seg<false, 64>;
-    case 128: return tma ? k_spmv_seg<true, 128> : k_spmv_seg<false, 128>;
-    default: return tma ? k_spmv_seg<true, 256> : k_spmv_seg<false, 256>;
-    }
-  }
+static RowsKernel mixed_kernel(bool tma, int threads) {
   switch (threads) {
   case 64: return tma ? k_spmv_mixed<true, 64> : k_spmv_mixed<false, 64>;
   case 128: return tma ? k_spmv_mixed<true, 128> : k_spmv_mixed<false, 128>;
   default: return tma ? k_spmv_mixed<true, 256> : k_spmv_mixed<false, 256>;
   }
+}
+
+// slot rotation of the MEDIUM kernel: only where gathers do not coalesce across rows anyway (C3: 1.836 ms against
+// 1.882 ms); on a stencil it breaks the coalescing of neighbouring rows (C5s: 1.08 ms against 0.97 ms). Tuning bit 26
+// switches it off.
+static bool rotate_slots(const spmv_b200_plan *p) { return p->irregular && !((p->flags >> 26) & 1u); }
+
+static const RowsVariant &rows_variant(const spmv_b200_plan *p, int kind) {
+  if (kind == SPMV_B200_KIND_SHORT)
+    return kShortVariants[p->variant_short];
+  return rotate_slots(p) ? kMediumVariantsRot[p->variant_medium] : kMediumVariants[p->variant_medium];
 }
 
 // The dynamic shared-memory limit is an attribute of the kernel function, not of a plan: several plans with different
@@ -1167,16 +967,19 @@ int kernels_configure(spmv_b200_plan *p) {
   int dev = 0, max_optin = 0;
   B200_CUDA(cudaGetDevice(&dev));
   B200_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  if (p->smem_bytes > (size_t)max_optin) {
-    set_error("tile_nnz too large for the shared memory of this device");
-    return SPMV_B200_ERR_ARG;
-  }
+  // every kernel that may be launched must fit the opt-in shared-memory limit of the device: say so here, in words,
+  // instead of letting cudaFuncSetAttribute fail with an opaque error
+  for (int k = 0; k < 3; ++k)
+    if (smem_for(p, k) > (size_t)max_optin) {
+      set_error("tile_nnz too large for the shared memory of this device");
+      return SPMV_B200_ERR_ARG;
+    }
   p->device = dev;
   if (p->flags & SPMV_B200_FLAG_L2_PERSIST_X) {
     int persist_max = 0, window_max = 0;
     B200_CUDA(cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, dev));
     B200_CUDA(cudaDeviceGetAttribute(&window_max, cudaDevAttrMaxAccessPolicyWindowSize, dev));
-    if (persist_max > 0) // device-wide carve-out of L2 for persisting lines; set to the maximum the device allows
+    if (persist_max > 0) // device-wide carve-out of L2 for persisting lines (released again by kernels_release)
       B200_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_max));
     p->persist_bytes = (size_t)persist_max;
     p->max_window_bytes = (size_t)window_max;
@@ -1189,9 +992,6 @@ int kernels_configure(spmv_b200_plan *p) {
   case 3: p->mixed_threads = 256; break;
   default: break;
   }
-  // tuning bit 22 selects the segmented-sum form of the MIXED kernel; the length-class-queue form is the default: the
-  // segmented form needs 6 resident CTAs, whose shared memory leaves too little L1 for the gathers (profiles/)
-  p->mixed_queue_form = ((p->flags >> 22) & 1u) == 0;
   p->variant_short = (int)((p->flags >> 8) & 0xf);
   p->variant_medium = (int)((p->flags >> 12) & 0xf);
   if (p->variant_short >= kNumShortVariants || p->variant_medium >= kNumMediumVariants) {
@@ -1200,48 +1000,55 @@ int kernels_configure(spmv_b200_plan *p) {
   }
   int rc;
   const RowsVariant &vs = kShortVariants[p->variant_short], &vm = kMediumVariants[p->variant_medium];
-  const bool persistent = (p->flags & SPMV_B200_FLAG_PERSISTENT) != 0;
-  // every kernel that may be launched must fit the opt-in shared-memory limit of the device: say so here, in words,
-  // instead of letting cudaFuncSetAttribute fail with an opaque error
-  for (int k = 0; k < 3; ++k) {
-    const size_t need = smem_for(p, k, persistent && k != SPMV_B200_KIND_MIXED);
-    if (need > (size_t)max_optin) {
-      set_error("tile_nnz too large for the shared memory of this device" +
-                std::string(persistent ? " (the persistent kernels keep two tiles per CTA)" : ""));
-      return SPMV_B200_ERR_ARG;
-    }
-  }
+  const RowsVariant &vr = kMediumVariantsRot[p->variant_medium];
   if ((rc = set_smem(vs.tma, smem_for(p, SPMV_B200_KIND_SHORT))) ||
       (rc = set_smem(vs.plain, smem_for(p, SPMV_B200_KIND_SHORT))) ||
       (rc = set_smem(vm.tma, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
       (rc = set_smem(vm.plain, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
-      (rc = set_smem(kMediumVariantsRot[p->variant_medium].tma, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
-      (rc = set_smem(kMediumVariantsRot[p->variant_medium].plain, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
-      (rc = set_smem(mixed_kernel(true, p->mixed_threads, p->mixed_queue_form), smem_for(p, SPMV_B200_KIND_MIXED))) ||
-      (rc = set_smem(mixed_kernel(false, p->mixed_threads, p->mixed_queue_form), smem_for(p, SPMV_B200_KIND_MIXED))))
+      (rc = set_smem(vr.tma, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
+      (rc = set_smem(vr.plain, smem_for(p, SPMV_B200_KIND_MEDIUM))) ||
+      (rc = set_smem(mixed_kernel(true, p->mixed_threads), smem_for(p, SPMV_B200_KIND_MIXED))) ||
+      (rc = set_smem(mixed_kernel(false, p->mixed_threads), smem_for(p, SPMV_B200_KIND_MIXED))))
     return rc;
-  if (persistent) { // one wave of CTAs, as many as fit on the device
-    if ((rc = set_smem(vs.persistent, smem_for(p, SPMV_B200_KIND_SHORT, true))) ||
-        (rc = set_smem(vm.persistent, smem_for(p, SPMV_B200_KIND_MEDIUM, true))))
-      return rc;
-    int sms = 0;
-    B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int occ_s = 0, occ_m = 0;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, vs.persistent, kThreads,
-                                                            smem_for(p, SPMV_B200_KIND_SHORT, true)));
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_m, vm.persistent, kThreads,
-                                                            smem_for(p, SPMV_B200_KIND_MEDIUM, true)));
-    p->persistent_grid[SPMV_B200_KIND_SHORT] = sms * (occ_s > 0 ? occ_s : 1);
-    p->persistent_grid[SPMV_B200_KIND_MEDIUM] = sms * (occ_m > 0 ? occ_m : 1);
-    if (const char *env = getenv("SPMV_B200_PERSIST_CTAS")) { // development knob: CTAs per SM of the persistent kernels
-      const int c = atoi(env);
-      if (c > 0) {
-        p->persistent_grid[SPMV_B200_KIND_SHORT] = sms * (c < occ_s ? c : occ_s);
-        p->persistent_grid[SPMV_B200_KIND_MEDIUM] = sms * (c < occ_m ? c : occ_m);
-      }
-    }
-  }
+  if (vs.halo && (rc = set_smem(vs.halo, smem_for(p, SPMV_B200_KIND_SHORT))))
+    return rc;
+  if (vm.halo && (rc = set_smem(vm.halo, smem_for(p, SPMV_B200_KIND_MEDIUM))))
+    return rc;
   return SPMV_B200_OK;
+}
+
+// second half, after the analysis has decided on the staged-x form (analysis_xstage): drops the form again if its
+// kernel variant was not built or its tile does not fit the shared memory of the device
+int kernels_configure_xs(spmv_b200_plan *p) {
+  if (!p->xstage)
+    return SPMV_B200_OK;
+  const int kind = p->count[SPMV_B200_KIND_SHORT] == p->ntiles ? SPMV_B200_KIND_SHORT : SPMV_B200_KIND_MEDIUM;
+  const RowsVariant &v = rows_variant(p, kind);
+  int max_optin = 0;
+  B200_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
+  if (!v.xs || xs_smem_for(p, kind) > (size_t)max_optin) {
+    p->xstage = false;
+    return SPMV_B200_OK;
+  }
+  int rc;
+  if ((rc = set_smem(v.xs, xs_smem_for(p, kind))))
+    return rc;
+  if (v.xs40 && (rc = set_smem(v.xs40, xs_smem_for(p, kind))))
+    return rc;
+  if (v.halo_xs && (rc = set_smem(v.halo_xs, xs_smem_for(p, kind))))
+    return rc;
+  p->smem_bytes = xs_smem_for(p, kind);
+  return SPMV_B200_OK;
+}
+
+// gives the device-wide L2 carve-out back (a plan with SPMV_B200_FLAG_L2_PERSIST_X took it): other plans of the process
+// would otherwise run with a fraction of the L2 (measured: C3 1.83 ms -> 2.34 ms after such a plan had existed)
+void kernels_release(spmv_b200_plan *p) {
+  if ((p->flags & SPMV_B200_FLAG_L2_PERSIST_X) && p->persist_bytes > 0) {
+    cudaCtxResetPersistingL2Cache();
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    p->persist_bytes = 0;
+  }
 }
 
 // Launch with an optional L2 access-policy window that marks x as persisting (gathers of x are the only re-used
@@ -1280,38 +1087,45 @@ static void kind_range(const spmv_b200_plan *p, int k, int tile_lo, int tile_hi,
   *hi = (int)(std::lower_bound(l.begin(), l.end(), tile_hi) - l.begin());
 }
 
+static void fill_args(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y,
+                      const PushArgs *push, SpmvArgs *a) {
+  *a = SpmvArgs{};
+  a->rowptr = p->rowptr;
+  a->col = p->col;
+  a->val = p->val;
+  a->x = x;
+  a->y = y;
+  a->alpha = alpha;
+  a->beta = beta;
+  a->partials = p->partials;
+  a->nnz = p->elem_end; // absolute index one past the last element (rowptr may be a view: rowptr[0] != 0)
+  a->vec_div = p->vec_div;
+  a->gather_na = (p->flags & (1u << 16)) ? 2 : ((p->flags & (1u << 27)) ? 3 : ((p->flags & SPMV_B200_FLAG_GATHER_NO_L1) ? 1 : 0));
+  a->read_y = (beta == 0.0 && (p->flags & SPMV_B200_FLAG_BETA0_SKIP_Y)) ? 0 : 1;
+  a->row_start_bits = p->row_start_bits;
+  a->nz_rows = p->nz_rows;
+  a->lcol = p->lcol;
+  a->xdesc = p->xdesc;
+  a->lcol_base = p->lcol_base;
+  a->n = p->n;
+  if (push)
+    a->push = *push;
+  else
+    a->push.count = 0;
+}
+
+// the staged-x form copies whole segments of x with TMA: x must be 16-byte aligned (cudaMalloc gives 256)
+static bool use_xs(const spmv_b200_plan *p, const double *x) {
+  return p->xstage && (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+}
+
 static int launch_range(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y, int tile_lo,
                         int tile_hi, bool with_fixup, cudaStream_t stream, const PushArgs *push = nullptr) {
   if (p->m == 0)
     return SPMV_B200_OK;
   SpmvArgs a;
-  a.rowptr = p->rowptr;
-  a.col = p->col;
-  a.val = p->val;
-  a.x = x;
-  a.y = y;
-  a.alpha = alpha;
-  a.beta = beta;
-  a.desc = nullptr;
-  a.partials = p->partials;
-  a.nnz = p->elem_end; // absolute index one past the last element (rowptr may be a view: rowptr[0] != 0)
-  a.vec_div = p->vec_div;
-  a.gather_na = (p->flags & (1u << 16)) ? 2 : ((p->flags & SPMV_B200_FLAG_GATHER_NO_L1) ? 1 : 0);
-  a.read_y = (beta == 0.0 && (p->flags & SPMV_B200_FLAG_BETA0_SKIP_Y)) ? 0 : 1;
-  a.ntiles = 0;
-  if (push)
-    a.push = *push;
-  else
-    a.push.count = 0;
-
-  // slot rotation of the MEDIUM kernel: only where gathers do not coalesce across rows anyway (C3: 1.836 ms against
-  // 1.882 ms); on a stencil it breaks the coalescing of neighbouring rows (C5s: 1.08 ms against 0.97 ms). Tuning bit 26
-  // switches it off.
-  a.rotate_slots = (p->irregular && !((p->flags >> 26) & 1u)) ? 1 : 0;
-  a.row_start_bits = p->row_start_bits;
-  a.nz_rows = p->nz_rows;
+  fill_args(p, alpha, beta, x, y, push, &a);
   const bool tma = p->uses_tma;
-  const bool persistent = (p->flags & SPMV_B200_FLAG_PERSISTENT) != 0;
   const bool whole = tile_lo <= 0 && tile_hi >= p->ntiles;
   if (p->direct) {
     const int lo = tile_lo < 0 ? 0 : tile_lo, hi = tile_hi > p->ntiles ? p->ntiles : tile_hi;
@@ -1337,16 +1151,15 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
     a.cap = cap_for(p, k);
     a.ntiles = hi - lo;
     if (k == SPMV_B200_KIND_MIXED) {
-      B200_CUDA(launch_spmv(mixed_kernel(tma, p->mixed_threads, p->mixed_queue_form), a.ntiles, smem_for(p, k), stream, a, p,
+      B200_CUDA(launch_spmv(mixed_kernel(tma, p->mixed_threads), a.ntiles, smem_for(p, k), stream, a, p,
                             p->mixed_threads));
       continue;
     }
-    const RowsVariant &v = k == SPMV_B200_KIND_SHORT ? kShortVariants[p->variant_short]
-                                                     : (a.rotate_slots ? kMediumVariantsRot[p->variant_medium]
-                                                                       : kMediumVariants[p->variant_medium]);
-    if (tma && persistent) {
-      const int grid = a.ntiles < p->persistent_grid[k] ? a.ntiles : p->persistent_grid[k];
-      B200_CUDA(launch_spmv(v.persistent, grid, smem_for(p, k, true), stream, a, p));
+    const RowsVariant &v = rows_variant(p, k);
+    if (use_xs(p, x)) {
+      a.cap = xs_cap_for(p, k);
+      a.xcap = xs_xcap(p);
+      B200_CUDA(launch_spmv((((p->flags >> 24) & 1u) && v.xs40) ? v.xs40 : v.xs, a.ntiles, xs_smem_for(p, k), stream, a, p));
     } else {
       B200_CUDA(launch_spmv(tma ? v.tma : v.plain, a.ntiles, smem_for(p, k), stream, a, p));
     }
@@ -1371,62 +1184,39 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
 }
 
 // ---- fused halo loop ----
-typedef void (*HaloKernel)(const SpmvArgs, const HaloSync);
-static HaloKernel halo_kernel(const spmv_b200_plan *p, int *kind) {
-  if (!p->uses_tma || p->direct || p->nsplit > 0 || p->ntiles == 0 || (p->flags & SPMV_B200_FLAG_PERSISTENT))
-    return nullptr;
-  if (p->count[SPMV_B200_KIND_SHORT] == p->ntiles) {
-    *kind = SPMV_B200_KIND_SHORT;
-    if (p->variant_short == 0)
-      return k_spmv_rows_halo<false, 6, 1>;
-    if (p->variant_short == 1)
-      return k_spmv_rows_halo<false, 8, 1>;
-  } else if (p->count[SPMV_B200_KIND_MEDIUM] == p->ntiles && !p->irregular) {
-    *kind = SPMV_B200_KIND_MEDIUM;
-    if (p->variant_medium == 0)
-      return k_spmv_rows_halo<true, 8, 1>;
-  }
-  return nullptr;
+// the plan's kind if the whole shard can run as one launch of a row kernel with the flag protocol inside, else -1
+static int halo_kind(const spmv_b200_plan *p) {
+  if (!p->uses_tma || p->direct || p->nsplit > 0 || p->ntiles == 0 || rotate_slots(p))
+    return -1;
+  for (int kind : {SPMV_B200_KIND_SHORT, SPMV_B200_KIND_MEDIUM})
+    if (p->count[kind] == p->ntiles && rows_variant(p, kind).halo && (!p->xstage || rows_variant(p, kind).halo_xs))
+      return kind;
+  return -1;
 }
 
-// true if the plan is covered by the single-launch kernel; raises its dynamic shared-memory limit (once, here: the
-// launches themselves may be recorded by a stream capture, where attribute calls do not belong)
-bool kernels_halo_single_launch_ok(const spmv_b200_plan *p) {
-  int kind = 0;
-  HaloKernel k = halo_kernel(p, &kind);
-  return k != nullptr && set_smem(k, smem_for(p, kind)) == SPMV_B200_OK;
-}
+bool kernels_halo_single_launch_ok(const spmv_b200_plan *p) { return halo_kind(p) >= 0; }
 
 int kernels_launch_halo(const spmv_b200_plan *p, const TileDesc *desc, const double *x, double *y,
                         const PushArgs *push, const HaloSync &sync, cudaStream_t stream) {
-  int kind = 0;
-  HaloKernel k = halo_kernel(p, &kind);
-  if (!k) {
+  const int kind = halo_kind(p);
+  if (kind < 0) {
     set_error("kernels_launch_halo: plan not covered by the single-launch kernel");
     return SPMV_B200_ERR_UNSUPPORTED;
   }
-  SpmvArgs a = {};
-  a.rowptr = p->rowptr;
-  a.col = p->col;
-  a.val = p->val;
-  a.x = x;
-  a.y = y;
-  a.alpha = 1.0;
-  a.beta = 0.0;
-  a.desc = desc;
-  a.partials = nullptr;
-  a.nnz = p->elem_end;
-  a.ntiles = p->ntiles;
-  a.cap = cap_for(p, kind);
-  a.vec_div = p->vec_div;
+  const RowsVariant &v = rows_variant(p, kind);
+  SpmvArgs a;
+  fill_args(p, 1.0, 0.0, x, y, push, &a);
   a.read_y = 0; // y is a slice of the next x: never read (SPMV_B200_FLAG_BETA0_SKIP_Y semantics)
-  a.gather_na = (p->flags & SPMV_B200_FLAG_GATHER_NO_L1) ? 1 : 0;
-  a.rotate_slots = 0;
-  if (push)
-    a.push = *push;
-  else
-    a.push.count = 0;
-  k<<<p->ntiles, kThreads, smem_for(p, kind), stream>>>(a, sync);
+  a.desc = desc;
+  a.ntiles = p->ntiles;
+  if (use_xs(p, x)) {
+    a.cap = xs_cap_for(p, kind);
+    a.xcap = xs_xcap(p);
+    v.halo_xs<<<p->ntiles, kThreads, xs_smem_for(p, kind), stream>>>(a, sync);
+  } else {
+    a.cap = cap_for(p, kind);
+    v.halo<<<p->ntiles, kThreads, smem_for(p, kind), stream>>>(a, sync);
+  }
   B200_CUDA(cudaGetLastError());
   return SPMV_B200_OK;
 }

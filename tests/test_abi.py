@@ -31,7 +31,29 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Options) == 20
     # int32 m,n | int64 nnz | 4 x int32 | uint32 | 2 x int32 | 3 x int32 | 3 x int32 (+4 pad) | 8 x int64 | 2 x int64
-    assert ctypes.sizeof(_lib.PlanInfo) == 8 + 8 + 16 + 4 + 8 + 12 + 16 + 64 + 16 + 16
+    # | 2 x int64 | 2 x int32
+    assert ctypes.sizeof(_lib.PlanInfo) == 8 + 8 + 16 + 4 + 8 + 12 + 16 + 64 + 16 + 16 + 8
+    assert ctypes.sizeof(_lib.HaloLoopDesc) == 712 and ctypes.sizeof(_lib.HaloLoopInfo) == 24
+
+
+def test_struct_layouts_match_the_c_compiler(tmp_path):
+    """sizeof of every ABI struct as gcc sees include/spmv_b200.h equals the ctypes mirror."""
+    import shutil
+    import subprocess
+    import pytest
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    if not Path(gcc).exists():
+        pytest.skip("gcc not available")
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "spmv_b200.h"\nint main(void) { printf("%zu %zu %zu %zu %zu\\n", '
+                   'sizeof(spmv_b200_options), sizeof(spmv_b200_plan_info), sizeof(spmv_b200_push), '
+                   'sizeof(spmv_b200_halo_loop_desc), sizeof(spmv_b200_halo_loop_info)); return 0; }\n')
+    exe = tmp_path / "sz"
+    r = subprocess.run([gcc, "-std=c99", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    want = [ctypes.sizeof(t) for t in (_lib.Options, _lib.PlanInfo, _lib.Push, _lib.HaloLoopDesc, _lib.HaloLoopInfo)]
+    assert got == want
 
 
 def test_product_package_never_imports_the_oracle():

@@ -80,6 +80,55 @@ def test_direct_form_arrays_bit_exact(opts):
         plan.destroy()
 
 
+def _banded(seed, m, half_width, per_row):
+    """rows with `per_row` columns inside [r - half_width, r + half_width]: one run of lines per row block"""
+    rng = np.random.default_rng(seed)
+    cols = []
+    for r in range(m):
+        lo, hi = max(0, r - half_width), min(m, r + half_width + 1)
+        cols.append(np.sort(rng.choice(np.arange(lo, hi), size=min(per_row, hi - lo), replace=False)))
+    rp = np.zeros(m + 1, np.int32)
+    rp[1:] = np.cumsum([c.size for c in cols])
+    col = np.concatenate(cols).astype(np.int32)
+    return synth.Csr(m, m, rp, col, rng.standard_normal(col.size))
+
+
+def test_staged_x_arrays_bit_exact_and_only_for_regular_matrices():
+    """lcol (16-bit local column indices) and the per-row-block segment tables of the staged-x form equal the CPU
+    restatement (oracle/analysis_port.c:port_xstage); stencils and banded matrices take the form, matrices with
+    scattered columns, split rows or mixed row blocks do not; SPMV_B200_FLAG_NO_XSTAGE switches it off."""
+    from spmv_acc_b200 import FLAG_NO_XSTAGE
+    takes = {"stencil2d": synth.stencil2d_numpy(100), "stencil3d": synth.stencil3d_numpy(20),
+             "stencil3d_odd_n": synth.stencil3d_numpy(15), "banded": _banded(5, 4000, 40, 9),
+             "stencil2d_rows_1000_3000": synth.stencil2d_numpy(100, 1000, 3000)}
+    for name, h in takes.items():
+        for T in (0, 512, 1792):
+            d = synth.to_device(h)
+            plan = SpmvPlan(desc_of(d), make_options(T))
+            info = plan.info()
+            assert info.xstage == 1 and info.xstage_lines > 0, (name, T, list(info.tiles_per_kind))
+            ref = oracle.port_xstage(h.col, plan.export("tile_elem"))
+            assert ref["failed"] == 0 and ref["max_lines"] == info.xstage_lines, name
+            assert np.array_equal(plan.export("lcol"), ref["lcol"]), f"{name}: lcol differs (T={info.tile_nnz})"
+            assert np.array_equal(plan.export("xdesc"), ref["xdesc"]), f"{name}: xdesc differs (T={info.tile_nnz})"
+            plan.destroy()
+            plan = SpmvPlan(desc_of(d), make_options(T, flags=FLAG_NO_XSTAGE))
+            assert plan.info().xstage == 0 and plan.export("lcol").size == 0
+            plan.destroy()
+    for name, h in _matrices():
+        if name in ("stencil2d", "stencil3d") or h.nnz == 0:
+            continue
+        d = synth.to_device(h)
+        plan = SpmvPlan(desc_of(d))
+        info = plan.info()
+        if info.xstage:  # small matrices with few columns may qualify; then the arrays must still be exact
+            ref = oracle.port_xstage(h.col, plan.export("tile_elem"))
+            assert ref["failed"] == 0 and np.array_equal(plan.export("lcol"), ref["lcol"]), name
+        else:
+            assert name in ("uniform", "rmat", "ragged", "one_row", "circuit"), name
+        plan.destroy()
+
+
 def test_tile_partition_equals_reference_merge_path_partition_kernel():
     """TILE_PART (T = 2048) against the reference's `partition` kernel, compiled in place into oracle/_ref/libref_gpu.so
     (benchmark/merge-path/merge_path_partition.h:7-17; launch shape of merge_path_spmv.cu:44)."""

@@ -9,7 +9,7 @@ import pytest
 import oracle
 from conftest import GOLDEN_CASES, load_golden
 from gpu_helpers import assert_parity, desc_of, gpu_spmv
-from spmv_acc_b200 import (FLAG_BETA0_SKIP_Y, FLAG_DIRECT, FLAG_NO_DIRECT, FLAG_NO_TMA, CsrDesc, HostMatrix, SpmvB200Error, SpmvPlan,
+from spmv_acc_b200 import (FLAG_BETA0_SKIP_Y, FLAG_DIRECT, FLAG_NO_DIRECT, FLAG_NO_TMA, FLAG_NO_XSTAGE, CsrDesc, HostMatrix, SpmvB200Error, SpmvPlan,
                            cache_invalidate, cache_revalidations, cache_size, host_spmv, make_options, sparse_csr_spmv,
                            sparse_spmv, synth)
 
@@ -21,15 +21,17 @@ OPTS = {
     "no_tma": make_options(flags=FLAG_NO_TMA),
     "small_tiles": make_options(256, 4, 16, 2, flags=FLAG_NO_DIRECT),
     "big_tiles": make_options(8192, 16, 256, 16, flags=FLAG_NO_DIRECT),
-    "persistent": make_options(flags=0x20000 | FLAG_NO_DIRECT),
-    "persistent_small": make_options(256, 4, 16, 2, flags=0x20000 | FLAG_NO_DIRECT),
+    "no_staged_x": make_options(flags=FLAG_NO_XSTAGE),
+    "staged_x_40_registers": make_options(flags=1 << 24),
+    "staged_x_small_tiles": make_options(512, 4, 16, 4),
+    "staged_x_T1792_4_lanes": make_options(1792, 0, 0, 8),
     "tiled_only": make_options(flags=FLAG_NO_DIRECT),
     "direct": make_options(flags=FLAG_DIRECT),
     "direct_scalar_loads": make_options(flags=FLAG_DIRECT | FLAG_NO_TMA),
     "direct_40_registers": make_options(flags=FLAG_DIRECT | (1 << 23)),
     "direct_T512_L64": make_options(512, 8, 64, flags=FLAG_DIRECT),
-    "mixed_segmented": make_options(flags=(1 << 22) | FLAG_NO_DIRECT),
-    "mixed_segmented_small": make_options(256, 4, 16, 2, flags=(1 << 22) | FLAG_NO_DIRECT),
+    "short_w8": make_options(flags=1 << 8),
+    "short_w4_medium_w4": make_options(flags=(2 << 8) | (1 << 12)),
 }
 
 
@@ -60,6 +62,8 @@ def _ragged(seed, m, n, choices):
 def _families():
     yield "stencil2d_200", synth.stencil2d_numpy(200)
     yield "stencil3d_24", synth.stencil3d_numpy(24)
+    yield "stencil3d_15_odd_n", synth.stencil3d_numpy(15)          # n odd: the last entry of x cannot travel by TMA
+    yield "stencil2d_rows_shard", synth.stencil2d_numpy(120, 3000, 9000)  # a row shard: columns outside its rows
     yield "uniform_3000x5000_32", synth.uniform_numpy(3000, 5000, 32, seed=1)
     yield "rmat_s14", synth.rmat_numpy(14, 16, seed=1)
     yield "ragged_mixed", _ragged(3, 5000, 3000, [0, 0, 1, 2, 3, 5, 9, 17, 40, 130, 300, 700, 5000])
@@ -80,9 +84,11 @@ def test_seeded_families_against_oracle(opt):
 
 
 def test_kinds_are_exercised():
-    """Each per-bin kernel and the fix-up pass must actually run somewhere in this suite."""
+    """Each per-bin kernel, the staged-x form of both row kernels and the fix-up pass must actually run somewhere in
+    this suite."""
     seen = np.zeros(3, dtype=np.int64)
     splits = 0
+    staged = set()
     for name, h in _families():
         d = synth.to_device(h)
         p = SpmvPlan(desc_of(d))
@@ -90,8 +96,11 @@ def test_kinds_are_exercised():
         seen += np.array(list(i.tiles_per_kind))
         splits += i.nsplit_rows
         assert i.uses_tma == 1
+        if i.xstage:
+            staged.add(int(np.argmax(list(i.tiles_per_kind))))
         p.destroy()
     assert np.all(seen > 0) and splits > 0
+    assert staged == {0, 1}, f"staged-x form seen for tile kinds {staged} (want SHORT and MEDIUM)"
 
 
 def test_edge_shapes():
