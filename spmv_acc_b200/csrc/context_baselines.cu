@@ -155,6 +155,128 @@ CTX_API int spmv_b200_ctx_gather_bound(long long nnz, const int *d_col, const do
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Gather bound through the TMA unit (context, not product): the same column stream, but x is fetched with
+// cp.async.bulk.tensor ... tile::gather4 instead of LSU loads. x is described as a 2-D tensor [n/2][2] of fp64 (16-byte
+// rows, the smallest box TMA accepts); one instruction names four rows (col >> 1) and lands their 4 x 16 bytes in
+// shared memory, from where the wanted half (col & 1) is read. The LSU gather rate is capped by L1TEX at one 128-byte
+// line per clock and SM (profiles/r1_gather_bound.jsonl: 257 G gathers/s); this measures whether the TMA path, which
+// does not go through L1TEX, gets past that. Two stages of 1024 elements per CTA; every thread issues one gather4
+// per stage. Returns the kernel's result in out[] (one partial sum per thread) so that it can be checked against the
+// LSU kernel.
+#include <cuda.h>
+
+template <int STAGES>
+__global__ void __launch_bounds__(256) k_gather4_bound(const __grid_constant__ CUtensorMap tmap,
+                                                       const int *__restrict__ col, long long nnz,
+                                                       double *__restrict__ out) {
+  extern __shared__ __align__(128) unsigned char g4_smem[]; // STAGES x 256 slots of 128 bytes (64 used)
+  __shared__ __align__(8) unsigned long long bar[STAGES];
+  const int tid = threadIdx.x;
+  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&bar[0]);
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s), "r"(1u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long chunk = 1024, stride = (long long)gridDim.x * chunk;
+  double acc = 0.0;
+  int4 cpend[STAGES];
+  long long base = (long long)blockIdx.x * chunk;
+  auto issue = [&](int s, long long b) {
+    int4 c = make_int4(0, 0, 0, 0);
+    const long long k = b + 4 * tid;
+    if (k + 3 < nnz)
+      c = __ldcs(reinterpret_cast<const int4 *>(col + k));
+    else
+      for (int j = 0; j < 4; ++j)
+        if (k + j < nnz)
+          (&c.x)[j] = __ldcs(col + k + j);
+    cpend[s] = c;
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * s), "r"(256u * 64u)
+                   : "memory");
+    __syncwarp();
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(g4_smem + ((size_t)s * 256 + tid) * 128);
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, "
+                 "%3, %4, %5, %6}], [%7];" ::"r"(dst),
+                 "l"(&tmap), "r"(0), "r"(c.x >> 1), "r"(c.y >> 1), "r"(c.z >> 1), "r"(c.w >> 1), "r"(bar0 + 8u * s)
+                 : "memory");
+  };
+  // (the lane-0 arrive of warp 0 and the copies of the other warps may come in any order: the only pending arrival
+  // is that one arrive, so the phase cannot complete before the expected bytes are known)
+  int filled = 0;
+  for (; filled < STAGES && base + (long long)filled * stride < nnz; ++filled)
+    issue(filled, base + (long long)filled * stride);
+  for (int it = 0; base < nnz; ++it, base += stride) {
+    const int s = it % STAGES;
+    const unsigned parity = (unsigned)((it / STAGES) & 1);
+    unsigned done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done)
+                   : "r"(bar0 + 8u * s), "r"(parity)
+                   : "memory");
+    const int4 c = cpend[s];
+    const double *slot = reinterpret_cast<const double *>(g4_smem + ((size_t)s * 256 + tid) * 128);
+    const long long k = base + 4 * tid;
+    double v = 0.0;
+    if (k < nnz) v += slot[0 + (c.x & 1)];
+    if (k + 1 < nnz) v += slot[2 + (c.y & 1)];
+    if (k + 2 < nnz) v += slot[4 + (c.z & 1)];
+    if (k + 3 < nnz) v += slot[6 + (c.w & 1)];
+    acc += v;
+    __syncthreads(); // every thread has read its slot of this stage before it is refilled
+    const long long nb = base + (long long)STAGES * stride;
+    if (nb < nnz)
+      issue(s, nb);
+  }
+  out[blockIdx.x * 256 + tid] = acc;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// out must hold grid*256 doubles; returns the grid size when d_out == nullptr; box_rows = second box dimension of the
+// tensor map (1 or 4: the two readings of the gather4 box rule; the caller checks which one the driver accepts and
+// which one gives the right sums)
+CTX_API int spmv_b200_ctx_gather4_bound(long long nnz, const int *d_col, const double *d_x, long long n, double *d_out,
+                                        int ctas_per_sm, int box_rows, void *stream) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = sms * (ctas_per_sm > 0 ? ctas_per_sm : 3);
+  if (!d_out)
+    return grid;
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return -10;
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {2, (cuuint64_t)(n / 2)};
+  const cuuint64_t strides[1] = {16};
+  const cuuint32_t box[2] = {2, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(d_x), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return -100 - (int)r;
+  constexpr int STAGES = 2;
+  const size_t smem = (size_t)STAGES * 256 * 128;
+  if (cudaFuncSetAttribute(k_gather4_bound<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return -3;
+  k_gather4_bound<STAGES><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmap, d_col, nnz, d_out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // cub::DeviceSpmv::CsrMV (merge-based, y = A*x), the second comparator of the reference harness
 // (benchmark/cub/spmv.cu:30-37: size query, cudaMalloc of the buffer, one call). Context only.
 // ---------------------------------------------------------------------------------------------------------------

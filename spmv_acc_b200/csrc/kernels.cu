@@ -248,10 +248,29 @@ __device__ __forceinline__ void emit_y(double *__restrict__ y, const PushArgs &p
 // ---------------------------------------------------------------------------------------------------------------
 // SHORT (VEC = false) and MEDIUM (VEC = true) tiles: every owned row lies completely inside the tile
 // ---------------------------------------------------------------------------------------------------------------
-// W = x gathers issued back to back per row and round. All W gathers of a round are in flight before the first FMA,
-// and y is fetched before the tile has landed, so that a CTA exposes one round trip to memory per phase (tile,
-// gathers) instead of one per batch of four elements. XS: x comes from the staged copy in shared memory (sx) through
-// the 16-bit local indices (slcol) instead of being gathered through L1.
+// One slot = one (value, column) pair of a row. In the staged-x form the slot loads are written as predicated PTX on
+// 32-bit shared-space addresses: a slot behind the end of its row keeps its zero-initialised registers and contributes
+// fma(0, 0, sum). The C++ form of the same thing -- (k < e) ? sx[lcol[k]] : 0 -- compiles into a branch per slot around
+// two dependent loads plus a generic-to-shared address conversion per access (22 instructions per slot in the SASS, 54
+// thread instructions per non-zero on the 27-point stencil: with no long-latency load left in the loop the kernel was
+// bound by instruction issue, ncu 54 % issue slots busy at 49 % DRAM); here a slot is 8-10 instructions, branch-free.
+// staged-x form: x[col] = sx[lcol[k]], everything in shared memory
+__device__ __forceinline__ void slot_xs(double &xv, double &vv, bool p, uint32_t a_lcol, uint32_t a_val, uint32_t sx_s) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\t.reg .u16 h;\n\t"
+               "setp.ne.u32 p, %2, 0;\n\t"
+               "@p ld.shared.u16 h, [%3];\n\t"
+               "@p ld.shared.f64 %1, [%4];\n\t"
+               "@p cvt.u32.u16 t, h;\n\t"
+               "@p shl.b32 t, t, 3;\n\t"
+               "@p add.u32 t, t, %5;\n\t"
+               "@p ld.shared.f64 %0, [t];\n\t}"
+               : "+d"(xv), "+d"(vv)
+               : "r"((uint32_t)p), "r"(a_lcol), "r"(a_val), "r"(sx_s));
+}
+// W = x gathers issued back to back per row and round (gather form): all W gathers of a round are in flight before the
+// first FMA, and y is fetched before the tile has landed, so that a CTA exposes one round trip to memory per phase
+// (tile, gathers) instead of one per batch of four elements. The staged-x form has no long-latency load in the loop
+// and walks rounds of 4 slots.
 // Rows of one tile whose value / colindex are (being) staged in shared memory; waits for the TMA phase `parity` of `bar`.
 template <bool TMA, bool VEC, int W, bool ROT, bool XS>
 __device__ __forceinline__ void rows_tile(const SpmvArgs &a, const double *__restrict__ sval,
@@ -270,6 +289,7 @@ __device__ __forceinline__ void rows_tile(const SpmvArgs &a, const double *__res
   const int G = kThreads >> lv; // rows per lane-group pass
   const int g = tid >> lv;
   const int l = tid & (V - 1);
+  const uint32_t sval_s = XS ? smem_u32(sval) : 0u, sx_s = XS ? smem_u32(sx) : 0u, scol_s = XS ? smem_u32(slcol) : 0u;
 
   // y of the first pass, requested while the tile is still in flight
   const double ypre = (a.read_y && l == 0 && g < nrows && g < kRowChunk) ? a.y[r0 + g] : 0.0;
@@ -293,38 +313,55 @@ __device__ __forceinline__ void rows_tile(const SpmvArgs &a, const double *__res
       const int e = act ? srow[r + 1] - a0 : 0;
       double sum = 0.0;
       const double yv = (cb == 0 && rb == 0) ? ypre : ((a.read_y && act && l == 0) ? a.y[r0 + cb + r] : 0.0);
-      // Irregular-gather plans: lane groups of a warp walk the W slots of a round in rotated order. With rows whose
-      // length is a multiple of 16 (32 nnz per row in C3) every group would otherwise read the same shared-memory banks
-      // in the same step (ncu: 8-way conflicts, 130 M extra wavefronts on C3). The rotation depends only on the
-      // group's position in the tile.
-      int rot = ROT ? (g % W) * V : 0; // offset of the first slot this group reads in a round
-      while (k < e) {
-        double xv[W];
+      if (XS) {
+        // rounds of 4 predicated slots, everything from shared memory
+        for (; k < e; k += 4 << lv) {
+          double xv[4], vv[4];
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
-          int kk = k + j * V;
-          if (ROT) {
-            kk += rot;
-            kk -= (kk >= k + W * V) ? W * V : 0; // wrap around inside the round
+          for (int j = 0; j < 4; ++j) {
+            const int kk = k + (j << lv);
+            xv[j] = 0.0;
+            vv[j] = 0.0;
+            slot_xs(xv[j], vv[j], kk < e, scol_s + 2u * (uint32_t)kk, sval_s + 8u * (uint32_t)kk, sx_s);
           }
-          if (XS)
-            xv[j] = (kk < e) ? sx[slcol[kk]] : 0.0;
-          else
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sum = fma(vv[j], xv[j], sum);
+        }
+      } else {
+        // Gather form: bound by the latency of the W gathers in flight, not by instruction issue; the compiler's
+        // branchy code keeps all W gathers in flight inside the register budget (a predicated-PTX version of this
+        // loop spilled or serialised the gathers at 40 registers).
+        // Irregular-gather plans (ROT): lane groups of a warp walk the W slots of a round in rotated order. With rows
+        // whose length is a multiple of 16 (32 nnz per row in C3) every group would otherwise read the same
+        // shared-memory banks in the same step (ncu: 8-way conflicts, 130 M extra wavefronts on C3). The rotation
+        // depends only on the group's position in the tile.
+        int rot = ROT ? (g % W) * V : 0; // offset of the first slot this group reads in a round
+        while (k < e) {
+          double xv[W];
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            int kk = k + j * V;
+            if (ROT) {
+              kk += rot;
+              kk -= (kk >= k + W * V) ? W * V : 0; // wrap around inside the round
+            }
             xv[j] = (kk < e) ? gather_x(a.x, scol[kk], a.gather_na) : 0.0;
-        }
-        if (ROT)
-          asm volatile("" : "+r"(rot)); // recompute the indices below instead of keeping W of them in registers
-#pragma unroll
-        for (int j = 0; j < W; ++j) {
-          int kk = k + j * V;
-          if (ROT) {
-            kk += rot;
-            kk -= (kk >= k + W * V) ? W * V : 0;
           }
-          if (kk < e)
-            sum = fma(sval[kk], xv[j], sum);
+          if (ROT)
+            asm volatile("" : "+r"(rot)); // recompute the indices below instead of keeping W of them in registers
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            int kk = k + j * V;
+            if (ROT) {
+              kk += rot;
+              kk -= (kk >= k + W * V) ? W * V : 0;
+            }
+            if (kk < e)
+              sum = fma(sval[kk], xv[j], sum);
+          }
+          k += W * V;
         }
-        k += W * V;
       }
       if (VEC) {
         for (int off = V >> 1; off > 0; off >>= 1)

@@ -316,3 +316,103 @@ def to_host(csr: Csr) -> Csr:
 def algorithmic_bytes(m: int, n: int, nnz: int) -> int:
     """Compulsory HBM bytes of one SpMV (BASELINE.json): 12*nnz + 4*(m+1) + 8*n + 16*m."""
     return 12 * nnz + 4 * (m + 1) + 8 * n + 16 * m
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# SuiteSparse-shaped stand-ins (the matrices of the reference's evaluation, examples/large-data-set-batch.sh:23-52, are
+# not shipped and there is no network): same rows / columns / average row length, a structure of the same family.
+# Device generators only (torch RNG with a fixed seed); used by the selector study, not by the headline benchmark.
+# ----------------------------------------------------------------------------------------------------------------
+SUITESPARSE_SHAPES = {
+    # name: (rows, cols, nnz per row, family)
+    "boneS10": (914_898, 914_898, 30.81, "fem3"),           # 3 dof per node, banded FEM
+    "Bump_2911": (2_911_419, 2_911_419, 22.44, "fem3"),
+    "Cube_Coup_dt6": (2_164_760, 2_164_760, 29.88, "fem3"),
+    "dielFilterV3real": (1_102_824, 1_102_824, 40.99, "fem1"),
+    "Ga41As41H72": (268_096, 268_096, 34.98, "skewed"),     # quantum chemistry: a few hundred long rows
+    "Hardesty3": (8_217_820, 7_591_564, 4.92, "short_rect"),
+    "largebasis": (440_020, 440_020, 12.64, "fem1"),
+    "RM07R": (381_689, 381_689, 98.16, "blocks"),           # CFD, dense blocks of ~100
+    "TSOPF_RS_b2383": (38_120, 38_120, 424.22, "blocks"),   # power network, dense blocks of ~400
+    "vas_stokes_2M": (2_146_677, 2_146_677, 30.34, "skewed"),
+}
+
+
+def suitesparse_like_device(name: str, seed: int = 1, device: str = "cuda", shrink: int = 1) -> Csr:
+    """`shrink` divides rows and columns (host-side tests of the generator itself)."""
+    import torch
+    m, n, avg, family = SUITESPARSE_SHAPES[name]
+    m, n = max(64, m // shrink), max(64, n // shrink)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed * 7919 + sum(map(ord, name)))
+    dev = device
+    if family in ("fem1", "fem3", "blocks"):
+        # rows of a node share a block of consecutive columns around the diagonal plus blocks further away (a banded
+        # graph with `reach` neighbours per node, `dof` unknowns per node)
+        dof = {"fem1": 1, "fem3": 3, "blocks": 1}[family]
+        per = max(1, int(round(avg / dof)))                  # neighbour nodes per row
+        width = {"fem1": 6, "fem3": 4, "blocks": int(avg)}[family]
+        nodes = (m + dof - 1) // dof
+        r = torch.arange(m, device=dev, dtype=torch.int64)
+        node = r // dof
+        if family == "blocks":
+            # one dense run of `avg` columns per row, starting at a block boundary
+            start = (node // width) * width - width // 2 + torch.randint(0, width, (m,), generator=g, device=dev)
+            start = start.clamp(0, max(n - width, 0))
+            lens = torch.full((m,), min(width, n), dtype=torch.int64, device=dev)
+            rowptr = torch.zeros(m + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(lens, 0, out=rowptr[1:])
+            owner = torch.repeat_interleave(r, lens)
+            col = start[owner] + (torch.arange(int(rowptr[-1]), device=dev) - rowptr[owner])
+        else:
+            # neighbour nodes: the node itself, +-1.. in the same "line", and +-stride lines (a 3-D mesh numbering)
+            stride1 = max(2, int(round(nodes ** (1.0 / 3.0))))
+            stride2 = stride1 * stride1
+            offs = [0]
+            k = 1
+            while len(offs) < per:
+                for o in (k, -k, k * stride1, -k * stride1, k * stride2, -k * stride2):
+                    if len(offs) < per:
+                        offs.append(o)
+                k += 1
+            offs = torch.tensor(sorted(offs), device=dev, dtype=torch.int64)
+            nb = (node[:, None] + offs[None, :])                      # [m, per] neighbour node ids
+            ok = (nb >= 0) & (nb < nodes)
+            cols = (nb[:, :, None] * dof + torch.arange(dof, device=dev)[None, None, :]).reshape(m, per * dof)
+            okc = ok[:, :, None].expand(m, per, dof).reshape(m, per * dof) & (cols < n)
+            lens = okc.sum(1)
+            rowptr = torch.zeros(m + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(lens, 0, out=rowptr[1:])
+            col = cols[okc]
+    elif family == "short_rect":
+        lens = torch.randint(3, 8, (m,), generator=g, device=dev)          # 3..7, mean 5
+        rowptr = torch.zeros(m + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(lens, 0, out=rowptr[1:])
+        nnz = int(rowptr[-1])
+        owner = torch.repeat_interleave(torch.arange(m, device=dev), lens)
+        centre = (owner.double() * (n / m)).long()
+        col = (centre + torch.randint(-2000, 2001, (nnz,), generator=g, device=dev)).clamp(0, n - 1)
+    else:  # skewed: log-normal row lengths with a heavy tail, columns clustered around the diagonal + a random part
+        z = torch.randn(m, generator=g, device=dev, dtype=torch.float64)
+        lens = torch.exp(0.9 * z)
+        lens = (lens * (avg / float(lens.mean()))).round().long().clamp(1, n)
+        heavy = torch.randint(0, m, (max(1, m // 2000),), generator=g, device=dev)
+        lens[heavy] = (lens[heavy] * 40).clamp(max=min(n, 20000))
+        rowptr = torch.zeros(m + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(lens, 0, out=rowptr[1:])
+        nnz = int(rowptr[-1])
+        owner = torch.repeat_interleave(torch.arange(m, device=dev), lens)
+        near = owner + torch.randint(-300, 301, (nnz,), generator=g, device=dev)
+        far = torch.randint(0, n, (nnz,), generator=g, device=dev)
+        pick = torch.rand(nnz, generator=g, device=dev) < 0.8
+        col = torch.where(pick, near, far).clamp(0, n - 1)
+    nnz = int(rowptr[-1])
+    if nnz >= 2 ** 31:
+        raise ValueError("matrix too large for int32 indices")
+    # sort the columns inside every row (the reference's readers produce sorted rows, cli/sparse_format.h:105-112)
+    owner = torch.repeat_interleave(torch.arange(m, device=dev), (rowptr[1:] - rowptr[:-1]))
+    key = owner * n + col
+    key = torch.sort(key)[0]
+    col = (key % n).to(torch.int32)
+    val = torch.rand(nnz, generator=g, device=dev, dtype=torch.float64) * 2.0 - 1.0
+    return Csr(m, n, rowptr.to(torch.int32), col, val)

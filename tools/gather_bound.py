@@ -43,6 +43,59 @@ def time_case(col, val, x, nnz, with_val, flavour, cps, smem_kb, reps):
     return e0.elapsed_time(e1) / reps
 
 
+def time_gather4(col, x, nnz, cps, box_rows, reps):
+    """cp.async.bulk.tensor tile::gather4 flavour (spmv_b200_ctx_gather4_bound). Returns (ms, sum of the gathered x)
+    or (None, error code)."""
+    X = _lib.ctx()
+    n = x.numel()
+    grid = X.spmv_b200_ctx_gather4_bound(nnz, 0, 0, n, 0, cps, box_rows, 0)
+    out = torch.zeros(grid * 256, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    args = (nnz, col.data_ptr(), x.data_ptr(), n, out.data_ptr(), cps, box_rows, st)
+    rc = X.spmv_b200_ctx_gather4_bound(*args)
+    if rc != 0:
+        return None, rc
+    torch.cuda.synchronize()
+    total = float(out.sum().item())
+    for _ in range(2):
+        X.spmv_b200_ctx_gather4_bound(*args)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        X.spmv_b200_ctx_gather4_bound(*args)
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / reps, total
+
+
+def gather4_cases(a):
+    """TMA gather4 against the LSU gather on uniformly random columns (and C3's own column stream)."""
+    nnz = 320_000_000
+    cases = [("uniform-random columns", int(t)) for t in a.tables.split(",") if t]
+    for name, n in cases:
+        col = torch.randint(0, n, (nnz,), dtype=torch.int32, device="cuda")
+        x = synth.vector_device(n, 2)
+        want = float(x[col.long()].sum().item()) if n <= 20_000_000 else None
+        lsu = time_case(col, None, x, nnz, False, 0, 8, 0, a.reps)
+        print(json.dumps({"case": name, "nnz": nnz, "x_MB": n * 8 / 1e6, "gather": "ld.global.nc (LSU)",
+                          "ms": round(lsu, 4), "Ggather_s": round(nnz / lsu / 1e6, 1)}), flush=True)
+        for box_rows in (1, 4):
+            for cps in (2, 3, 4):
+                ms, total = time_gather4(col, x, nnz, cps, box_rows, a.reps)
+                rec = {"case": name, "nnz": nnz, "x_MB": n * 8 / 1e6,
+                       "gather": f"TMA tile::gather4, x as [n/2][2] fp64, box {{2,{box_rows}}}", "ctas_per_sm": cps}
+                if ms is None:
+                    rec["error"] = total
+                else:
+                    rec.update({"ms": round(ms, 4), "Ggather_s": round(nnz / ms / 1e6, 1), "sum": total,
+                                "sum_expected": want,
+                                "sum_ok": (abs(total - want) <= 1e-9 * max(1.0, abs(want))) if want is not None else None})
+                print(json.dumps(rec), flush=True)
+        del col, x
+        torch.cuda.empty_cache()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workloads", default="c3,c4")
@@ -51,7 +104,11 @@ def main():
     ap.add_argument("--ctas", default="8")
     ap.add_argument("--smem", default="0", help="KB of dynamic shared memory per CTA (shrinks L1), comma list")
     ap.add_argument("--flavours", default="0,1")
+    ap.add_argument("--gather4", action="store_true", help="only the TMA tile::gather4 comparison")
     a = ap.parse_args()
+    if a.gather4:
+        gather4_cases(a)
+        return
     fls = [int(f) for f in a.flavours.split(",")]
     for w in [w for w in a.workloads.split(",") if w]:
         csr = make(w)
