@@ -108,6 +108,8 @@ struct SpmvArgs {
   long long lcol_base;
   int n;        // entries of x (the last line of x may be short)
   int xcap;     // doubles of shared memory reserved for the staged x
+  int m;        // rows of the plan (rowptr has m + 1 entries)
+  int ring_stages, ring_stage_bytes; // staged-x ring kernel: shared-memory stages per CTA and bytes per stage
   PushArgs push;
 };
 
@@ -165,6 +167,7 @@ struct spmv_b200_plan {
   b200::XDesc *xdesc = nullptr;
   long long lcol_base = 0;
   int xlines = 0; // largest number of staged lines of any row block
+  int ring_ctas = 0, ring_stages = 0; // persistent ring form of the staged-x kernels: CTAs per SM, stages per CTA (0: off)
   // device arrays owned by the plan
   int *tile_row = nullptr;
   int *tile_elem = nullptr;

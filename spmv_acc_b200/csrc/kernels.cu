@@ -101,20 +101,9 @@ __device__ __forceinline__ int ld_stream_s32(const int *p) {
 }
 
 // x gather through the read-only path; `na` selects L1::no_allocate (the line is not kept in L1)
-// x gather that asks L2 to keep the line (evict_last): tuning bit 27, for matrices whose x does not quite fit the L2
-__device__ __forceinline__ double ld_x_evict_last(const double *p) {
-  unsigned long long pol;
-  double v;
-  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-  return v;
-}
-
 __device__ __forceinline__ double gather_x(const double *__restrict__ x, int c, int na) {
   if (na == 2) // experiment: no gather at all (wrong results; isolates the cost of the x traffic)
     return 1.0;
-  if (na == 3)
-    return ld_x_evict_last(x + c);
   if (na)
     return ld_stream_f64(x + c);
   return __ldg(x + c);
@@ -491,6 +480,188 @@ __global__ void k_halo_wait(const HaloSync h) { halo_wait(h); }
 __global__ void k_halo_signal(const HaloSync h) { halo_signal(h); }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Staged-x form as a persistent ring: one wave of CTAs walks the row blocks, S stages of shared memory per CTA
+// ---------------------------------------------------------------------------------------------------------------
+// The one-row-block-per-CTA kernels alternate between waiting for their TMA copies and computing; with the 45-50 KB a
+// staged-x row block of the 27-point stencil needs, four CTAs fit on an SM and the bytes in flight dip every time one of
+// them computes, retires or starts (ncu: 61 % of the DRAM peak, the barrier the top stall). Here the copies of row block
+// i + (S - 1) * grid are issued before row block i is summed, so S - 1 stages per CTA are always in flight, and
+// everything a row block needs -- value, 16-bit local column indices, its segments of x, its row pointers -- arrives
+// through the same mbarrier: the loop has no global load left except y (when beta != 0) and one CTA barrier per row
+// block (the stage may be refilled once every thread has left it).
+// Stage layout (offsets multiples of 128 bytes): sval[cap] | sx[xcap] | srow[kRingRowCap] (int32) | slcol[cap] (uint16).
+constexpr int kRingStagesMax = 8;
+constexpr int kRingRowCap = kSparseTileRows + 8; // SHORT / MEDIUM row blocks own at most kSparseTileRows rows
+
+struct RingStage {
+  double *sval, *sx;
+  int *srow;
+  unsigned short *slcol;
+};
+__device__ __forceinline__ RingStage ring_stage(unsigned char *base, int cap, int xcap) {
+  RingStage st;
+  st.sval = reinterpret_cast<double *>(base);
+  st.sx = st.sval + ((cap + 15) & ~15);
+  st.srow = reinterpret_cast<int *>(st.sx + xcap);
+  st.slcol = reinterpret_cast<unsigned short *>(st.srow + ((kRingRowCap + 31) & ~31));
+  return st;
+}
+
+// warp 0: all copies of one row block into one stage (see tile_issue_loads_xs for the x segments); srow[0] will hold
+// rowptr[r0 & ~3]
+__device__ __forceinline__ void ring_issue(const SpmvArgs &a, const TileDesc &d, const RingStage &st,
+                                           unsigned long long *bar, int lane) {
+  const int a0 = d.e0 & ~7;
+  const int span = d.e1 - a0;
+  const long long avail = a.nnz - (long long)a0;
+  int cnt = (span + 7) & ~7;
+  if ((long long)cnt > avail)
+    cnt = (int)(avail & ~7LL);
+  const int rbase = d.r0 & ~3;
+  const int rspan = d.r1 + 1 - rbase; // row pointers rbase .. r1
+  int rcnt = (rspan + 3) & ~3;
+  if (rcnt > a.m + 1 - rbase)
+    rcnt = (a.m + 1 - rbase) & ~3;
+  const XDesc *__restrict__ xd = a.xdesc + d.tile;
+  const int nseg = __ldg(&xd->nseg);
+  unsigned int xbytes = 0;
+  int line = 0, off = 0;
+  if (lane < nseg) {
+    line = __ldg(&xd->line[lane]);
+    off = (int)__ldg(&xd->off[lane]);
+    const int end = lane + 1 < nseg ? (int)__ldg(&xd->off[lane + 1]) : __ldg(&xd->nlines);
+    long long elems = (long long)(end - off) * 16;
+    const long long left = (long long)a.n - (long long)line * 16;
+    if (elems > left)
+      elems = left;
+    xbytes = (unsigned int)(elems & ~1LL) * 8u;
+    if (elems & 1)
+      st.sx[(long long)off * 16 + elems - 1] = __ldg(a.x + (long long)line * 16 + elems - 1);
+  }
+  unsigned int total = xbytes;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    total += __shfl_xor_sync(0xffffffffu, total, o);
+  total += (unsigned int)cnt * 10u + (unsigned int)rcnt * 4u;
+  if (lane == 0)
+    mbar_arrive_expect_tx(bar, total); // total > 0: at least the row pointers or their thread-loaded tail exist
+  __syncwarp();
+  if (lane == 0) {
+    const unsigned long long pol = policy_evict_first();
+    if (cnt > 0) {
+      tma_bulk_g2s(st.sval, a.val + a0, (uint32_t)cnt * 8u, bar, pol);
+      tma_bulk_g2s(st.slcol, a.lcol + ((long long)a0 - a.lcol_base), (uint32_t)cnt * 2u, bar, pol);
+    }
+    if (rcnt > 0)
+      tma_bulk_g2s_nohint(st.srow, a.rowptr + rbase, (uint32_t)rcnt * 4u, bar);
+  }
+  if (xbytes > 0)
+    tma_bulk_g2s_nohint(st.sx + (long long)off * 16, a.x + (long long)line * 16, xbytes, bar);
+  // what 16-byte copies cannot bring (ends of the arrays): plain loads; the consumers see them after the CTA barrier
+  // that separates this issue from the stage's use
+  for (int i = cnt + lane; i < span; i += 32) {
+    st.sval[i] = ld_stream_f64(a.val + a0 + i);
+    st.slcol[i] = __ldg(a.lcol + ((long long)a0 - a.lcol_base) + i);
+  }
+  for (int i = rcnt + lane; i < rspan; i += 32)
+    st.srow[i] = __ldg(a.rowptr + rbase + i);
+}
+
+template <bool VEC, bool HALO>
+__global__ void __launch_bounds__(kThreads, 2) k_spmv_ring(const SpmvArgs a, const HaloSync h) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bar[kRingStagesMax];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int S = a.ring_stages, G = (int)gridDim.x, nt = a.ntiles;
+  if ((int)blockIdx.x >= nt)
+    return;
+  if (tid == 0)
+    for (int s = 0; s < S; ++s)
+      mbar_init(&bar[s], 1);
+  __syncthreads();
+  if (tid < 32) { // prologue: the first S row blocks of this CTA
+    for (int s = 0; s < S; ++s) {
+      const int j = (int)blockIdx.x + s * G;
+      if (j < nt) {
+        if (HALO && j < h.n_boundary) { // the x segments of a boundary row block include halo entries
+          if (lane == 0)
+            halo_wait(h);
+          __syncwarp();
+        }
+        ring_issue(a, load_desc(a.desc, j), ring_stage(smem_raw + (size_t)s * a.ring_stage_bytes, a.cap, a.xcap),
+                   &bar[s], lane);
+      }
+    }
+  }
+  __syncthreads();
+  int it = 0;
+  for (int i = (int)blockIdx.x; i < nt; i += G, ++it) {
+    const int s = it % S;
+    const RingStage st = ring_stage(smem_raw + (size_t)s * a.ring_stage_bytes, a.cap, a.xcap);
+    const TileDesc d = load_desc(a.desc, i);
+    const int a0 = d.e0 & ~7, nrows = d.r1 - d.r0;
+    const int *srow = st.srow + (d.r0 & 3);
+    // lanes per row from the block's average row, as in rows_tile
+    int lv = 0;
+    if (VEC) {
+      const int avg = (d.e1 - d.e0) / (nrows > 0 ? nrows : 1);
+      const int want = (avg + a.vec_div - 1) / a.vec_div;
+      while ((1 << lv) < want && lv < 5)
+        ++lv;
+    }
+    const int Gr = kThreads >> lv, g = tid >> lv, l = tid & ((1 << lv) - 1);
+    const double ypre = (a.read_y && l == 0 && g < nrows) ? a.y[d.r0 + g] : 0.0; // in flight during the wait below
+    mbar_wait(&bar[s], (uint32_t)((it / S) & 1));
+    const uint32_t sval_s = smem_u32(st.sval), sx_s = smem_u32(st.sx), scol_s = smem_u32(st.slcol);
+    for (int rb = 0; rb < nrows; rb += Gr) {
+      const int r = rb + g;
+      const bool act = r < nrows;
+      int k = act ? srow[r] - a0 + l : 0;
+      const int e = act ? srow[r + 1] - a0 : 0;
+      const double yv = rb == 0 ? ypre : ((a.read_y && act && l == 0) ? a.y[d.r0 + r] : 0.0);
+      double sum = 0.0;
+      for (; k < e; k += 4 << lv) {
+        double xv[4], vv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kk = k + (j << lv);
+          xv[j] = 0.0;
+          vv[j] = 0.0;
+          slot_xs(xv[j], vv[j], kk < e, scol_s + 2u * (uint32_t)kk, sval_s + 8u * (uint32_t)kk, sx_s);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sum = fma(vv[j], xv[j], sum);
+      }
+      if (VEC) {
+        for (int off = (1 << lv) >> 1; off > 0; off >>= 1)
+          sum += __shfl_down_sync(0xffffffffu, sum, off, 1 << lv);
+      }
+      if (act && l == 0) // cli/verification.cpp:64  y[i] = alpha * y0 + beta * y[i]
+        emit_y(a.y, a.push, d.r0 + r, a.alpha * sum + a.beta * yv);
+    }
+    __syncthreads(); // every thread has left stage s (and has stored its rows)
+    if (HALO && i < h.n_boundary && tid == 0) {
+      __threadfence_system();
+      if (atomicAdd(h.state + 1, 1u) == (unsigned int)h.n_boundary - 1u) { // last boundary row block of the iteration
+        st_volatile_u32(h.state + 1, 0u);
+        halo_signal(h);
+      }
+    }
+    const int nxt = i + S * G;
+    if (tid < 32 && nxt < nt) { // refill the stage just left
+      if (HALO && nxt < h.n_boundary) {
+        if (lane == 0)
+          halo_wait(h);
+        __syncwarp();
+      }
+      ring_issue(a, load_desc(a.desc, nxt), st, &bar[s], lane);
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
 // MIXED tiles
 // ---------------------------------------------------------------------------------------------------------------
 // deterministic CTA-wide sum of sval[lo, hi): strided per-thread partials, xor-shuffle tree, warp partials in order
@@ -788,15 +959,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmv_warp(const SpmvArgs a) 
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         c[j] = (unsigned)(i0 + 32 * j - e0) < span ? ld_cs_s32(a.col + i0 + 32 * j) : -1;
-      if (a.gather_na == 3) { // (uniform) tuning bit 27: L2 evict_last on the gathers
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          p[j] = c[j] >= 0 ? ld_x_evict_last(a.x + c[j]) : 0.0;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          p[j] = c[j] >= 0 ? ld_nc_f64(a.x + c[j]) : 0.0;
-      }
+      for (int j = 0; j < 4; ++j)
+        p[j] = c[j] >= 0 ? ld_nc_f64(a.x + c[j]) : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -925,6 +1090,50 @@ static size_t xs_smem_for(const spmv_b200_plan *p, int kind) {
 
 typedef void (*RowsKernel)(const SpmvArgs);
 typedef void (*HaloKernel)(const SpmvArgs, const HaloSync);
+
+// ---- staged-x ring (persistent CTAs): geometry ----
+static size_t ring_stage_bytes(const spmv_b200_plan *p, int kind) {
+  const size_t cap = (size_t)xs_cap_for(p, kind);
+  size_t b = ((cap + 15) & ~(size_t)15) * 8 + (size_t)xs_xcap(p) * 8 + (size_t)((kRingRowCap + 31) & ~31) * 4 + cap * 2;
+  return (b + 127) & ~(size_t)127;
+}
+static HaloKernel ring_kernel(int kind, bool halo) {
+  if (kind == SPMV_B200_KIND_SHORT)
+    return halo ? k_spmv_ring<false, true> : k_spmv_ring<false, false>;
+  return halo ? k_spmv_ring<true, true> : k_spmv_ring<true, false>;
+}
+// CTAs per SM and stages per CTA for the plan's tile size: two CTAs (16 warps sum while the copies of the next row
+// blocks are in flight) with as many stages as fit, at least two; SPMV_B200_RING_CTAS / SPMV_B200_RING_STAGES override
+static bool ring_geometry(const spmv_b200_plan *p, int kind, int *ctas, int *stages) {
+  int max_optin = 0;
+  if (cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device) != cudaSuccess)
+    return false;
+  const size_t per_sm = 228 * 1024, stage = ring_stage_bytes(p, kind);
+  const char *ec = getenv("SPMV_B200_RING_CTAS"), *es = getenv("SPMV_B200_RING_STAGES");
+  for (int c = ec ? atoi(ec) : 2; c >= 1; --c) {
+    const size_t budget = per_sm / (size_t)c - 2048; // 1 KB per CTA is reserved by the system, some static shared memory
+    int s = (int)(budget / stage);
+    if ((size_t)s * stage > (size_t)max_optin)
+      s = (int)((size_t)max_optin / stage);
+    if (es && atoi(es) > 0 && atoi(es) < s)
+      s = atoi(es);
+    if (s > kRingStagesMax)
+      s = kRingStagesMax;
+    if (s >= 2) {
+      int occ = 0; // registers may allow fewer CTAs than the shared memory does
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel(kind, true), kThreads, (size_t)s * stage) !=
+              cudaSuccess ||
+          occ < c) {
+        cudaGetLastError();
+        continue;
+      }
+      *ctas = c;
+      *stages = s;
+      return true;
+    }
+  }
+  return false;
+}
 struct RowsVariant {
   RowsKernel tma, plain; // tiles by TMA / by plain loads (misaligned value / colindex)
   RowsKernel xs;         // staged-x form (nullptr: not built for this variant)
@@ -1075,6 +1284,14 @@ int kernels_configure_xs(spmv_b200_plan *p) {
   if (v.halo_xs && (rc = set_smem(v.halo_xs, xs_smem_for(p, kind))))
     return rc;
   p->smem_bytes = xs_smem_for(p, kind);
+  // the persistent ring form of the same kernels (tuning bit 25 switches it off)
+  p->ring_ctas = p->ring_stages = 0;
+  if (!((p->flags >> 25) & 1u) && ring_geometry(p, kind, &p->ring_ctas, &p->ring_stages)) {
+    const size_t bytes = (size_t)p->ring_stages * ring_stage_bytes(p, kind);
+    if ((rc = set_smem(ring_kernel(kind, false), bytes)) || (rc = set_smem(ring_kernel(kind, true), bytes)))
+      return rc;
+    p->smem_bytes = bytes;
+  }
   return SPMV_B200_OK;
 }
 
@@ -1137,7 +1354,7 @@ static void fill_args(const spmv_b200_plan *p, double alpha, double beta, const 
   a->partials = p->partials;
   a->nnz = p->elem_end; // absolute index one past the last element (rowptr may be a view: rowptr[0] != 0)
   a->vec_div = p->vec_div;
-  a->gather_na = (p->flags & (1u << 16)) ? 2 : ((p->flags & (1u << 27)) ? 3 : ((p->flags & SPMV_B200_FLAG_GATHER_NO_L1) ? 1 : 0));
+  a->gather_na = (p->flags & (1u << 16)) ? 2 : ((p->flags & SPMV_B200_FLAG_GATHER_NO_L1) ? 1 : 0);
   a->read_y = (beta == 0.0 && (p->flags & SPMV_B200_FLAG_BETA0_SKIP_Y)) ? 0 : 1;
   a->row_start_bits = p->row_start_bits;
   a->nz_rows = p->nz_rows;
@@ -1145,6 +1362,7 @@ static void fill_args(const spmv_b200_plan *p, double alpha, double beta, const 
   a->xdesc = p->xdesc;
   a->lcol_base = p->lcol_base;
   a->n = p->n;
+  a->m = p->m;
   if (push)
     a->push = *push;
   else
@@ -1193,7 +1411,17 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
       continue;
     }
     const RowsVariant &v = rows_variant(p, k);
-    if (use_xs(p, x)) {
+    if (use_xs(p, x) && p->ring_stages >= 2) {
+      a.cap = xs_cap_for(p, k);
+      a.xcap = xs_xcap(p);
+      a.ring_stages = p->ring_stages;
+      a.ring_stage_bytes = (int)ring_stage_bytes(p, k);
+      int sms = 0;
+      B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
+      const int grid = a.ntiles < sms * p->ring_ctas ? a.ntiles : sms * p->ring_ctas;
+      HaloSync none = {};
+      ring_kernel(k, false)<<<grid, kThreads, (size_t)p->ring_stages * ring_stage_bytes(p, k), stream>>>(a, none);
+    } else if (use_xs(p, x)) {
       a.cap = xs_cap_for(p, k);
       a.xcap = xs_xcap(p);
       B200_CUDA(launch_spmv((((p->flags >> 24) & 1u) && v.xs40) ? v.xs40 : v.xs, a.ntiles, xs_smem_for(p, k), stream, a, p));
@@ -1246,7 +1474,16 @@ int kernels_launch_halo(const spmv_b200_plan *p, const TileDesc *desc, const dou
   a.read_y = 0; // y is a slice of the next x: never read (SPMV_B200_FLAG_BETA0_SKIP_Y semantics)
   a.desc = desc;
   a.ntiles = p->ntiles;
-  if (use_xs(p, x)) {
+  if (use_xs(p, x) && p->ring_stages >= 2) {
+    a.cap = xs_cap_for(p, kind);
+    a.xcap = xs_xcap(p);
+    a.ring_stages = p->ring_stages;
+    a.ring_stage_bytes = (int)ring_stage_bytes(p, kind);
+    int sms = 0;
+    B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
+    const int grid = p->ntiles < sms * p->ring_ctas ? p->ntiles : sms * p->ring_ctas;
+    ring_kernel(kind, true)<<<grid, kThreads, (size_t)p->ring_stages * ring_stage_bytes(p, kind), stream>>>(a, sync);
+  } else if (use_xs(p, x)) {
     a.cap = xs_cap_for(p, kind);
     a.xcap = xs_xcap(p);
     v.halo_xs<<<p->ntiles, kThreads, xs_smem_for(p, kind), stream>>>(a, sync);

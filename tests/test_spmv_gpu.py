@@ -22,7 +22,8 @@ OPTS = {
     "small_tiles": make_options(256, 4, 16, 2, flags=FLAG_NO_DIRECT),
     "big_tiles": make_options(8192, 16, 256, 16, flags=FLAG_NO_DIRECT),
     "no_staged_x": make_options(flags=FLAG_NO_XSTAGE),
-    "staged_x_40_registers": make_options(flags=1 << 24),
+    "staged_x_no_ring": make_options(flags=1 << 25),
+    "staged_x_no_ring_40_registers": make_options(flags=(1 << 25) | (1 << 24)),
     "staged_x_small_tiles": make_options(512, 4, 16, 4),
     "staged_x_T1792_4_lanes": make_options(1792, 0, 0, 8),
     "tiled_only": make_options(flags=FLAG_NO_DIRECT),
@@ -81,6 +82,32 @@ def test_seeded_families_against_oracle(opt):
         for a, b in AB[:3]:
             y, info = gpu_spmv(h, x, y0, a, b, OPTS[opt], repeat=2)
             assert_parity(h, x, y0, a, b, y, what=f"{name}/{opt}/a={a},b={b}")
+
+
+@pytest.mark.parametrize("ctas,stages", [("1", "0"), ("1", "2"), ("2", "2"), ("2", "3"), ("3", "0")])
+def test_staged_x_ring_geometries(ctas, stages, monkeypatch):
+    """The persistent ring form of the staged-x kernels with other CTAs-per-SM / stages-per-CTA than the default, on
+    whole matrices and on row-block ranges (each range is its own launch of the ring)."""
+    import torch
+    monkeypatch.setenv("SPMV_B200_RING_CTAS", ctas)
+    monkeypatch.setenv("SPMV_B200_RING_STAGES", stages)
+    for name, h in (("stencil3d_30", synth.stencil3d_numpy(30)), ("stencil2d_150", synth.stencil2d_numpy(150)),
+                    ("stencil3d_15_odd_n", synth.stencil3d_numpy(15))):
+        x, y0 = synth.vector_numpy(h.cols, 2), synth.vector_numpy(h.rows, 3)
+        for a, b in AB[:2]:
+            y, info = gpu_spmv(h, x, y0, a, b, None, repeat=2)
+            assert info.xstage == 1
+            assert_parity(h, x, y0, a, b, y, what=f"ring {ctas}x{stages} {name} a={a} b={b}")
+        d = synth.to_device(h)
+        p = SpmvPlan(desc_of(d))
+        nt = p.info().ntiles
+        dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y0).cuda()
+        cuts = [0, nt // 3, nt // 3 + 1, nt]
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            p.execute_tiles(0.75, -0.5, dx, dy, lo, hi)
+        torch.cuda.synchronize()
+        assert_parity(h, x, y0, 0.75, -0.5, dy.cpu().numpy(), what=f"ring {ctas}x{stages} {name} tile ranges")
+        p.destroy()
 
 
 def test_kinds_are_exercised():

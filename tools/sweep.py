@@ -31,6 +31,8 @@ def make(workload):
         return synth.stencil3d_device(384)
     if workload == "c5s":
         return synth.stencil3d_device(256)
+    if workload.startswith("ss:"):  # SuiteSparse-shaped stand-in (synth.SUITESPARSE_SHAPES)
+        return synth.suitesparse_like_device(workload[3:])
     raise ValueError(workload)
 
 
@@ -94,7 +96,10 @@ def main():
     ap.add_argument("--cusparse", action="store_true")
     ap.add_argument("--svar", default="0", help="SHORT kernel variants (option flag bits 8-11)")
     ap.add_argument("--mvar", default="0", help="MEDIUM kernel variants (option flag bits 12-15)")
+    ap.add_argument("--ring", default="", help="staged-x ring geometries CTASxSTAGES (0 = automatic), comma list, e.g. 2x0,1x0,2x2")
     args = ap.parse_args()
+    import os
+    rings = [r for r in args.ring.split(",") if r] or [""]
     for w in args.workloads.split(","):
         csr = make(w)
         torch.cuda.synchronize()
@@ -104,14 +109,19 @@ def main():
                 variants = [(int(a) << 8) | (int(b) << 12) for a in args.svar.split(",") for b in args.mvar.split(",")]
                 for flags in [v | f | int(xf) for v in variants for f in ([0, FLAG_NO_TMA] if args.no_tma_too else [0])
                               for xf in args.xflags.split(",")]:
+                  for ring in rings:
+                    if ring:
+                        c, st = ring.split("x")
+                        os.environ["SPMV_B200_RING_CTAS"] = c
+                        os.environ["SPMV_B200_RING_STAGES"] = st
                     try:
                         ms, info = time_plan(csr, make_options(T, 0, 0, vd, flags), args.reps)
-                        print(json.dumps({"workload": w, "tile": info.tile_nnz, "vec_div": vd, "flags": flags, "svar": (flags >> 8) & 15, "mvar": (flags >> 12) & 15, "ms": round(ms, 5),
+                        print(json.dumps({"workload": w, "tile": info.tile_nnz, "vec_div": vd, "flags": flags, "ring": ring, "ms": round(ms, 5),
                                           "gbs": round(balg / ms / 1e6, 1), "gflops": round(2 * csr.nnz / ms / 1e6, 1),
-                                          "kinds": list(info.tiles_per_kind), "split": info.nsplit_rows,
-                                          "launches": info.launches_per_execute, "smem": info.smem_bytes}), flush=True)
+                                          "kinds": list(info.tiles_per_kind), "split": info.nsplit_rows, "direct": info.direct,
+                                          "xstage": info.xstage, "launches": info.launches_per_execute, "smem": info.smem_bytes}), flush=True)
                     except Exception as e:
-                        print(json.dumps({"workload": w, "tile": info.tile_nnz, "error": str(e)}), flush=True)
+                        print(json.dumps({"workload": w, "tile": T, "flags": flags, "ring": ring, "error": str(e)}), flush=True)
         if args.cusparse:
             print(json.dumps({"workload": w, **cusparse_ms(csr, args.reps, balg)}), flush=True)
         del csr
