@@ -82,6 +82,8 @@ typedef struct spmv_b200_plan_info {
   int64_t workspace_bytes;   /* device memory owned by the plan                                 */
   int32_t xstage;            /* 1 if the staged-x form is used (x segments in shared memory, 16-bit local indices) */
   int32_t xstage_lines;      /* largest number of 128-byte lines of x any row block stages      */
+  int32_t ring_ctas;         /* staged-x form as a persistent ring: CTAs per SM (0: one row block per CTA) */
+  int32_t ring_stages;       /* ... and shared-memory stages per CTA                            */
 } spmv_b200_plan_info;
 
 /* arrays that spmv_b200_plan_export can copy to the host (for bit-exact analysis checks) */

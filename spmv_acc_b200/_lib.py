@@ -67,7 +67,7 @@ class PlanInfo(C.Structure):
                 ("nsplit_rows", C.c_int32), ("launches_per_execute", C.c_int32), ("direct", C.c_int32), ("bin_rows", C.c_int64 * 4),
                 ("bin_nnz", C.c_int64 * 4), ("gather_active", C.c_int64), ("gather_lines", C.c_int64),
                 ("smem_bytes", C.c_int64), ("workspace_bytes", C.c_int64), ("xstage", C.c_int32),
-                ("xstage_lines", C.c_int32)]
+                ("xstage_lines", C.c_int32), ("ring_ctas", C.c_int32), ("ring_stages", C.c_int32)]
 
 
 FLAG_NO_TMA = 1

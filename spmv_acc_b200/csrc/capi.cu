@@ -693,6 +693,8 @@ int spmv_b200_plan_get_info(const spmv_b200_plan *p, spmv_b200_plan_info *info) 
   info->workspace_bytes = (int64_t)p->workspace_bytes;
   info->xstage = p->xstage ? 1 : 0;
   info->xstage_lines = p->xstage ? p->xlines : 0;
+  info->ring_ctas = p->xstage ? p->ring_ctas : 0;
+  info->ring_stages = p->xstage ? p->ring_stages : 0;
   return SPMV_B200_OK;
 }
 

@@ -1091,6 +1091,8 @@ static size_t xs_smem_for(const spmv_b200_plan *p, int kind) {
 typedef void (*RowsKernel)(const SpmvArgs);
 typedef void (*HaloKernel)(const SpmvArgs, const HaloSync);
 
+template <typename K> static int set_smem(K kernel, size_t bytes);
+
 // ---- staged-x ring (persistent CTAs): geometry ----
 static size_t ring_stage_bytes(const spmv_b200_plan *p, int kind) {
   const size_t cap = (size_t)xs_cap_for(p, kind);
@@ -1120,8 +1122,9 @@ static bool ring_geometry(const spmv_b200_plan *p, int kind, int *ctas, int *sta
     if (s > kRingStagesMax)
       s = kRingStagesMax;
     if (s >= 2) {
-      int occ = 0; // registers may allow fewer CTAs than the shared memory does
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel(kind, true), kThreads, (size_t)s * stage) !=
+      int occ = 0; // registers may allow fewer CTAs than the shared memory does (the query needs the raised limit)
+      if (set_smem(ring_kernel(kind, true), (size_t)s * stage) != SPMV_B200_OK ||
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel(kind, true), kThreads, (size_t)s * stage) !=
               cudaSuccess ||
           occ < c) {
         cudaGetLastError();
@@ -1373,6 +1376,11 @@ static void fill_args(const spmv_b200_plan *p, double alpha, double beta, const 
 static bool use_xs(const spmv_b200_plan *p, const double *x) {
   return p->xstage && (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
 }
+// the ring form also brings the row pointers by TMA: a row-pointer window that starts at an odd multiple of 4 bytes
+// (a shard given as rowptr[lo : hi + 1] of its parent) keeps the one-row-block-per-CTA kernels
+static bool use_ring(const spmv_b200_plan *p, const double *x) {
+  return use_xs(p, x) && p->ring_stages >= 2 && (reinterpret_cast<uintptr_t>(p->rowptr) & 15u) == 0;
+}
 
 static int launch_range(const spmv_b200_plan *p, double alpha, double beta, const double *x, double *y, int tile_lo,
                         int tile_hi, bool with_fixup, cudaStream_t stream, const PushArgs *push = nullptr) {
@@ -1411,7 +1419,7 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
       continue;
     }
     const RowsVariant &v = rows_variant(p, k);
-    if (use_xs(p, x) && p->ring_stages >= 2) {
+    if (use_ring(p, x)) {
       a.cap = xs_cap_for(p, k);
       a.xcap = xs_xcap(p);
       a.ring_stages = p->ring_stages;
@@ -1474,7 +1482,7 @@ int kernels_launch_halo(const spmv_b200_plan *p, const TileDesc *desc, const dou
   a.read_y = 0; // y is a slice of the next x: never read (SPMV_B200_FLAG_BETA0_SKIP_Y semantics)
   a.desc = desc;
   a.ntiles = p->ntiles;
-  if (use_xs(p, x) && p->ring_stages >= 2) {
+  if (use_ring(p, x)) {
     a.cap = xs_cap_for(p, kind);
     a.xcap = xs_xcap(p);
     a.ring_stages = p->ring_stages;

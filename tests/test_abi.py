@@ -31,8 +31,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Options) == 20
     # int32 m,n | int64 nnz | 4 x int32 | uint32 | 2 x int32 | 3 x int32 | 3 x int32 (+4 pad) | 8 x int64 | 2 x int64
-    # | 2 x int64 | 2 x int32
-    assert ctypes.sizeof(_lib.PlanInfo) == 8 + 8 + 16 + 4 + 8 + 12 + 16 + 64 + 16 + 16 + 8
+    # | 2 x int64 | 4 x int32
+    assert ctypes.sizeof(_lib.PlanInfo) == 8 + 8 + 16 + 4 + 8 + 12 + 16 + 64 + 16 + 16 + 16
     assert ctypes.sizeof(_lib.HaloLoopDesc) == 712 and ctypes.sizeof(_lib.HaloLoopInfo) == 24
 
 

@@ -96,7 +96,9 @@ def test_staged_x_ring_geometries(ctas, stages, monkeypatch):
         x, y0 = synth.vector_numpy(h.cols, 2), synth.vector_numpy(h.rows, 3)
         for a, b in AB[:2]:
             y, info = gpu_spmv(h, x, y0, a, b, None, repeat=2)
-            assert info.xstage == 1
+            assert info.xstage == 1 and info.ring_stages >= 2 and info.ring_ctas >= 1, (info.ring_ctas, info.ring_stages)
+            if stages != "0":
+                assert info.ring_stages <= int(stages)
             assert_parity(h, x, y0, a, b, y, what=f"ring {ctas}x{stages} {name} a={a} b={b}")
         d = synth.to_device(h)
         p = SpmvPlan(desc_of(d))
@@ -201,6 +203,31 @@ def test_rowptr_view_and_misaligned_pointers():
     torch.cuda.synchronize()
     assert_parity(h, x, y0, 1.0, 1.0, dy.cpu().numpy(), what="misaligned")
     p.destroy()
+
+
+def test_staged_x_on_row_pointer_windows():
+    """A row shard given as a window of the parent's row pointers (rowptr[lo : hi + 1], colindex / value of the parent):
+    the staged-x form indexes its 16-bit column copy from the window's first element; windows whose first row pointer
+    is not 16-byte aligned cannot take the ring form (its row pointers travel by TMA) and must still be right."""
+    import torch
+    h = synth.stencil3d_numpy(28)
+    x = synth.vector_numpy(h.cols, 2)
+    d = synth.to_device(h)
+    dx = torch.from_numpy(x).cuda()
+    for lo, hi in ((4000, 15000), (4001, 15003), (4002, 21952), (0, 7777)):
+        y0 = synth.vector_numpy(hi - lo, 3)
+        dy = torch.from_numpy(y0).cuda()
+        view = CsrDesc(hi - lo, h.cols, int(h.rowptr[hi] - h.rowptr[lo]), d.rowptr[lo:hi + 1], d.col, d.val)
+        p = SpmvPlan(view)
+        assert p.info().xstage == 1
+        p.execute(0.75, -0.5, dx, dy)
+        torch.cuda.synchronize()
+        sub = synth.Csr(hi - lo, h.cols, h.rowptr[lo:hi + 1] - h.rowptr[lo], h.col[h.rowptr[lo]:h.rowptr[hi]],
+                        h.val[h.rowptr[lo]:h.rowptr[hi]])
+        assert_parity(sub, x, y0, 0.75, -0.5, dy.cpu().numpy(), what=f"staged x on rows {lo}:{hi}")
+        ref = oracle.port_xstage(h.col, p.export("tile_elem"))
+        assert np.array_equal(p.export("lcol"), ref["lcol"])
+        p.destroy()
 
 
 def test_reference_shaped_entry_points_and_plan_cache():

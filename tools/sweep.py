@@ -119,7 +119,7 @@ def main():
                         print(json.dumps({"workload": w, "tile": info.tile_nnz, "vec_div": vd, "flags": flags, "ring": ring, "ms": round(ms, 5),
                                           "gbs": round(balg / ms / 1e6, 1), "gflops": round(2 * csr.nnz / ms / 1e6, 1),
                                           "kinds": list(info.tiles_per_kind), "split": info.nsplit_rows, "direct": info.direct,
-                                          "xstage": info.xstage, "launches": info.launches_per_execute, "smem": info.smem_bytes}), flush=True)
+                                          "xstage": info.xstage, "ring_used": f"{info.ring_ctas}x{info.ring_stages}", "launches": info.launches_per_execute, "smem": info.smem_bytes}), flush=True)
                     except Exception as e:
                         print(json.dumps({"workload": w, "tile": T, "flags": flags, "ring": ring, "error": str(e)}), flush=True)
         if args.cusparse:
