@@ -203,6 +203,19 @@ int spmv_b200_plan_create(spmv_b200_plan **out, int32_t m, int32_t n, int64_t nn
         rc = analysis_run(p, static_cast<cudaStream_t>(stream));
     }
   }
+  // Automatic tile size, third look: 1024 is the choice for irregular gathers with uniform rows (C3: MEDIUM row blocks,
+  // small tiles leave L1 to the gathers). If the row lengths are skewed as well, most row blocks end up in the MIXED
+  // kernel, which is faster with 2048 (measured on log-normal row lengths, profiles/r2_sweep_suitesparse_shapes.jsonl:
+  // 0.0554 against 0.0607 ms and 0.2949 against 0.3025 ms).
+  if (rc == SPMV_B200_OK && !(opt && opt->tile_nnz) && !p->direct && p->irregular && p->T == 1024 && p->ntiles > 0 &&
+      2 * (long long)p->count[SPMV_B200_KIND_MIXED] > (long long)p->ntiles) {
+    free_plan_arrays(p);
+    reset_plan_arrays(p);
+    p->T = 2048;
+    rc = kernels_configure(p);
+    if (rc == SPMV_B200_OK)
+      rc = analysis_run(p, static_cast<cudaStream_t>(stream));
+  }
   // staged-x form for regular matrices (x segments of every row block in shared memory, 16-bit local column indices)
   if (rc == SPMV_B200_OK && p->nnz > 0 && d_colidx)
     rc = analysis_xstage(p, static_cast<cudaStream_t>(stream));

@@ -256,6 +256,17 @@ __device__ __forceinline__ void slot_xs(double &xv, double &vv, bool p, uint32_t
                : "+d"(xv), "+d"(vv)
                : "r"((uint32_t)p), "r"(a_lcol), "r"(a_val), "r"(sx_s));
 }
+// log2 of the lanes per row of a MEDIUM row block: the smallest lv with 2^lv >= ceil(avg / vec_div), avg = floor(elems /
+// rows), at most 5. Written without the two integer divisions (each costs ~20 instructions, paid per row block and warp):
+// 2^lv * vec_div >= floor(elems / rows)  <=>  (2^lv * vec_div + 1) * rows > elems.
+__device__ __forceinline__ int lanes_log2(int elems, int nrows, int vec_div) {
+  const int n = nrows > 0 ? nrows : 1;
+  int lv = 0;
+  while (lv < 5 && (long long)((vec_div << lv) + 1) * n <= (long long)elems)
+    ++lv;
+  return lv;
+}
+
 // W = x gathers issued back to back per row and round (gather form): all W gathers of a round are in flight before the
 // first FMA, and y is fetched before the tile has landed, so that a CTA exposes one round trip to memory per phase
 // (tile, gathers) instead of one per batch of four elements. The staged-x form has no long-latency load in the loop
@@ -267,13 +278,7 @@ __device__ __forceinline__ void rows_tile(const SpmvArgs &a, const double *__res
                                           const double *__restrict__ sx, int *__restrict__ srow,
                                           unsigned long long *bar, uint32_t parity, int r0, int nrows, int a0, int e0,
                                           int e1, int tid) {
-  int lv = 0; // log2(lanes per row)
-  if (VEC) {
-    const int avg = (e1 - e0) / (nrows > 0 ? nrows : 1);
-    const int want = (avg + a.vec_div - 1) / a.vec_div;
-    while ((1 << lv) < want && lv < 5)
-      ++lv;
-  }
+  const int lv = VEC ? lanes_log2(e1 - e0, nrows, a.vec_div) : 0; // log2(lanes per row)
   const int V = 1 << lv;
   const int G = kThreads >> lv; // rows per lane-group pass
   const int g = tid >> lv;
@@ -507,10 +512,38 @@ __device__ __forceinline__ RingStage ring_stage(unsigned char *base, int cap, in
   return st;
 }
 
+// What warp 0 needs to issue the copies of one row block: its descriptor and (one segment per lane) its XDesc entry.
+// Fetched one row block ahead, so that the two dependent global round trips (descriptor, segment table) are not paid
+// between two row blocks: with them in the loop every row block cost ~2.8 us whatever its size.
+struct RingFetch {
+  TileDesc d;
+  int nseg, line, off, end; // this lane's segment: lines [line, line + end - off) of x to line `off` of the stage
+};
+__device__ __forceinline__ RingFetch ring_fetch(const SpmvArgs &a, int j, int lane) {
+  RingFetch f;
+  f.d = load_desc(a.desc, j);
+  const XDesc *__restrict__ xd = a.xdesc + f.d.tile;
+  f.nseg = __ldg(&xd->nseg);
+  // (lanes beyond nseg read entries that exist -- the table has kXsegMax slots -- and ignore them)
+  const int sl = lane < kXsegMax ? lane : kXsegMax - 1;
+  f.line = __ldg(&xd->line[sl]);
+  f.off = (int)__ldg(&xd->off[sl]);
+  const int nxt = (int)__ldg(&xd->off[sl + 1 < kXsegMax ? sl + 1 : kXsegMax - 1]);
+  f.end = lane + 1 < f.nseg ? nxt : __ldg(&xd->nlines);
+  return f;
+}
+
 // warp 0: all copies of one row block into one stage (see tile_issue_loads_xs for the x segments); srow[0] will hold
-// rowptr[r0 & ~3]
-__device__ __forceinline__ void ring_issue(const SpmvArgs &a, const TileDesc &d, const RingStage &st,
+// rowptr[r0 & ~3]; the four descriptor fields the consumers need go to sdesc
+__device__ __forceinline__ void ring_issue(const SpmvArgs &a, const RingFetch &f, const RingStage &st, int *sdesc,
                                            unsigned long long *bar, int lane) {
+  const TileDesc &d = f.d;
+  if (lane == 0) {
+    sdesc[0] = d.r0;
+    sdesc[1] = d.r1;
+    sdesc[2] = d.e0;
+    sdesc[3] = d.e1;
+  }
   const int a0 = d.e0 & ~7;
   const int span = d.e1 - a0;
   const long long avail = a.nnz - (long long)a0;
@@ -522,21 +555,15 @@ __device__ __forceinline__ void ring_issue(const SpmvArgs &a, const TileDesc &d,
   int rcnt = (rspan + 3) & ~3;
   if (rcnt > a.m + 1 - rbase)
     rcnt = (a.m + 1 - rbase) & ~3;
-  const XDesc *__restrict__ xd = a.xdesc + d.tile;
-  const int nseg = __ldg(&xd->nseg);
   unsigned int xbytes = 0;
-  int line = 0, off = 0;
-  if (lane < nseg) {
-    line = __ldg(&xd->line[lane]);
-    off = (int)__ldg(&xd->off[lane]);
-    const int end = lane + 1 < nseg ? (int)__ldg(&xd->off[lane + 1]) : __ldg(&xd->nlines);
-    long long elems = (long long)(end - off) * 16;
-    const long long left = (long long)a.n - (long long)line * 16;
+  if (lane < f.nseg) {
+    long long elems = (long long)(f.end - f.off) * 16;
+    const long long left = (long long)a.n - (long long)f.line * 16;
     if (elems > left)
       elems = left;
     xbytes = (unsigned int)(elems & ~1LL) * 8u;
     if (elems & 1)
-      st.sx[(long long)off * 16 + elems - 1] = __ldg(a.x + (long long)line * 16 + elems - 1);
+      st.sx[(long long)f.off * 16 + elems - 1] = __ldg(a.x + (long long)f.line * 16 + elems - 1);
   }
   unsigned int total = xbytes;
 #pragma unroll
@@ -544,7 +571,7 @@ __device__ __forceinline__ void ring_issue(const SpmvArgs &a, const TileDesc &d,
     total += __shfl_xor_sync(0xffffffffu, total, o);
   total += (unsigned int)cnt * 10u + (unsigned int)rcnt * 4u;
   if (lane == 0)
-    mbar_arrive_expect_tx(bar, total); // total > 0: at least the row pointers or their thread-loaded tail exist
+    mbar_arrive_expect_tx(bar, total);
   __syncwarp();
   if (lane == 0) {
     const unsigned long long pol = policy_evict_first();
@@ -556,7 +583,7 @@ __device__ __forceinline__ void ring_issue(const SpmvArgs &a, const TileDesc &d,
       tma_bulk_g2s_nohint(st.srow, a.rowptr + rbase, (uint32_t)rcnt * 4u, bar);
   }
   if (xbytes > 0)
-    tma_bulk_g2s_nohint(st.sx + (long long)off * 16, a.x + (long long)line * 16, xbytes, bar);
+    tma_bulk_g2s_nohint(st.sx + (long long)f.off * 16, a.x + (long long)f.line * 16, xbytes, bar);
   // what 16-byte copies cannot bring (ends of the arrays): plain loads; the consumers see them after the CTA barrier
   // that separates this issue from the stage's use
   for (int i = cnt + lane; i < span; i += 32) {
@@ -571,6 +598,7 @@ template <bool VEC, bool HALO>
 __global__ void __launch_bounds__(kThreads, 2) k_spmv_ring(const SpmvArgs a, const HaloSync h) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar[kRingStagesMax];
+  __shared__ int sdesc[kRingStagesMax][4];
   const int tid = threadIdx.x, lane = tid & 31;
   const int S = a.ring_stages, G = (int)gridDim.x, nt = a.ntiles;
   if ((int)blockIdx.x >= nt)
@@ -579,6 +607,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_spmv_ring(const SpmvArgs a, con
     for (int s = 0; s < S; ++s)
       mbar_init(&bar[s], 1);
   __syncthreads();
+  RingFetch ahead; // warp 0: the row block that will refill the stage being summed
+  ahead.nseg = 0;
   if (tid < 32) { // prologue: the first S row blocks of this CTA
     for (int s = 0; s < S; ++s) {
       const int j = (int)blockIdx.x + s * G;
@@ -588,37 +618,32 @@ __global__ void __launch_bounds__(kThreads, 2) k_spmv_ring(const SpmvArgs a, con
             halo_wait(h);
           __syncwarp();
         }
-        ring_issue(a, load_desc(a.desc, j), ring_stage(smem_raw + (size_t)s * a.ring_stage_bytes, a.cap, a.xcap),
-                   &bar[s], lane);
+        ring_issue(a, ring_fetch(a, j, lane), ring_stage(smem_raw + (size_t)s * a.ring_stage_bytes, a.cap, a.xcap),
+                   sdesc[s], &bar[s], lane);
       }
     }
+    if ((int)blockIdx.x + S * G < nt)
+      ahead = ring_fetch(a, (int)blockIdx.x + S * G, lane);
   }
   __syncthreads();
-  int it = 0;
-  for (int i = (int)blockIdx.x; i < nt; i += G, ++it) {
-    const int s = it % S;
+  int s = 0;
+  uint32_t parity = 0u; // stage and barrier phase of the row block being summed (no division by the run-time S)
+  for (int i = (int)blockIdx.x; i < nt; i += G) {
     const RingStage st = ring_stage(smem_raw + (size_t)s * a.ring_stage_bytes, a.cap, a.xcap);
-    const TileDesc d = load_desc(a.desc, i);
-    const int a0 = d.e0 & ~7, nrows = d.r1 - d.r0;
-    const int *srow = st.srow + (d.r0 & 3);
-    // lanes per row from the block's average row, as in rows_tile
-    int lv = 0;
-    if (VEC) {
-      const int avg = (d.e1 - d.e0) / (nrows > 0 ? nrows : 1);
-      const int want = (avg + a.vec_div - 1) / a.vec_div;
-      while ((1 << lv) < want && lv < 5)
-        ++lv;
-    }
+    const int r0 = sdesc[s][0], nrows = sdesc[s][1] - r0, e0 = sdesc[s][2], e1 = sdesc[s][3];
+    const int a0 = e0 & ~7;
+    const int *srow = st.srow + (r0 & 3);
+    const int lv = VEC ? lanes_log2(e1 - e0, nrows, a.vec_div) : 0; // lanes per row, as in rows_tile
     const int Gr = kThreads >> lv, g = tid >> lv, l = tid & ((1 << lv) - 1);
-    const double ypre = (a.read_y && l == 0 && g < nrows) ? a.y[d.r0 + g] : 0.0; // in flight during the wait below
-    mbar_wait(&bar[s], (uint32_t)((it / S) & 1));
+    const double ypre = (a.read_y && l == 0 && g < nrows) ? a.y[r0 + g] : 0.0; // in flight during the wait below
+    mbar_wait(&bar[s], parity);
     const uint32_t sval_s = smem_u32(st.sval), sx_s = smem_u32(st.sx), scol_s = smem_u32(st.slcol);
     for (int rb = 0; rb < nrows; rb += Gr) {
       const int r = rb + g;
       const bool act = r < nrows;
       int k = act ? srow[r] - a0 + l : 0;
       const int e = act ? srow[r + 1] - a0 : 0;
-      const double yv = rb == 0 ? ypre : ((a.read_y && act && l == 0) ? a.y[d.r0 + r] : 0.0);
+      const double yv = rb == 0 ? ypre : ((a.read_y && act && l == 0) ? a.y[r0 + r] : 0.0);
       double sum = 0.0;
       for (; k < e; k += 4 << lv) {
         double xv[4], vv[4];
@@ -638,7 +663,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_spmv_ring(const SpmvArgs a, con
           sum += __shfl_down_sync(0xffffffffu, sum, off, 1 << lv);
       }
       if (act && l == 0) // cli/verification.cpp:64  y[i] = alpha * y0 + beta * y[i]
-        emit_y(a.y, a.push, d.r0 + r, a.alpha * sum + a.beta * yv);
+        emit_y(a.y, a.push, r0 + r, a.alpha * sum + a.beta * yv);
     }
     __syncthreads(); // every thread has left stage s (and has stored its rows)
     if (HALO && i < h.n_boundary && tid == 0) {
@@ -649,17 +674,22 @@ __global__ void __launch_bounds__(kThreads, 2) k_spmv_ring(const SpmvArgs a, con
       }
     }
     const int nxt = i + S * G;
-    if (tid < 32 && nxt < nt) { // refill the stage just left
+    if (tid < 32 && nxt < nt) { // refill the stage just left with the row block fetched one iteration ago
       if (HALO && nxt < h.n_boundary) {
         if (lane == 0)
           halo_wait(h);
         __syncwarp();
       }
-      ring_issue(a, load_desc(a.desc, nxt), st, &bar[s], lane);
+      ring_issue(a, ahead, st, sdesc[s], &bar[s], lane);
+      if (nxt + G < nt)
+        ahead = ring_fetch(a, nxt + G, lane);
+    }
+    if (++s == S) {
+      s = 0;
+      parity ^= 1u;
     }
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------
 // MIXED tiles
