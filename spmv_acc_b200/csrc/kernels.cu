@@ -512,16 +512,14 @@ __device__ __forceinline__ RingStage ring_stage(unsigned char *base, int cap, in
   return st;
 }
 
-// What warp 0 needs to issue the copies of one row block: its descriptor and (one segment per lane) its XDesc entry.
-// Fetched one row block ahead, so that the two dependent global round trips (descriptor, segment table) are not paid
-// between two row blocks: with them in the loop every row block cost ~2.8 us whatever its size.
+// What the producer warp needs to issue the copies of one row block: its descriptor and (one segment per lane) its
+// XDesc entry. Both are fetched ahead of their use (the descriptor two row blocks ahead, the segment table one), so that
+// the two dependent global round trips are not paid between two row blocks.
 struct RingFetch {
   TileDesc d;
   int nseg, line, off, end; // this lane's segment: lines [line, line + end - off) of x to line `off` of the stage
 };
-__device__ __forceinline__ RingFetch ring_fetch(const SpmvArgs &a, int j, int lane) {
-  RingFetch f;
-  f.d = load_desc(a.desc, j);
+__device__ __forceinline__ void ring_fetch_segments(const SpmvArgs &a, RingFetch &f, int lane) {
   const XDesc *__restrict__ xd = a.xdesc + f.d.tile;
   f.nseg = __ldg(&xd->nseg);
   // (lanes beyond nseg read entries that exist -- the table has kXsegMax slots -- and ignore them)
@@ -529,12 +527,13 @@ __device__ __forceinline__ RingFetch ring_fetch(const SpmvArgs &a, int j, int la
   f.line = __ldg(&xd->line[sl]);
   f.off = (int)__ldg(&xd->off[sl]);
   const int nxt = (int)__ldg(&xd->off[sl + 1 < kXsegMax ? sl + 1 : kXsegMax - 1]);
-  f.end = lane + 1 < f.nseg ? nxt : __ldg(&xd->nlines);
-  return f;
+  const int nlines = __ldg(&xd->nlines); // (unconditional: a load predicated on nseg would wait for nseg first)
+  f.end = lane + 1 < f.nseg ? nxt : nlines;
 }
 
-// warp 0: all copies of one row block into one stage (see tile_issue_loads_xs for the x segments); srow[0] will hold
-// rowptr[r0 & ~3]; the four descriptor fields the consumers need go to sdesc
+// producer warp: all copies of one row block into one stage (see tile_issue_loads_xs for the x segments); srow[0] will
+// hold rowptr[r0 & ~3]; the four descriptor fields the consumers need go to sdesc. Everything written here with plain
+// stores precedes lane 0's arrive on the stage's barrier, which the consumers wait for.
 __device__ __forceinline__ void ring_issue(const SpmvArgs &a, const RingFetch &f, const RingStage &st, int *sdesc,
                                            unsigned long long *bar, int lane) {
   const TileDesc &d = f.d;
@@ -565,15 +564,21 @@ __device__ __forceinline__ void ring_issue(const SpmvArgs &a, const RingFetch &f
     if (elems & 1)
       st.sx[(long long)f.off * 16 + elems - 1] = __ldg(a.x + (long long)f.line * 16 + elems - 1);
   }
+  // what 16-byte copies cannot bring (ends of the arrays): plain loads
+  for (int i = cnt + lane; i < span; i += 32) {
+    st.sval[i] = ld_stream_f64(a.val + a0 + i);
+    st.slcol[i] = __ldg(a.lcol + ((long long)a0 - a.lcol_base) + i);
+  }
+  for (int i = rcnt + lane; i < rspan; i += 32)
+    st.srow[i] = __ldg(a.rowptr + rbase + i);
   unsigned int total = xbytes;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
     total += __shfl_xor_sync(0xffffffffu, total, o);
   total += (unsigned int)cnt * 10u + (unsigned int)rcnt * 4u;
-  if (lane == 0)
-    mbar_arrive_expect_tx(bar, total);
   __syncwarp();
   if (lane == 0) {
+    mbar_arrive_expect_tx(bar, total);
     const unsigned long long pol = policy_evict_first();
     if (cnt > 0) {
       tma_bulk_g2s(st.sval, a.val + a0, (uint32_t)cnt * 8u, bar, pol);
@@ -582,68 +587,95 @@ __device__ __forceinline__ void ring_issue(const SpmvArgs &a, const RingFetch &f
     if (rcnt > 0)
       tma_bulk_g2s_nohint(st.srow, a.rowptr + rbase, (uint32_t)rcnt * 4u, bar);
   }
+  __syncwarp();
   if (xbytes > 0)
     tma_bulk_g2s_nohint(st.sx + (long long)f.off * 16, a.x + (long long)f.line * 16, xbytes, bar);
-  // what 16-byte copies cannot bring (ends of the arrays): plain loads; the consumers see them after the CTA barrier
-  // that separates this issue from the stage's use
-  for (int i = cnt + lane; i < span; i += 32) {
-    st.sval[i] = ld_stream_f64(a.val + a0 + i);
-    st.slcol[i] = __ldg(a.lcol + ((long long)a0 - a.lcol_base) + i);
-  }
-  for (int i = rcnt + lane; i < rspan; i += 32)
-    st.srow[i] = __ldg(a.rowptr + rbase + i);
 }
 
+// barrier of the kThreads consumer threads only (the producer warp never joins it)
+__device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
+
+// kThreads consumer threads (8 warps) and kRingProducers producer warps. Per stage two mbarriers: `full` (the producer's
+// arrive plus the bytes of the copies) and `empty` (one arrive per consumer warp once it has read its last element of
+// the stage). The producers run up to S row blocks ahead of the consumers; neither side ever waits at a CTA-wide
+// barrier. One producer warp needs ~450 dependent instructions per row block (~2700 cycles: ncu showed it never waiting
+// for a free stage while the consumers waited 35 % of their time for a full one), so the row blocks of a CTA alternate
+// between two of them.
+constexpr int kRingProducers = 2;
+constexpr int kRingThreads = kThreads + 32 * kRingProducers;
+constexpr int kRingConsumerWarps = kThreads / 32;
+
 template <bool VEC, bool HALO>
-__global__ void __launch_bounds__(kThreads, 2) k_spmv_ring(const SpmvArgs a, const HaloSync h) {
+__global__ void __launch_bounds__(kRingThreads, VEC ? 2 : 3) k_spmv_ring(const SpmvArgs a, const HaloSync h) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long bar[kRingStagesMax];
+  __shared__ __align__(8) unsigned long long full[kRingStagesMax], empty[kRingStagesMax];
   __shared__ int sdesc[kRingStagesMax][4];
   const int tid = threadIdx.x, lane = tid & 31;
   const int S = a.ring_stages, G = (int)gridDim.x, nt = a.ntiles;
   if ((int)blockIdx.x >= nt)
     return;
   if (tid == 0)
-    for (int s = 0; s < S; ++s)
-      mbar_init(&bar[s], 1);
-  __syncthreads();
-  RingFetch ahead; // warp 0: the row block that will refill the stage being summed
-  ahead.nseg = 0;
-  if (tid < 32) { // prologue: the first S row blocks of this CTA
     for (int s = 0; s < S; ++s) {
-      const int j = (int)blockIdx.x + s * G;
-      if (j < nt) {
-        if (HALO && j < h.n_boundary) { // the x segments of a boundary row block include halo entries
-          if (lane == 0)
-            halo_wait(h);
-          __syncwarp();
-        }
-        ring_issue(a, ring_fetch(a, j, lane), ring_stage(smem_raw + (size_t)s * a.ring_stage_bytes, a.cap, a.xcap),
-                   sdesc[s], &bar[s], lane);
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kRingConsumerWarps);
+    }
+  __syncthreads();
+  if (tid >= kThreads) { // ---- producer warps: warp p issues the CTA's row blocks p, p + P, p + 2P, ... ----
+    const int p = (tid - kThreads) >> 5, step = kRingProducers * G;
+    RingFetch cur, nxt; // cur: complete; nxt: descriptor only
+    int i = (int)blockIdx.x + p * G;
+    if (i >= nt)
+      return;
+    cur.d = load_desc(a.desc, i);
+    if (i + step < nt)
+      nxt.d = load_desc(a.desc, i + step);
+    ring_fetch_segments(a, cur, lane);
+    int s = p; // stage of the CTA's k-th row block: k mod S, barrier phase (k / S) & 1
+    uint32_t eparity = 1u; // a fresh barrier passes a wait on parity 1: the first S stages are free
+    while (s >= S) {
+      s -= S;
+      eparity ^= 1u;
+    }
+    for (; i < nt; i += step) {
+      mbar_wait(&empty[s], eparity);
+      if (HALO && i < h.n_boundary) { // the x segments of a boundary row block include halo entries
+        if (lane == 0)
+          halo_wait(h);
+        __syncwarp();
+      }
+      ring_issue(a, cur, ring_stage(smem_raw + (size_t)s * a.ring_stage_bytes, a.cap, a.xcap), sdesc[s], &full[s], lane);
+      if (i + step < nt) {
+        cur.d = nxt.d;
+        ring_fetch_segments(a, cur, lane); // its descriptor was requested one round ago
+        if (i + 2 * step < nt)
+          nxt.d = load_desc(a.desc, i + 2 * step);
+      }
+      s += kRingProducers;
+      while (s >= S) {
+        s -= S;
+        eparity ^= 1u;
       }
     }
-    if ((int)blockIdx.x + S * G < nt)
-      ahead = ring_fetch(a, (int)blockIdx.x + S * G, lane);
+    return;
   }
-  __syncthreads();
+  // ---- consumers ----
   int s = 0;
   uint32_t parity = 0u; // stage and barrier phase of the row block being summed (no division by the run-time S)
   for (int i = (int)blockIdx.x; i < nt; i += G) {
     const RingStage st = ring_stage(smem_raw + (size_t)s * a.ring_stage_bytes, a.cap, a.xcap);
+    mbar_wait(&full[s], parity);
     const int r0 = sdesc[s][0], nrows = sdesc[s][1] - r0, e0 = sdesc[s][2], e1 = sdesc[s][3];
     const int a0 = e0 & ~7;
     const int *srow = st.srow + (r0 & 3);
     const int lv = VEC ? lanes_log2(e1 - e0, nrows, a.vec_div) : 0; // lanes per row, as in rows_tile
     const int Gr = kThreads >> lv, g = tid >> lv, l = tid & ((1 << lv) - 1);
-    const double ypre = (a.read_y && l == 0 && g < nrows) ? a.y[r0 + g] : 0.0; // in flight during the wait below
-    mbar_wait(&bar[s], parity);
     const uint32_t sval_s = smem_u32(st.sval), sx_s = smem_u32(st.sx), scol_s = smem_u32(st.slcol);
     for (int rb = 0; rb < nrows; rb += Gr) {
       const int r = rb + g;
       const bool act = r < nrows;
       int k = act ? srow[r] - a0 + l : 0;
       const int e = act ? srow[r + 1] - a0 : 0;
-      const double yv = rb == 0 ? ypre : ((a.read_y && act && l == 0) ? a.y[r0 + r] : 0.0);
+      const double yv = (a.read_y && act && l == 0) ? a.y[r0 + r] : 0.0; // in flight during the row sum
       double sum = 0.0;
       for (; k < e; k += 4 << lv) {
         double xv[4], vv[4];
@@ -665,24 +697,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_spmv_ring(const SpmvArgs a, con
       if (act && l == 0) // cli/verification.cpp:64  y[i] = alpha * y0 + beta * y[i]
         emit_y(a.y, a.push, r0 + r, a.alpha * sum + a.beta * yv);
     }
-    __syncthreads(); // every thread has left stage s (and has stored its rows)
-    if (HALO && i < h.n_boundary && tid == 0) {
-      __threadfence_system();
-      if (atomicAdd(h.state + 1, 1u) == (unsigned int)h.n_boundary - 1u) { // last boundary row block of the iteration
-        st_volatile_u32(h.state + 1, 0u);
-        halo_signal(h);
+    __syncwarp();
+    if (lane == 0)
+      mbar_arrive(&empty[s]); // this warp has left stage s
+    if (HALO && i < h.n_boundary) {
+      consumers_sync(); // every row of the boundary row block is stored (and pushed)
+      if (tid == 0) {
+        __threadfence_system();
+        if (atomicAdd(h.state + 1, 1u) == (unsigned int)h.n_boundary - 1u) { // last boundary row block of the iteration
+          st_volatile_u32(h.state + 1, 0u);
+          halo_signal(h);
+        }
       }
-    }
-    const int nxt = i + S * G;
-    if (tid < 32 && nxt < nt) { // refill the stage just left with the row block fetched one iteration ago
-      if (HALO && nxt < h.n_boundary) {
-        if (lane == 0)
-          halo_wait(h);
-        __syncwarp();
-      }
-      ring_issue(a, ahead, st, sdesc[s], &bar[s], lane);
-      if (nxt + G < nt)
-        ahead = ring_fetch(a, nxt + G, lane);
     }
     if (++s == S) {
       s = 0;
@@ -1134,15 +1160,15 @@ static HaloKernel ring_kernel(int kind, bool halo) {
     return halo ? k_spmv_ring<false, true> : k_spmv_ring<false, false>;
   return halo ? k_spmv_ring<true, true> : k_spmv_ring<true, false>;
 }
-// CTAs per SM and stages per CTA for the plan's tile size: two CTAs (16 warps sum while the copies of the next row
-// blocks are in flight) with as many stages as fit, at least two; SPMV_B200_RING_CTAS / SPMV_B200_RING_STAGES override
+// CTAs per SM and stages per CTA for the plan's tile size: two CTAs (three for SHORT row blocks, whose kernel fits 64
+// registers) with as many stages as fit, at least two; SPMV_B200_RING_CTAS / SPMV_B200_RING_STAGES override
 static bool ring_geometry(const spmv_b200_plan *p, int kind, int *ctas, int *stages) {
   int max_optin = 0;
   if (cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device) != cudaSuccess)
     return false;
   const size_t per_sm = 228 * 1024, stage = ring_stage_bytes(p, kind);
   const char *ec = getenv("SPMV_B200_RING_CTAS"), *es = getenv("SPMV_B200_RING_STAGES");
-  for (int c = ec ? atoi(ec) : 2; c >= 1; --c) {
+  for (int c = ec ? atoi(ec) : (kind == SPMV_B200_KIND_SHORT ? 3 : 2); c >= 1; --c) {
     const size_t budget = per_sm / (size_t)c - 2048; // 1 KB per CTA is reserved by the system, some static shared memory
     int s = (int)(budget / stage);
     if ((size_t)s * stage > (size_t)max_optin)
@@ -1154,7 +1180,7 @@ static bool ring_geometry(const spmv_b200_plan *p, int kind, int *ctas, int *sta
     if (s >= 2) {
       int occ = 0; // registers may allow fewer CTAs than the shared memory does (the query needs the raised limit)
       if (set_smem(ring_kernel(kind, true), (size_t)s * stage) != SPMV_B200_OK ||
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel(kind, true), kThreads, (size_t)s * stage) !=
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel(kind, true), kRingThreads, (size_t)s * stage) !=
               cudaSuccess ||
           occ < c) {
         cudaGetLastError();
@@ -1458,7 +1484,7 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
       B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
       const int grid = a.ntiles < sms * p->ring_ctas ? a.ntiles : sms * p->ring_ctas;
       HaloSync none = {};
-      ring_kernel(k, false)<<<grid, kThreads, (size_t)p->ring_stages * ring_stage_bytes(p, k), stream>>>(a, none);
+      ring_kernel(k, false)<<<grid, kRingThreads, (size_t)p->ring_stages * ring_stage_bytes(p, k), stream>>>(a, none);
     } else if (use_xs(p, x)) {
       a.cap = xs_cap_for(p, k);
       a.xcap = xs_xcap(p);
@@ -1520,7 +1546,7 @@ int kernels_launch_halo(const spmv_b200_plan *p, const TileDesc *desc, const dou
     int sms = 0;
     B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
     const int grid = p->ntiles < sms * p->ring_ctas ? p->ntiles : sms * p->ring_ctas;
-    ring_kernel(kind, true)<<<grid, kThreads, (size_t)p->ring_stages * ring_stage_bytes(p, kind), stream>>>(a, sync);
+    ring_kernel(kind, true)<<<grid, kRingThreads, (size_t)p->ring_stages * ring_stage_bytes(p, kind), stream>>>(a, sync);
   } else if (use_xs(p, x)) {
     a.cap = xs_cap_for(p, kind);
     a.xcap = xs_xcap(p);
