@@ -1168,7 +1168,8 @@ static bool ring_geometry(const spmv_b200_plan *p, int kind, int *ctas, int *sta
     return false;
   const size_t per_sm = 228 * 1024, stage = ring_stage_bytes(p, kind);
   const char *ec = getenv("SPMV_B200_RING_CTAS"), *es = getenv("SPMV_B200_RING_STAGES");
-  for (int c = ec ? atoi(ec) : (kind == SPMV_B200_KIND_SHORT ? 3 : 2); c >= 1; --c) {
+  const int cdef = kind == SPMV_B200_KIND_SHORT ? 3 : 2;
+  for (int c = (ec && atoi(ec) > 0) ? atoi(ec) : cdef; c >= 1; --c) {
     const size_t budget = per_sm / (size_t)c - 2048; // 1 KB per CTA is reserved by the system, some static shared memory
     int s = (int)(budget / stage);
     if ((size_t)s * stage > (size_t)max_optin)
