@@ -388,21 +388,24 @@ def run_b200(args, rank, world, local_rank):
     line["verified"] = bool(ok_all)
     line["verification"] = ver
 
-    # ---- the exchange BASELINE.json names (NCCL all-gather of x) and the launch forms, beside the headline ----
+    # ---- the exchange BASELINE.json names (NCCL all-gather of x) and the launch forms, beside the headline; the same
+    # number of iterations from the same x_0, so that every mode must end with the same x (x_checksum_first_16th) ----
     iterated = {"fused": head}
     if not args.no_iterated and world > 1:
         for mode in ("nccl_allgather", "nccl_halo", "fused_multi_launch"):
             try:
-                iterated[mode] = sharded.time_power_loop(shard, mode, iters=min(args.steps, 100), warmup=4)
+                iterated[mode] = sharded.time_power_loop(shard, mode, iters=args.steps, warmup=args.warmup)
             except Exception as e:
                 iterated[mode] = {"error": f"{type(e).__name__}: {e}"}
     elif not args.no_iterated and not args.quick:
         try:
             iterated["fused_multi_launch"] = sharded.time_power_loop(shard, "fused_multi_launch",
-                                                                    iters=min(args.steps, 100), warmup=4)
+                                                                    iters=args.steps, warmup=args.warmup)
         except Exception as e:
             iterated["fused_multi_launch"] = {"error": f"{type(e).__name__}: {e}"}
     line["iterated"] = iterated
+    sums = {r.get("x_checksum_first_16th") for r in iterated.values() if "error" not in r}
+    line["iterated_checksums_agree"] = len(sums) == 1
 
     # ---- e2e: the reference-facing host-buffer call on the same workload (H2D x; SpMV; D2H y every step) ----
     if not args.no_e2e:

@@ -102,6 +102,7 @@ struct SpmvArgs {
   const int *__restrict__ nz_rows;                 // direct form only
   int read_y;   // 0: beta == 0 and SPMV_B200_FLAG_BETA0_SKIP_Y
   int gather_na; // 1: x gathers use L1::no_allocate
+  int stream_keep; // 1: matrix streams with the normal L2 policy instead of evict-first (small matrices)
   // staged-x form only
   const unsigned short *__restrict__ lcol; // 16-bit offsets into the staged x, indexed like col minus lcol_base
   const XDesc *__restrict__ xdesc;         // by tile id
@@ -167,6 +168,7 @@ struct spmv_b200_plan {
   b200::XDesc *xdesc = nullptr;
   long long lcol_base = 0;
   int xlines = 0; // largest number of staged lines of any row block
+  int stream_keep = 0; // matrix streams with the normal L2 policy (see policy_stream in kernels.cu)
   int ring_ctas = 0, ring_stages = 0; // persistent ring form of the staged-x kernels: CTAs per SM, stages per CTA (0: off)
   // device arrays owned by the plan
   int *tile_row = nullptr;

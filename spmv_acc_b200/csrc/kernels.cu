@@ -71,6 +71,16 @@ __device__ __forceinline__ unsigned long long policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+// L2 policy of the matrix streams: evict-first when the matrix is much larger than the L2 (every byte is read once per
+// SpMV and should not displace x); normal when it is small enough for part of it to survive until the next SpMV
+__device__ __forceinline__ unsigned long long policy_stream(int keep) {
+  unsigned long long pol;
+  if (keep)
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  else
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 
 __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,
                                              unsigned long long *bar, unsigned long long policy) {
@@ -144,7 +154,7 @@ __device__ __forceinline__ void tile_issue_loads(const SpmvArgs &a, int a0, int 
       cnt = (int)(avail & ~3LL);
     if (tid == 0) {
       if (cnt > 0) {
-        const unsigned long long pol = policy_evict_first();
+        const unsigned long long pol = policy_stream(a.stream_keep);
         mbar_arrive_expect_tx(bar, (uint32_t)cnt * 12u);
         tma_bulk_g2s(sval, a.val + a0, (uint32_t)cnt * 8u, bar, pol);
         tma_bulk_g2s(scol, a.col + a0, (uint32_t)cnt * 4u, bar, pol);
@@ -210,7 +220,7 @@ __device__ __forceinline__ void tile_issue_loads_xs(const SpmvArgs &a, int tile,
     }
     __syncwarp();
     if (tid == 0 && cnt > 0) {
-      const unsigned long long pol = policy_evict_first(); // the streams are read exactly once
+      const unsigned long long pol = policy_stream(a.stream_keep);
       tma_bulk_g2s(sval, a.val + a0, (uint32_t)cnt * 8u, bar, pol);
       tma_bulk_g2s(slcol, a.lcol + ((long long)a0 - a.lcol_base), (uint32_t)cnt * 2u, bar, pol);
     }
@@ -579,7 +589,7 @@ __device__ __forceinline__ void ring_issue(const SpmvArgs &a, const RingFetch &f
   __syncwarp();
   if (lane == 0) {
     mbar_arrive_expect_tx(bar, total);
-    const unsigned long long pol = policy_evict_first();
+    const unsigned long long pol = policy_stream(a.stream_keep);
     if (cnt > 0) {
       tma_bulk_g2s(st.sval, a.val + a0, (uint32_t)cnt * 8u, bar, pol);
       tma_bulk_g2s(st.slcol, a.lcol + ((long long)a0 - a.lcol_base), (uint32_t)cnt * 2u, bar, pol);
@@ -636,12 +646,14 @@ __global__ void __launch_bounds__(kRingThreads, VEC ? 2 : 3) k_spmv_ring(const S
       s -= S;
       eparity ^= 1u;
     }
+    bool halo_seen = false; // the neighbours' flags are polled once per producer warp and launch
     for (; i < nt; i += step) {
       mbar_wait(&empty[s], eparity);
-      if (HALO && i < h.n_boundary) { // the x segments of a boundary row block include halo entries
+      if (HALO && i < h.n_boundary && !halo_seen) { // the x segments of a boundary row block include halo entries
         if (lane == 0)
           halo_wait(h);
         __syncwarp();
+        halo_seen = true;
       }
       ring_issue(a, cur, ring_stage(smem_raw + (size_t)s * a.ring_stage_bytes, a.cap, a.xcap), sdesc[s], &full[s], lane);
       if (i + step < nt) {
@@ -700,11 +712,16 @@ __global__ void __launch_bounds__(kRingThreads, VEC ? 2 : 3) k_spmv_ring(const S
     __syncwarp();
     if (lane == 0)
       mbar_arrive(&empty[s]); // this warp has left stage s
-    if (HALO && i < h.n_boundary) {
-      consumers_sync(); // every row of the boundary row block is stored (and pushed)
+    if (HALO && i < h.n_boundary && i + G >= h.n_boundary) { // this CTA's last boundary row block
+      // One system-scope fence per CTA and launch, not per row block: it waits for the NVLink stores of the pushed
+      // rows to be acknowledged (microseconds), and with one per boundary row block the single-launch loop ran 3 %
+      // behind the multi-launch one at two GPUs. The barrier orders every consumer warp's stores of all this CTA's
+      // boundary row blocks before thread 0's fence; the counter counts CTAs that own boundary row blocks.
+      consumers_sync();
       if (tid == 0) {
         __threadfence_system();
-        if (atomicAdd(h.state + 1, 1u) == (unsigned int)h.n_boundary - 1u) { // last boundary row block of the iteration
+        const unsigned int owners = (unsigned int)(h.n_boundary < G ? h.n_boundary : G);
+        if (atomicAdd(h.state + 1, 1u) == owners - 1u) { // last CTA of the iteration to finish its boundary row blocks
           st_volatile_u32(h.state + 1, 0u);
           halo_signal(h);
         }
@@ -1281,6 +1298,7 @@ int kernels_configure(spmv_b200_plan *p) {
       return SPMV_B200_ERR_ARG;
     }
   p->device = dev;
+  p->stream_keep = (int)((p->flags >> 27) & 1u); // tuning bit 27 (experiment: matrices that fit the L2)
   if (p->flags & SPMV_B200_FLAG_L2_PERSIST_X) {
     int persist_max = 0, window_max = 0;
     B200_CUDA(cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, dev));
@@ -1415,6 +1433,7 @@ static void fill_args(const spmv_b200_plan *p, double alpha, double beta, const 
   a->nnz = p->elem_end; // absolute index one past the last element (rowptr may be a view: rowptr[0] != 0)
   a->vec_div = p->vec_div;
   a->gather_na = (p->flags & (1u << 16)) ? 2 : ((p->flags & SPMV_B200_FLAG_GATHER_NO_L1) ? 1 : 0);
+  a->stream_keep = p->stream_keep;
   a->read_y = (beta == 0.0 && (p->flags & SPMV_B200_FLAG_BETA0_SKIP_Y)) ? 0 : 1;
   a->row_start_bits = p->row_start_bits;
   a->nz_rows = p->nz_rows;
