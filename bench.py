@@ -67,7 +67,8 @@ def profiled_traffic(key):
     p = ROOT / "profiles" / "ncu_traffic.json"
     try:
         rec = json.loads(p.read_text())[key]
-        return rec["dram_bytes_per_launch"], f"profiles/{rec['source']} (ncu --set full, same kernel and matrix)"
+        note = f"; {rec['note']}" if rec.get("note") else ""
+        return rec["dram_bytes_per_launch"], f"profiles/{rec['source']} (ncu --set full, same kernel and matrix{note})"
     except Exception:
         return None, "no ncu capture for this configuration"
 

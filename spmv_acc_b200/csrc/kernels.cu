@@ -1298,7 +1298,15 @@ int kernels_configure(spmv_b200_plan *p) {
       return SPMV_B200_ERR_ARG;
     }
   p->device = dev;
-  p->stream_keep = (int)((p->flags >> 27) & 1u); // tuning bit 27 (experiment: matrices that fit the L2)
+  {
+    // matrices whose streams fit the L2 with room to spare are kept there between SpMVs (normal policy instead of
+    // evict-first): 67 MB stand-in for largebasis 15.2 -> 13.2 us; at 345 MB (boneS10) the same switch costs 19 %
+    // (profiles/r2_sweep_small_matrices_l2_policy.jsonl). Tuning bit 27 inverts the choice.
+    int l2 = 0;
+    B200_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
+    const bool fits = (double)p->nnz * 12.0 <= 0.6 * (double)l2;
+    p->stream_keep = (int)(fits != (((p->flags >> 27) & 1u) != 0));
+  }
   if (p->flags & SPMV_B200_FLAG_L2_PERSIST_X) {
     int persist_max = 0, window_max = 0;
     B200_CUDA(cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, dev));
