@@ -140,6 +140,10 @@ int spmv_b200_execute_tiles_push(spmv_b200_plan *plan, double alpha, double beta
 /* smallest / largest column index referenced by each tile (h_min / h_max: int32 [ntiles]; INT32_MAX / -1 if empty):
  * a sharded caller uses it to find the row blocks that read entries of x owned by other GPUs */
 int spmv_b200_plan_tile_col_range(spmv_b200_plan *plan, int32_t *h_min, int32_t *h_max, void *stream);
+/* Multi-GPU callers that run a collective (NCCL) next to spmv_b200_execute_tiles: leave `sms` SMs free. Plans in the
+ * persistent form fill every SM with CTAs that stay until the launch ends, so a communication kernel launched beside
+ * them would otherwise wait for the whole SpMV. 0 (default) = use every SM. Applies to execute / execute_tiles. */
+int spmv_b200_plan_set_comm_sms(spmv_b200_plan *plan, int32_t sms);
 int spmv_b200_enable_peer_access(int32_t peer_device);
 
 /* The iterated loop x <- A*x of one rank (one row shard) with the halo exchange fused into the SpMV kernels. Iteration k

@@ -15,6 +15,7 @@ LIB_DIR = PKG / "lib"
 ABI_SYMBOLS = [
     "spmv_b200_abi_version", "spmv_b200_last_error", "spmv_b200_plan_create", "spmv_b200_execute",
     "spmv_b200_execute_tiles", "spmv_b200_execute_push", "spmv_b200_execute_tiles_push", "spmv_b200_plan_tile_col_range",
+    "spmv_b200_plan_set_comm_sms",
     "spmv_b200_halo_loop_create", "spmv_b200_halo_loop_run", "spmv_b200_halo_loop_sync", "spmv_b200_halo_loop_get_info",
     "spmv_b200_halo_loop_destroy", "spmv_b200_enable_peer_access", "spmv_b200_peer_alloc", "spmv_b200_peer_open",
     "spmv_b200_peer_close", "spmv_b200_peer_free", "spmv_b200_cache_revalidations",
@@ -112,6 +113,7 @@ def lib() -> C.CDLL:
         L.spmv_b200_execute_push.argtypes = [vp, dbl, dbl, vp, vp, C.POINTER(Push), vp]
         L.spmv_b200_execute_tiles_push.argtypes = [vp, dbl, dbl, vp, vp, i32, i32, C.POINTER(Push), vp]
         L.spmv_b200_plan_tile_col_range.argtypes = [vp, vp, vp, vp]
+        L.spmv_b200_plan_set_comm_sms.argtypes = [vp, i32]
         L.spmv_b200_halo_loop_create.argtypes = [C.POINTER(vp), C.POINTER(HaloLoopDesc)]
         L.spmv_b200_halo_loop_run.argtypes = [vp, i32, vp]
         L.spmv_b200_halo_loop_sync.argtypes = [vp, vp]

@@ -137,6 +137,12 @@ class SpmvPlan:
                                           _current_stream() if stream is None else stream)
         check(rc, "execute")
 
+    def set_comm_sms(self, sms: int) -> None:
+        """Leave ``sms`` SMs free for a collective running beside the SpMV launches (persistent form only)."""
+        if not self._h:
+            raise SpmvB200Error("plan was destroyed")
+        check(_lib.lib().spmv_b200_plan_set_comm_sms(self._h, int(sms)), "plan_set_comm_sms")
+
     def execute_tiles(self, alpha: float, beta: float, dx: Any, dy: Any, tile_lo: int, tile_hi: int,
                       stream: Optional[int] = None) -> None:
         """Row blocks [tile_lo, tile_hi) only (``export("tile_row")`` gives their row ranges); no split rows allowed."""

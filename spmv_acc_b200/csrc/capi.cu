@@ -325,6 +325,15 @@ int spmv_b200_execute_tiles_push(spmv_b200_plan *plan, double alpha, double beta
   return kernels_launch_tiles(plan, alpha, beta, d_x, d_y, tile_lo, tile_hi, static_cast<cudaStream_t>(stream), &pa);
 }
 
+int spmv_b200_plan_set_comm_sms(spmv_b200_plan *plan, int32_t sms) {
+  if (!plan || sms < 0) {
+    set_error("plan_set_comm_sms: plan is NULL or sms < 0");
+    return SPMV_B200_ERR_ARG;
+  }
+  plan->comm_sms = sms;
+  return SPMV_B200_OK;
+}
+
 int spmv_b200_plan_tile_col_range(spmv_b200_plan *plan, int32_t *h_min, int32_t *h_max, void *stream) {
   if (!plan || !h_min || !h_max) {
     set_error("plan_tile_col_range: NULL argument");

@@ -169,6 +169,7 @@ struct spmv_b200_plan {
   long long lcol_base = 0;
   int xlines = 0; // largest number of staged lines of any row block
   int stream_keep = 0; // matrix streams with the normal L2 policy (see policy_stream in kernels.cu)
+  int comm_sms = 0;    // SMs the persistent form leaves free for a concurrently running collective
   int ring_ctas = 0, ring_stages = 0; // persistent ring form of the staged-x kernels: CTAs per SM, stages per CTA (0: off)
   // device arrays owned by the plan
   int *tile_row = nullptr;

@@ -1510,6 +1510,8 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
       a.ring_stage_bytes = (int)ring_stage_bytes(p, k);
       int sms = 0;
       B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
+      if (p->comm_sms > 0) // room for a collective running beside this launch (spmv_b200_plan_set_comm_sms)
+        sms = sms - p->comm_sms > 8 ? sms - p->comm_sms : 8;
       const int grid = a.ntiles < sms * p->ring_ctas ? a.ntiles : sms * p->ring_ctas;
       HaloSync none = {};
       ring_kernel(k, false)<<<grid, kRingThreads, (size_t)p->ring_stages * ring_stage_bytes(p, k), stream>>>(a, none);

@@ -20,6 +20,7 @@ values, only on its own rowptr).
 """
 from __future__ import annotations
 
+import os
 import time
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional, Tuple
@@ -184,7 +185,9 @@ class PowerLoop:
         self.overlapped = True
         if self.x.is_cuda:
             import torch
-            self.comm_stream = torch.cuda.Stream()
+            # high priority: when the collective's CTAs and the SpMV's are both waiting for an SM, the collective's go
+            # first (its duration, not the SpMV's, bounds the iteration)
+            self.comm_stream = torch.cuda.Stream(priority=-1)
 
     def _allgather(self, v):
         """Every rank's slice of v to every rank, one collective."""
@@ -196,14 +199,26 @@ class PowerLoop:
                 if np.all(sizes == sizes[0]):
                     dist.all_gather_into_tensor(v, v[lo:hi])  # in place: ncclAllGather, no staging copy
                 else:
-                    # unequal slices: ProcessGroupNCCL turns this into ONE ncclGroup of broadcasts (all-gather-v)
-                    dist.all_gather([v[int(self.bounds[g]):int(self.bounds[g + 1])] for g in range(self.world)], v[lo:hi])
+                    # Unequal slices (nnz-balanced shards), in place: one NCCL group of point-to-point sends / receives.
+                    # Measured at 8 GPUs on 453 MB of x (profiles/r2_allgather_probe_n8.jsonl): 0.754 ms against 0.868 ms
+                    # for dist.all_gather with a list (a group of broadcasts), 0.910 ms for ncclAllGather of padded
+                    # slots + copies into place, and 0.698 ms for ncclAllGather of equal slices.
+                    ops = []
+                    for d in range(1, self.world):
+                        dst, src = (self.rank + d) % self.world, (self.rank - d) % self.world
+                        a, e = int(self.bounds[src]), int(self.bounds[src + 1])
+                        if hi > lo:
+                            ops.append(dist.P2POp(dist.isend, v[lo:hi], dst))
+                        if e > a:
+                            ops.append(dist.P2POp(dist.irecv, v[a:e], src))
+                    for req in dist.batch_isend_irecv(ops):
+                        req.wait()
                 self._ag_native = True
                 return
             except Exception:
                 if self._ag_native is True:
                     raise
-                self._ag_native = False  # backend without unequal all_gather: broadcasts below
+                self._ag_native = False  # backend without grouped point-to-point: broadcasts below
         for src in range(self.world):
             a, e = int(self.bounds[src]), int(self.bounds[src + 1])
             if e > a:
@@ -489,10 +504,12 @@ def make_loop(shard: Shard, exchange: str = "auto", overlap: bool = True) -> Pow
         plan.execute_tiles(1.0, 0.0, xf, ys, t0, t1)
 
     x = synth.vector_device(shard.n, 2)
-    return PowerLoop(n=shard.n, bounds=shard.bounds, spmv=spmv, x=x, x_next=torch.zeros_like(x),
+    loop = PowerLoop(n=shard.n, bounds=shard.bounds, spmv=spmv, x=x, x_next=torch.zeros_like(x),
                      need_local=shard.need, exchange=exchange,
                      spmv_tiles=spmv_tiles if shard.tile_row is not None else None, tile_row=shard.tile_row,
                      tile_reads_halo=shard.reads_halo, overlap=overlap)
+    loop.plan = plan
+    return loop
 
 
 def build_stencil3d_power_loop(N: int, exchange: str = "auto", options=None, overlap: bool = True):
@@ -563,9 +580,14 @@ def time_power_loop(shard: Shard, mode: str = "fused", iters: int = 100, warmup:
         except Exception as e:  # no peer path / IPC unavailable: keep the NCCL exchange
             native, note = False, f"{type(e).__name__}: {e}"
     use_graph = False
+    comm_sms = 0
     if native:
         run = runner.run
     else:
+        if world > 1 and getattr(loop, "overlapped", False):
+            # the collective runs beside persistent SpMV CTAs: leave it some SMs (spmv_b200_plan_set_comm_sms)
+            comm_sms = int(os.environ.get("SPMV_B200_COMM_SMS", "32"))
+            shard.plan.set_comm_sms(comm_sms)
         if world > 1 and mode.startswith("fused"):
             note = note or f"the halo is not sparse for this matrix (exchange = {loop.mode}): NCCL exchange used"
         try:
@@ -578,18 +600,22 @@ def time_power_loop(shard: Shard, mode: str = "fused", iters: int = 100, warmup:
         except Exception as e:
             note = (note + "; " if note else "") + f"graph capture failed ({type(e).__name__}: {e}); eager launches"
             run = lambda k: loop.run(k, finish=False)  # noqa: E731
-    run(warmup)
-    sync()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if sampler:
-        sampler.start()
-    e0.record()
-    run(iters)
-    e1.record()
-    e1.synchronize()
-    if sampler:
-        sampler.stop()
-    sync()
+    try:
+        run(warmup)
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.start()
+        e0.record()
+        run(iters)
+        e1.record()
+        e1.synchronize()
+        if sampler:
+            sampler.stop()
+        sync()
+    finally:
+        if comm_sms:
+            shard.plan.set_comm_sms(0)
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -608,6 +634,7 @@ def time_power_loop(shard: Shard, mode: str = "fused", iters: int = 100, warmup:
                      "raised inside the kernel" if native else f"NCCL {loop.mode}"),
         "exchange_bytes_in_per_iter_rank0": loop.bytes_in_per_iter,
         "exchange_overlapped_with_local_rows": bool(getattr(loop, "overlapped", False)),
+        "sms_left_to_the_collective": comm_sms,
         "boundary_row_blocks_rank0": int(sum(b - a for a, b in loop.boundary)),
         # bit pattern checksum of this rank-0-owned range after the last iteration: equal values across runs with
         # 1/2/4/8 GPUs and across modes prove bitwise-identical results (n/16 rows belong to rank 0 for <= 8 ranks)
