@@ -393,7 +393,7 @@ def run_b200(args, rank, world, local_rank):
     # number of iterations from the same x_0, so that every mode must end with the same x (x_checksum_first_16th) ----
     iterated = {"fused": head}
     if not args.no_iterated and world > 1:
-        for mode in ("nccl_allgather", "nccl_halo", "fused_multi_launch"):
+        for mode in ("fused_allgather", "nccl_allgather", "nccl_halo", "fused_multi_launch"):
             try:
                 iterated[mode] = sharded.time_power_loop(shard, mode, iters=args.steps, warmup=args.warmup)
             except Exception as e:
@@ -426,6 +426,12 @@ def run_b200(args, rank, world, local_rank):
             ush = sharded.build_shard("uniform", m=10_000_000, k=32)
             rec = sharded.time_power_loop(ush, "fused", iters=20, warmup=4)
             rec["workload"] = f"{ush.name}, values / 32, x <- A*x"
+            try:
+                nc = sharded.time_power_loop(ush, "nccl_allgather", iters=20, warmup=4)
+                rec["nccl_allgather_ms_per_iter"] = nc["ms_per_iter"]
+                rec["checksums_agree"] = nc["x_checksum_first_16th"] == rec["x_checksum_first_16th"]
+            except Exception as e:
+                rec["nccl_allgather_error"] = f"{type(e).__name__}: {e}"
             line["iterated_uniform"] = rec
             ush.destroy()
             del ush

@@ -85,6 +85,26 @@ def exchange_schedule(need: np.ndarray, bounds: np.ndarray, rank: int, shift: in
     return sends, recvs
 
 
+def align_bounds(bounds: np.ndarray, rows: int = 16) -> np.ndarray:
+    """Interior shard boundaries rounded to a multiple of `rows` (16 rows = one 128-byte line of x): a slice of x that
+    starts at an odd element is not 16-byte aligned, and NCCL then moves it 2.5x slower (8 GPUs, 453 MB: 1.78 ms
+    against 0.70 ms, profiles/r2_allgather_loop_probe_n8.jsonl); the nnz balance moves by at most 8 rows."""
+    b = np.asarray(bounds, dtype=np.int64).copy()
+    if b.size > 2:
+        b[1:-1] = np.clip((b[1:-1] + rows // 2) // rows * rows, b[0], b[-1])
+        b = np.maximum.accumulate(b)
+    return b
+
+
+def allgather_schedule(bounds: np.ndarray, rank: int):
+    """(sends, recvs) of the exchange in which every rank's whole slice goes to every other rank."""
+    G = len(bounds) - 1
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    sends = [(p, lo, hi) for p in range(G) if p != rank and hi > lo]
+    recvs = [(p, int(bounds[p]), int(bounds[p + 1])) for p in range(G) if p != rank and bounds[p + 1] > bounds[p]]
+    return sends, recvs
+
+
 def split_boundary_interior(sends, tile_row, tile_reads_halo, lo: int):
     """(boundary, interior) tile ranges of a shard for the halo exchange, or None if most of the shard is boundary.
     Boundary = row blocks that produce a row another rank receives, plus (when known) every row block that reads an
@@ -459,7 +479,7 @@ def build_shard(kind: str = "stencil3d", N: int = 384, m: int = 0, k: int = 32, 
             counts = synth.stencil_row_counts_device("stencil3d", N)
             rowptr = synth._rowptr_from_counts_device(counts)
             del counts
-            bounds = shard_bounds(rowptr, n, world).astype(np.int64)
+            bounds = align_bounds(shard_bounds(rowptr, n, world).astype(np.int64))
             del rowptr
             torch.cuda.empty_cache()
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
@@ -544,7 +564,7 @@ class LocalLoop:
         return self.bufs[self.k % 2]
 
 
-MODES = ("fused", "fused_multi_launch", "nccl_halo", "nccl_allgather")
+MODES = ("fused", "fused_multi_launch", "nccl_halo", "nccl_allgather", "fused_allgather")
 
 
 def time_power_loop(shard: Shard, mode: str = "fused", iters: int = 100, warmup: int = 4, sampler=None) -> dict:
@@ -554,7 +574,9 @@ def time_power_loop(shard: Shard, mode: str = "fused", iters: int = 100, warmup:
     runs through the same native runner), "fused_multi_launch" (the same protocol as separate wait / boundary / flag /
     interior launches without a graph), "nccl_halo" (grouped NCCL send/recv of the halo blocks overlapped with the
     interior row blocks, CUDA graph), "nccl_allgather" (one grouped NCCL all-gather of x per iteration overlapped with
-    the row blocks that read only local columns, CUDA graph)."""
+    the row blocks that read only local columns, CUDA graph), "fused_allgather" (the all-gather done by the SpMV kernel
+    itself: every row is stored into every other GPU's copy of the next x as it is produced, the kernel waits for all
+    peers' flags before its first row block and raises its own after its last; one launch per iteration, no NCCL)."""
     import torch
     from . import _lib
     dist = _dist()
@@ -568,9 +590,19 @@ def time_power_loop(shard: Shard, mode: str = "fused", iters: int = 100, warmup:
 
     warmup = max(4, int(warmup))
     iters = int(iters)
-    exchange = {"nccl_allgather": "allgather", "nccl_halo": "halo"}.get(mode, "auto")
-    loop = make_loop(shard, exchange)
+    exchange = {"nccl_allgather": "allgather", "nccl_halo": "halo", "fused_allgather": "allgather"}.get(mode, "auto")
+    loop = make_loop(shard, exchange, overlap=mode != "fused_allgather")
     native = mode in ("fused", "fused_multi_launch") and (world == 1 or loop.mode == "halo")
+    dense_halo = mode in ("fused", "fused_multi_launch") and world > 1 and loop.mode == "allgather"
+    if (mode == "fused_allgather" or dense_halo) and world > 1:
+        # every rank needs (nearly) all of x: the kernels push whole slices to every peer (whole-shard schedule)
+        if world - 1 > _lib.MAX_PUSH:
+            if mode == "fused_allgather":
+                raise RuntimeError(f"fused all-gather supports at most {_lib.MAX_PUSH + 1} GPUs")
+        else:
+            loop.sends, loop.recvs = allgather_schedule(loop.bounds, rank)
+            loop.overlapped = False
+            native = True
     note = ""
     runner = None
     if native:
@@ -630,6 +662,9 @@ def time_power_loop(shard: Shard, mode: str = "fused", iters: int = 100, warmup:
         "ms_per_iter": sec_iter * 1e3, "value": 2.0 * nnz_total / sec_iter / 1e9, "unit": "GFLOP/s",
         "effective_gbs": (12 * nnz_total + 4 * (n + 1) + 8 * n + 16 * n) / sec_iter / 1e9,
         "exchange": ("none (one rank)" if world == 1 else
+                     "all-gather by the SpMV kernel: every row stored into every peer's next x (NVLink stores), all "
+                     "peers' flags waited for and raised inside the kernel"
+                     if native and (mode == "fused_allgather" or dense_halo) else
                      "halo rows pushed by the SpMV kernels into peer memory (NVLink stores), flags waited for and "
                      "raised inside the kernel" if native else f"NCCL {loop.mode}"),
         "exchange_bytes_in_per_iter_rank0": loop.bytes_in_per_iter,

@@ -23,7 +23,7 @@ sys.path.insert(0, str(ROOT))
 pytestmark = pytest.mark.gpu
 
 
-def _build_ranks(N, world, flags):
+def _build_ranks(N, world, flags, allgather=False):
     import torch
     from spmv_acc_b200 import (CsrDesc, HaloLoop, SpmvPlan, col_block_bitmap, make_options, shard_bounds, sharded,
                                synth, FLAG_BETA0_SKIP_Y)
@@ -44,11 +44,13 @@ def _build_ranks(N, world, flags):
     loops, splits, all_recvs = [], [], []
     for r in range(world):
         lo, hi = int(bounds[r]), int(bounds[r + 1])
-        sends, recvs = sharded.exchange_schedule(need, bounds, r, shift)
+        sends, recvs = (sharded.allgather_schedule(bounds, r) if allgather else
+                        sharded.exchange_schedule(need, bounds, r, shift))
         all_recvs.append(recvs)
         neigh = sorted({p for p, _, _ in sends} | {p for p, _, _ in recvs})
         cmin, cmax = plans[r].tile_col_range()
-        split = sharded.split_boundary_interior(sends, plans[r].export("tile_row"), (cmin < lo) | (cmax >= hi), lo)
+        split = None if allgather else sharded.split_boundary_interior(sends, plans[r].export("tile_row"),
+                                                                       (cmin < lo) | (cmax >= hi), lo)
         splits.append(split is not None)
         push = [[(a - lo, e - lo, bufs[p][b].data_ptr() + 8 * lo) for p, a, e in sends] for b in (0, 1)]
         desc = sharded.make_halo_desc(
@@ -108,6 +110,35 @@ def test_fused_halo_loop_equals_sequential_shards_and_oracle(world, N, flags):
     for _ in range(iters):
         xr = oracle.best_host_spmv(1.0, 0.0, h.rowptr, h.col, h.val, xr, np.zeros(n))
     assert np.max(np.abs(got.cpu().numpy() - xr)) <= 1e-12 * max(1.0, np.max(np.abs(xr)))
+    for lp in R["loops"]:
+        lp.destroy()
+    for p in R["plans"]:
+        p.destroy()
+
+
+@pytest.mark.parametrize("world,N,flags", [(3, 40, 0), (4, 48, 0), (3, 40, 3)])
+def test_fused_allgather_push_leaves_the_whole_x_everywhere(world, N, flags):
+    """The all-gather done by the SpMV kernels: every rank pushes its whole slice to every other rank (whole-shard
+    schedule: all peers' flags are awaited before the first row block, the own flag is raised after the last). After k
+    iterations EVERY rank's buffer must hold the complete x_k, bitwise equal to the sequential shard loop."""
+    import torch
+    R = _build_ranks(N, world, flags, allgather=True)
+    n, bounds, iters = R["n"], R["bounds"], 5
+    for _ in range(iters):
+        for lp in R["loops"]:
+            lp.run(1)
+    for lp in R["loops"]:
+        lp.sync()
+    x, y = R["x0"].clone(), torch.zeros(n, dtype=torch.float64, device="cuda")
+    for _ in range(iters):
+        for r, plan in enumerate(R["plans"]):
+            plan.execute(1.0, 0.0, x, y[int(bounds[r]):int(bounds[r + 1])])
+        x, y = y, x
+    torch.cuda.synchronize()
+    for r in range(world):
+        assert torch.equal(R["bufs"][r][iters % 2], x), f"rank {r} does not hold the whole x after the fused all-gather"
+        fw = R["flag_words"][r].cpu().numpy()
+        assert sorted(np.nonzero(fw)[0].tolist()) == [p for p in range(world) if p != r] and set(fw[fw > 0]) == {iters}
     for lp in R["loops"]:
         lp.destroy()
     for p in R["plans"]:

@@ -112,3 +112,17 @@ def test_two_rank_power_loop_equals_single_process(tmp_path, mode):
     if mode == "halo":
         # z-slab shards of a 27-point stencil need about one plane per neighbour, not the whole vector
         assert max(moved) < 0.5 * 8 * N ** 3 / 2
+
+
+def test_align_bounds_rounds_interior_boundaries_to_lines_of_x():
+    from spmv_acc_b200 import sharded
+    b = np.array([0, 7114817, 14180438, 21246059, 56623104], dtype=np.int64)
+    a = sharded.align_bounds(b)
+    assert a[0] == 0 and a[-1] == b[-1] and np.all(a[1:-1] % 16 == 0) and np.all(np.abs(a - b) <= 8)
+    assert np.all(np.diff(a) >= 0)
+    # degenerate inputs: one shard, empty shards, tiny matrices
+    assert sharded.align_bounds(np.array([0, 100])).tolist() == [0, 100]
+    assert sharded.align_bounds(np.array([0, 3, 3, 5])).tolist() == [0, 0, 0, 5]
+    s, r = sharded.allgather_schedule(a, 1)
+    assert [p for p, _, _ in s] == [0, 2, 3] and all((lo, hi) == (a[1], a[2]) for _, lo, hi in s)
+    assert [(p, lo, hi) for p, lo, hi in r] == [(0, a[0], a[1]), (2, a[2], a[3]), (3, a[3], a[4])]

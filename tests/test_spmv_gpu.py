@@ -112,6 +112,39 @@ def test_staged_x_ring_geometries(ctas, stages, monkeypatch):
         p.destroy()
 
 
+def test_sms_left_to_a_collective_do_not_change_results():
+    """spmv_b200_plan_set_comm_sms: the persistent form launches fewer CTAs (row blocks are dealt to fewer of them); every
+    row must come out bitwise identical, for whole launches and row-block ranges. Plans not in the persistent form ignore
+    the setting."""
+    import torch
+    for name, h in (("stencil3d_40", synth.stencil3d_numpy(40)), ("stencil2d_300", synth.stencil2d_numpy(300)),
+                    ("rmat_12", synth.rmat_numpy(12, 16, seed=1))):
+        x, y0 = synth.vector_numpy(h.cols, 2), synth.vector_numpy(h.rows, 3)
+        d = synth.to_device(h)
+        p = SpmvPlan(desc_of(d))
+        nt = p.info().ntiles
+        dx = torch.from_numpy(x).cuda()
+        outs = []
+        for sms in (0, 16, 140, 1000):
+            p.set_comm_sms(sms)
+            dy = torch.from_numpy(y0).cuda()
+            p.execute(0.75, -0.5, dx, dy)
+            if p.info().nsplit_rows == 0:
+                dy2 = torch.from_numpy(y0).cuda()
+                for lo, hi in ((0, nt // 2), (nt // 2, nt)):
+                    p.execute_tiles(0.75, -0.5, dx, dy2, lo, hi)
+                torch.cuda.synchronize()
+                assert torch.equal(dy, dy2), (name, sms)
+            torch.cuda.synchronize()
+            outs.append(dy.cpu().numpy())
+        assert_parity(h, x, y0, 0.75, -0.5, outs[0], what=f"comm_sms {name}")
+        for o in outs[1:]:
+            assert np.array_equal(o, outs[0]), name
+        with pytest.raises(Exception):
+            p.set_comm_sms(-1)
+        p.destroy()
+
+
 def test_kinds_are_exercised():
     """Each per-bin kernel, the staged-x form of both row kernels and the fix-up pass must actually run somewhere in
     this suite."""
