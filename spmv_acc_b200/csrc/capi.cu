@@ -999,9 +999,15 @@ struct spmv_b200_hostmat {
 };
 
 constexpr int kHostChunksMax = 64;
-static int host_chunks() { // row chunks of the pipelined host-buffer path (SPMV_B200_HOST_CHUNKS overrides)
+// Row chunks of the pipelined host-buffer path (SPMV_B200_HOST_CHUNKS overrides): pieces of ~28 MB per direction, at
+// least 8 and at most 16 of them. Measured on C5 (453 MB each way; both PCIe directions busy at once run 45.8 GB/s each
+// on these boxes = 9.9 ms): 4 chunks 13.2 ms, 8: 12.2, 16: 11.8, 32: 11.9 (profiles/r2_e2e_chunks_c5.jsonl); on C2
+// (134 MB each way) 8 chunks were best in round 1.
+static int host_chunks(size_t bytes_per_direction) {
   const char *e = getenv("SPMV_B200_HOST_CHUNKS");
-  const int c = e ? atoi(e) : 8;
+  int c = e ? atoi(e) : (int)(bytes_per_direction / (28u << 20));
+  if (!e)
+    c = c < 8 ? 8 : (c > 16 ? 16 : c);
   return c < 1 ? 1 : (c > kHostChunksMax ? kHostChunksMax : c);
 }
 
@@ -1161,7 +1167,7 @@ int spmv_b200_hostmat_spmv(spmv_b200_hostmat *hm, double alpha, double beta, con
   // Pipelined path (no split rows, enough tiles): x goes up first; then the rows are walked in chunks of tiles, the y0
   // chunk c+1 travels host->device while chunk c is multiplied and the y chunk c-1 travels device->host, so the two
   // PCIe directions are busy at the same time. Rows of a chunk are final once its kernels have run.
-  const int kHostChunks = host_chunks();
+  const int kHostChunks = host_chunks(sizeof(double) * (size_t)hm->m);
   if (p->nsplit == 0 && p->ntiles >= 4 * kHostChunks && hm->m > 0) {
     // x travels in pieces as well: a chunk of row blocks needs x up to the largest column it references, so for banded
     // matrices the first kernel starts after 1/chunks of the input has arrived; a matrix whose first rows reference the
