@@ -617,9 +617,13 @@ def time_power_loop(shard: Shard, mode: str = "fused", iters: int = 100, warmup:
         run = runner.run
     else:
         if world > 1 and getattr(loop, "overlapped", False):
-            # the collective runs beside persistent SpMV CTAs: leave it some SMs (spmv_b200_plan_set_comm_sms)
-            comm_sms = int(os.environ.get("SPMV_B200_COMM_SMS", "32"))
-            shard.plan.set_comm_sms(comm_sms)
+            # SMs left to the collective that runs beside the persistent SpMV CTAs (spmv_b200_plan_set_comm_sms). Off by
+            # default: measured at 2 and 8 GPUs it does not help -- the SpMV keeps ~20 MB of loads in flight and a
+            # co-running NCCL copy kernel gets bandwidth in proportion to its own few hundred KB, SMs or not
+            # (profiles/r2_overlap_probe_n2.jsonl, r2_iter_modes_vs_comm_sms_n8.jsonl)
+            comm_sms = int(os.environ.get("SPMV_B200_COMM_SMS", "0"))
+            if comm_sms:
+                shard.plan.set_comm_sms(comm_sms)
         if world > 1 and mode.startswith("fused"):
             note = note or f"the halo is not sparse for this matrix (exchange = {loop.mode}): NCCL exchange used"
         try:
