@@ -393,7 +393,7 @@ def run_b200(args, rank, world, local_rank):
     # number of iterations from the same x_0, so that every mode must end with the same x (x_checksum_first_16th) ----
     iterated = {"fused": head}
     if not args.no_iterated and world > 1:
-        for mode in ("fused_allgather", "nccl_allgather", "nccl_halo", "fused_multi_launch"):
+        for mode in ("fused_allgather_multicast", "fused_allgather", "nccl_allgather", "nccl_halo", "fused_multi_launch"):
             try:
                 iterated[mode] = sharded.time_power_loop(shard, mode, iters=args.steps, warmup=args.warmup)
             except Exception as e:

@@ -108,10 +108,14 @@ enum {
 };
 
 /* Fused halo push: rows [row_lo[j], row_hi[j]) of y are also stored to dst[j][row] (device pointers, typically
- * peer memory of another GPU mapped through CUDA IPC, offset so that they are indexed by the local row). */
+ * peer memory of another GPU mapped through CUDA IPC, offset so that they are indexed by the local row).
+ * Bit j of multicast_mask says that dst[j] is an NVLink multicast address (cuMulticast* / NVSwitch: one store is
+ * replicated by the switch into the memory of every GPU bound to the multicast object); the kernels then use
+ * multimem.st for it, and one destination replaces one per peer. */
 #define SPMV_B200_MAX_PUSH 8
 typedef struct spmv_b200_push {
   int32_t count;
+  uint32_t multicast_mask;
   int32_t row_lo[SPMV_B200_MAX_PUSH];
   int32_t row_hi[SPMV_B200_MAX_PUSH];
   double *dst[SPMV_B200_MAX_PUSH];

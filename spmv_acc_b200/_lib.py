@@ -36,8 +36,8 @@ IPC_HANDLE_BYTES = 64
 
 
 class Push(C.Structure):
-    _fields_ = [("count", C.c_int32), ("row_lo", C.c_int32 * MAX_PUSH), ("row_hi", C.c_int32 * MAX_PUSH),
-                ("dst", C.c_void_p * MAX_PUSH)]
+    _fields_ = [("count", C.c_int32), ("multicast_mask", C.c_uint32), ("row_lo", C.c_int32 * MAX_PUSH),
+                ("row_hi", C.c_int32 * MAX_PUSH), ("dst", C.c_void_p * MAX_PUSH)]
 
 
 MAX_RANGES = 16

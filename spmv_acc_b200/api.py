@@ -163,10 +163,7 @@ class SpmvPlan:
             raise SpmvB200Error(f"at most {_lib.MAX_PUSH} push ranges are supported")
         _require_device(dx, "dx", "float64")
         _require_device(dy, "dy", "float64")
-        ps = _lib.Push()
-        ps.count = len(push)
-        for j, (lo, hi, dst) in enumerate(push):
-            ps.row_lo[j], ps.row_hi[j], ps.dst[j] = int(lo), int(hi), int(dst)
+        ps = _fill_push(_lib.Push(), push)
         rc = _lib.lib().spmv_b200_execute_push(self._h, float(alpha), float(beta), _ptr(dx), _ptr(dy), C.byref(ps),
                                                _current_stream() if stream is None else stream)
         check(rc, "execute_push")
@@ -180,10 +177,7 @@ class SpmvPlan:
             raise SpmvB200Error(f"at most {_lib.MAX_PUSH} push ranges are supported")
         _require_device(dx, "dx", "float64")
         _require_device(dy, "dy", "float64")
-        ps = _lib.Push()
-        ps.count = len(push)
-        for j, (lo, hi, dst) in enumerate(push):
-            ps.row_lo[j], ps.row_hi[j], ps.dst[j] = int(lo), int(hi), int(dst)
+        ps = _fill_push(_lib.Push(), push)
         rc = _lib.lib().spmv_b200_execute_tiles_push(self._h, float(alpha), float(beta), _ptr(dx), _ptr(dy),
                                                      int(tile_lo), int(tile_hi), C.byref(ps),
                                                      _current_stream() if stream is None else stream)
@@ -311,6 +305,18 @@ class HaloLoop:
             self.destroy()
         except Exception:
             pass
+
+
+def _fill_push(ps, push):
+    """push = [(row_lo, row_hi, dst_address[, is_multicast_address])]"""
+    ps.count = len(push)
+    ps.multicast_mask = 0
+    for j, entry in enumerate(push):
+        lo, hi, dst = entry[:3]
+        ps.row_lo[j], ps.row_hi[j], ps.dst[j] = int(lo), int(hi), int(dst)
+        if len(entry) > 3 and entry[3]:
+            ps.multicast_mask |= 1 << j
+    return ps
 
 
 def cache_revalidations() -> int:

@@ -274,6 +274,7 @@ static int convert_push(const spmv_b200_plan *plan, const spmv_b200_push *push, 
     return SPMV_B200_ERR_ARG;
   }
   pa->count = push->count;
+  pa->multicast_mask = push->count >= 32 ? push->multicast_mask : (push->multicast_mask & ((1u << push->count) - 1u));
   for (int j = 0; j < kMaxPush; ++j) {
     pa->row_lo[j] = j < push->count ? push->row_lo[j] : 0;
     pa->row_hi[j] = j < push->count ? push->row_hi[j] : 0;

@@ -80,6 +80,7 @@ static_assert(sizeof(XDesc) == 128, "XDesc is one 128-byte line");
 constexpr int kMaxPush = SPMV_B200_MAX_PUSH;
 struct PushArgs {
   int count;
+  unsigned int multicast_mask; // bit j: dst[j] is an NVLink multicast address (stored to with multimem.st)
   int row_lo[kMaxPush], row_hi[kMaxPush];
   double *dst[kMaxPush];
 };

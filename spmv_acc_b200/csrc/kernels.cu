@@ -233,14 +233,21 @@ __device__ __forceinline__ void tile_issue_loads_xs(const SpmvArgs &a, int tile,
   }
 }
 
-// the y store of every kernel: local store plus, for rows another GPU waits for, a store into that GPU's memory
+// the y store of every kernel: local store plus, for rows another GPU waits for, a store into that GPU's memory.
+// MC: the kernel also understands NVLink multicast destinations (the row kernels and the ring; the MIXED, direct and
+// fix-up kernels do not -- their register budgets are tight and multicast pushes are refused for plans that need them).
+template <bool MC = false>
 __device__ __forceinline__ void emit_y(double *__restrict__ y, const PushArgs &push, int row, double v) {
   y[row] = v;
   if (push.count) {
 #pragma unroll 1
     for (int j = 0; j < push.count; ++j)
-      if (row >= push.row_lo[j] && row < push.row_hi[j])
-        push.dst[j][row] = v;
+      if (row >= push.row_lo[j] && row < push.row_hi[j]) {
+        if (MC && ((push.multicast_mask >> j) & 1u)) // the switch replicates the store into every GPU's copy
+          asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(push.dst[j] + row), "d"(v) : "memory");
+        else
+          push.dst[j][row] = v;
+      }
   }
 }
 
@@ -372,7 +379,7 @@ __device__ __forceinline__ void rows_tile(const SpmvArgs &a, const double *__res
           sum += __shfl_down_sync(0xffffffffu, sum, off, V);
       }
       if (act && l == 0) // cli/verification.cpp:64  y[i] = alpha * y0 + beta * y[i]
-        emit_y(a.y, a.push, r0 + cb + r, a.alpha * sum + a.beta * yv);
+        emit_y<true>(a.y, a.push, r0 + cb + r, a.alpha * sum + a.beta * yv);
     }
     if (cb + kRowChunk >= nrows)
       break;
@@ -707,7 +714,7 @@ __global__ void __launch_bounds__(kRingThreads, VEC ? 2 : 3) k_spmv_ring(const S
           sum += __shfl_down_sync(0xffffffffu, sum, off, 1 << lv);
       }
       if (act && l == 0) // cli/verification.cpp:64  y[i] = alpha * y0 + beta * y[i]
-        emit_y(a.y, a.push, r0 + r, a.alpha * sum + a.beta * yv);
+        emit_y<true>(a.y, a.push, r0 + r, a.alpha * sum + a.beta * yv);
     }
     __syncwarp();
     if (lane == 0)
@@ -1470,6 +1477,12 @@ static int launch_range(const spmv_b200_plan *p, double alpha, double beta, cons
                         int tile_hi, bool with_fixup, cudaStream_t stream, const PushArgs *push = nullptr) {
   if (p->m == 0)
     return SPMV_B200_OK;
+  if (push && push->count > 0 && push->multicast_mask != 0 &&
+      (p->direct || p->nsplit > 0 || p->count[SPMV_B200_KIND_MIXED] > 0)) {
+    set_error("multicast push destinations need a plan whose row blocks are all SHORT or MEDIUM (no direct form, no "
+              "split rows)");
+    return SPMV_B200_ERR_UNSUPPORTED;
+  }
   SpmvArgs a;
   fill_args(p, alpha, beta, x, y, push, &a);
   const bool tma = p->uses_tma;

@@ -354,8 +354,12 @@ def make_halo_desc(plan, buf_ptrs, lo: int, hi: int, wait_flags: list, signal_fl
         d.wait_flags[j], d.signal_flags[j] = int(w), int(g)
     for b in (0, 1):
         d.push[b].count = len(push[b])
-        for j, (rl, rh, dst) in enumerate(push[b]):
+        d.push[b].multicast_mask = 0
+        for j, entry in enumerate(push[b]):  # (row_lo, row_hi, dst_address[, is_multicast_address])
+            rl, rh, dst = entry[:3]
             d.push[b].row_lo[j], d.push[b].row_hi[j], d.push[b].dst[j] = int(rl), int(rh), int(dst)
+            if len(entry) > 3 and entry[3]:
+                d.push[b].multicast_mask |= 1 << j
     d.n_boundary, d.n_interior = len(boundary), len(interior)
     for j, (t0, t1) in enumerate(boundary):
         d.boundary[2 * j], d.boundary[2 * j + 1] = int(t0), int(t1)
@@ -363,6 +367,33 @@ def make_halo_desc(plan, buf_ptrs, lo: int, hi: int, wait_flags: list, signal_fl
         d.interior[2 * j], d.interior[2 * j + 1] = int(t0), int(t1)
     d.flags = int(flags)
     return d
+
+
+class SymmBuffer:
+    """Exchange memory from torch's symmetric memory (cuMemCreate + cuMulticast*, set up by the rendezvous): the same
+    allocation on every rank of the group, each rank's copy mapped into every other rank (``peer_address``) and, on
+    NVSwitch systems, one multicast address whose stores the switch replicates into all copies."""
+
+    def __init__(self, nbytes: int):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        dist = _dist()
+        self.nbytes = int(nbytes)
+        self._t = symm.empty(self.nbytes, dtype=torch.uint8, device="cuda")
+        self._h = symm.rendezvous(self._t, dist.group.WORLD)
+        self.address = int(self._t.data_ptr())
+        self.peer_address = [int(p) for p in self._h.buffer_ptrs]
+        self.multicast_address = int(self._h.multicast_ptr)
+
+    def tensor(self, dtype: str, count: int, offset: int):
+        import torch
+        dt = getattr(torch, dtype)
+        size = torch.empty(0, dtype=dt).element_size()
+        return self._t[offset:offset + count * size].view(dt)
+
+    def release(self):
+        self._h = None
+        self._t = None
 
 
 class FusedHaloLoop:
@@ -375,7 +406,7 @@ class FusedHaloLoop:
     after every neighbour has raised its flag to k, which means the neighbour's rows for x_k have arrived and the
     neighbour no longer reads the buffer about to be overwritten."""
 
-    def __init__(self, base: PowerLoop, plan, flags: int = 0):
+    def __init__(self, base: PowerLoop, plan, flags: int = 0, multicast: bool = False):
         import torch
         from . import HaloLoop, PeerBuffer
         dist = _dist()
@@ -384,27 +415,45 @@ class FusedHaloLoop:
         self.rank, self.world = base.rank, base.world
         self.lo, self.hi = int(base.bounds[self.rank]), int(base.bounds[self.rank + 1])
         self.neigh = sorted({p for p, _, _ in base.sends} | {p for p, _, _ in base.recvs})
-        # one exported allocation per rank: [x buffer 0 | x buffer 1 | flags], opened by the neighbours with THEIR
-        # device current (that is what maps it for their kernels; a torch-IPC tensor is mapped for the owner's device)
         n = base.n
         self.xbytes = (8 * n + 255) // 256 * 256
-        self.own = PeerBuffer.alloc(2 * self.xbytes + 4 * self.world)
+        self.multicast = bool(multicast)
+        if self.multicast:
+            # all-gather through the switch: the exchange memory comes from torch's symmetric memory, and ONE store to
+            # its multicast address puts a row into every GPU's copy of the next x (7 peer stores become one)
+            self.own = SymmBuffer(2 * self.xbytes + 4 * self.world)
+            if not self.own.multicast_address:
+                raise RuntimeError("this system gives no NVLink multicast address (no NVSwitch multicast support)")
+            peer_address = {p: self.own.peer_address[p] for p in self.neigh}
+            self.peer = {}
+        else:
+            # one exported allocation per rank: [x buffer 0 | x buffer 1 | flags], opened by the neighbours with THEIR
+            # device current (that is what maps it for their kernels; a torch-IPC tensor is mapped for the owner's device)
+            self.own = PeerBuffer.alloc(2 * self.xbytes + 4 * self.world)
         self.bufs = [self.own.tensor("float64", n, 0), self.own.tensor("float64", n, self.xbytes)]
         self.flags = self.own.tensor("int32", self.world, 2 * self.xbytes)
+        self.flags.zero_()
         self.bufs[0].copy_(base.x)
         torch.cuda.synchronize()
-        everyone = [None] * self.world
-        dist.all_gather_object(everyone, (self.own.handle, self.own.nbytes))
-        self.peer = {p: PeerBuffer.open(*everyone[p]) for p in self.neigh}
-        # push descriptors for both buffer parities: destination = neighbour's buffer, indexed by my local row
-        push = [[(a - self.lo, e - self.lo, self.peer[p].address + b * self.xbytes + 8 * self.lo)
-                 for p, a, e in base.sends] for b in (0, 1)]
+        if self.multicast:
+            dist.barrier()
+            # every row of the shard, both buffer parities: destination = the multicast image of the buffer
+            push = [[(0, self.hi - self.lo, self.own.multicast_address + b * self.xbytes + 8 * self.lo, True)]
+                    for b in (0, 1)]
+        else:
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, (self.own.handle, self.own.nbytes))
+            self.peer = {p: PeerBuffer.open(*everyone[p]) for p in self.neigh}
+            peer_address = {p: self.peer[p].address for p in self.neigh}
+            # push descriptors for both buffer parities: destination = neighbour's buffer, indexed by my local row
+            push = [[(a - self.lo, e - self.lo, peer_address[p] + b * self.xbytes + 8 * self.lo)
+                     for p, a, e in base.sends] for b in (0, 1)]
         # boundary-first schedule only if the boundary blocks are known to contain every reader of halo entries
         self.split = bool(getattr(base, "overlapped", False) and getattr(base, "boundary_reads_all_halo", False))
         desc = make_halo_desc(
             plan, [self.bufs[0].data_ptr(), self.bufs[1].data_ptr()], self.lo, self.hi,
             [self.flags.data_ptr() + 4 * p for p in self.neigh],
-            [self.peer[p].address + 2 * self.xbytes + 4 * self.rank for p in self.neigh], push,
+            [peer_address[p] + 2 * self.xbytes + 4 * self.rank for p in self.neigh], push,
             base.boundary if self.split else [], base.interior if self.split else [], flags)
         self.loop = HaloLoop(desc)
         self.k = 0
@@ -564,7 +613,7 @@ class LocalLoop:
         return self.bufs[self.k % 2]
 
 
-MODES = ("fused", "fused_multi_launch", "nccl_halo", "nccl_allgather", "fused_allgather")
+MODES = ("fused", "fused_multi_launch", "nccl_halo", "nccl_allgather", "fused_allgather", "fused_allgather_multicast")
 
 
 def time_power_loop(shard: Shard, mode: str = "fused", iters: int = 100, warmup: int = 4, sampler=None) -> dict:
@@ -576,7 +625,9 @@ def time_power_loop(shard: Shard, mode: str = "fused", iters: int = 100, warmup:
     interior row blocks, CUDA graph), "nccl_allgather" (one grouped NCCL all-gather of x per iteration overlapped with
     the row blocks that read only local columns, CUDA graph), "fused_allgather" (the all-gather done by the SpMV kernel
     itself: every row is stored into every other GPU's copy of the next x as it is produced, the kernel waits for all
-    peers' flags before its first row block and raises its own after its last; one launch per iteration, no NCCL)."""
+    peers' flags before its first row block and raises its own after its last; one launch per iteration, no NCCL),
+    "fused_allgather_multicast" (the same with ONE store per row to an NVLink multicast address: the NVSwitch replicates
+    it into every GPU's copy of the next x, so a GPU sends its slice once instead of once per peer)."""
     import torch
     from . import _lib
     dist = _dist()
@@ -590,14 +641,15 @@ def time_power_loop(shard: Shard, mode: str = "fused", iters: int = 100, warmup:
 
     warmup = max(4, int(warmup))
     iters = int(iters)
-    exchange = {"nccl_allgather": "allgather", "nccl_halo": "halo", "fused_allgather": "allgather"}.get(mode, "auto")
-    loop = make_loop(shard, exchange, overlap=mode != "fused_allgather")
+    fused_ag = mode in ("fused_allgather", "fused_allgather_multicast")
+    exchange = "allgather" if fused_ag else {"nccl_allgather": "allgather", "nccl_halo": "halo"}.get(mode, "auto")
+    loop = make_loop(shard, exchange, overlap=not fused_ag)
     native = mode in ("fused", "fused_multi_launch") and (world == 1 or loop.mode == "halo")
     dense_halo = mode in ("fused", "fused_multi_launch") and world > 1 and loop.mode == "allgather"
-    if (mode == "fused_allgather" or dense_halo) and world > 1:
+    if (fused_ag or dense_halo) and world > 1:
         # every rank needs (nearly) all of x: the kernels push whole slices to every peer (whole-shard schedule)
         if world - 1 > _lib.MAX_PUSH:
-            if mode == "fused_allgather":
+            if fused_ag:
                 raise RuntimeError(f"fused all-gather supports at most {_lib.MAX_PUSH + 1} GPUs")
         else:
             loop.sends, loop.recvs = allgather_schedule(loop.bounds, rank)
@@ -608,8 +660,13 @@ def time_power_loop(shard: Shard, mode: str = "fused", iters: int = 100, warmup:
     if native:
         flags = (_lib.HALO_NO_GRAPH | _lib.HALO_MULTI_LAUNCH) if mode == "fused_multi_launch" else 0
         try:
-            runner = (FusedHaloLoop if world > 1 else LocalLoop)(loop, shard.plan, flags)
+            if world > 1:
+                runner = FusedHaloLoop(loop, shard.plan, flags, multicast=mode == "fused_allgather_multicast")
+            else:
+                runner = LocalLoop(loop, shard.plan, flags)
         except Exception as e:  # no peer path / IPC unavailable: keep the NCCL exchange
+            if mode == "fused_allgather_multicast":
+                raise  # never time a fallback under this name
             native, note = False, f"{type(e).__name__}: {e}"
     use_graph = False
     comm_sms = 0
@@ -668,7 +725,9 @@ def time_power_loop(shard: Shard, mode: str = "fused", iters: int = 100, warmup:
         "exchange": ("none (one rank)" if world == 1 else
                      "all-gather by the SpMV kernel: every row stored into every peer's next x (NVLink stores), all "
                      "peers' flags waited for and raised inside the kernel"
-                     if native and (mode == "fused_allgather" or dense_halo) else
+                     + (" -- one multimem.st per row to the NVLink multicast address, replicated by the NVSwitch"
+                        if mode == "fused_allgather_multicast" else "")
+                     if native and (fused_ag or dense_halo) else
                      "halo rows pushed by the SpMV kernels into peer memory (NVLink stores), flags waited for and "
                      "raised inside the kernel" if native else f"NCCL {loop.mode}"),
         "exchange_bytes_in_per_iter_rank0": loop.bytes_in_per_iter,
