@@ -367,6 +367,50 @@ int port_xstage(const int *colindex, const int *tile_elem, int ntiles, int elem_
         if (i == 0 || lines[i] != lines[i - 1] + 1)
           nseg++;
       ok = (lines[nlines - 1] - lines[0]) < span_max && nlines <= lines_max && nseg <= seg_max;
+      /* too many runs: merge runs at most g missing lines apart, g = 1, 2, 4, ... 32 (k_xstage_build, merge path) */
+      if (!ok && (lines[nlines - 1] - lines[0]) < span_max && nlines <= lines_max && nseg > seg_max && nseg <= 1024) {
+        int pick = 0;
+        for (int g = 1; g <= 32 && !pick; g <<= 1) {
+          int c = 1;
+          for (int i = 1; i < nlines; i++)
+            c += (lines[i] - lines[i - 1] - 1) > g;
+          if (c <= seg_max)
+            pick = g;
+        }
+        if (pick) {
+          unsigned short *moff = (unsigned short *)(xd + 18);
+          int mline[64], mo[64], ms = 0, total = 0, start = lines[0];
+          for (int i = 1; i <= nlines; i++)
+            if (i == nlines || (lines[i] - lines[i - 1] - 1) > pick) {
+              mline[ms] = start;
+              mo[ms] = total;
+              total += lines[i - 1] + 1 - start;
+              ms++;
+              if (i < nlines)
+                start = lines[i];
+            }
+          if (total <= lines_max) {
+            for (int j = 0; j < ms; j++) {
+              xd[2 + j] = mline[j];
+              moff[j] = (unsigned short)mo[j];
+            }
+            xd[0] = ms;
+            xd[1] = total;
+            if (total > best)
+              best = total;
+            for (int k = 0; k < cnt; k++) {
+              const int c = colindex[e0 + k], l = c >> 4;
+              int sg = 0;
+              for (int j = 1; j < ms; j++)
+                if (mline[j] <= l)
+                  sg = j;
+              lcol[(long long)e0 + k - elem_base] = (unsigned short)(((mo[sg] + (l - mline[sg])) << 4) | (c & 15));
+            }
+            free(lines);
+            continue;
+          }
+        }
+      }
     }
     if (!ok) {
       xd[0] = -1;

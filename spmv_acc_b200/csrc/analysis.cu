@@ -543,6 +543,12 @@ int analysis_run(spmv_b200_plan *p, cudaStream_t stream) {
 //   lcol[k]    = (rank(col[k] >> 4) << 4) | (col[k] & 15)                (offset into the staged copy, in doubles)
 //   the tile qualifies iff it has elements, last line - first line < kXspanLinesMax, |lines| <= kXlinesMax and
 //   #segments <= kXsegMax; the plan takes the form iff every tile qualifies.
+//   Too many segments (unstructured meshes: many short runs a few lines apart) are repaired by staging the lines in
+//   between as well: for g = 1, 2, 4, 8, 16, 32 in turn, runs separated by at most g missing lines are merged; the first
+//   g that leaves <= kXsegMax segments is taken, and the tile qualifies if the merged segments hold <= kXlinesMax
+//   lines (at most kXrunsCap runs are examined). rank(l) is then the position of l in the merged segments:
+//   rank(l) = off[s] + (l - line[s]) for the segment s that contains l (identical to the definition above when nothing
+//   was merged).
 // One CTA per tile: a bitmap of the line span in shared memory (integer OR), a scan of its popcounts for the ranks.
 __global__ void __launch_bounds__(256)
     k_xstage_build(const int *__restrict__ col, const TileDesc *__restrict__ desc, int ntiles, long long lcol_base,
@@ -552,6 +558,8 @@ __global__ void __launch_bounds__(256)
   int *prefix = reinterpret_cast<int *>(xs_smem + kXspanLinesMax / 32);    // lines in front of each word
   __shared__ int s_red[2][8];
   __shared__ int s_scan[9], s_runs[9];
+  __shared__ int s_rs[kXrunsCap], s_re[kXrunsCap];                     // run starts / ends (merge path only)
+  __shared__ int s_mline[kXsegMax], s_moff[kXsegMax], s_mseg, s_mlines; // merged segment table
   const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (t >= ntiles)
     return;
@@ -634,8 +642,80 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
     const int nlines = s_scan[8], nruns = s_runs[8];
-    ok = nlines <= kXlinesMax && nruns <= kXsegMax;
-    if (ok) {
+    const bool plain = nlines <= kXlinesMax && nruns <= kXsegMax;
+    bool merged = false;
+    if (!plain && nruns > kXsegMax && nruns <= kXrunsCap && nlines <= kXlinesMax) { // (uniform over the CTA)
+      if (tid == 0) { // serial: only tiles of irregular meshes come here
+        int nrs = 0, nre = 0;
+        unsigned in = 0u;
+        for (int w = 0; w < nwords; ++w) {
+          const unsigned b = bitmap[w];
+          const unsigned next_lsb = (w + 1 < nwords) ? (bitmap[w + 1] & 1u) : 0u;
+          unsigned starts = b & ~((b << 1) | in), ends = b & ~((b >> 1) | (next_lsb << 31));
+          while (starts) {
+            s_rs[nrs++] = 32 * w + __ffs(starts) - 1;
+            starts &= starts - 1;
+          }
+          while (ends) {
+            s_re[nre++] = 32 * w + __ffs(ends); // one past the last line of the run
+            ends &= ends - 1;
+          }
+          in = b >> 31;
+        }
+        int pick = 0;
+        for (int g = 1; g <= 32 && !pick; g <<= 1) {
+          int cnt = 1;
+          for (int i = 1; i < nrs; ++i)
+            cnt += (s_rs[i] - s_re[i - 1]) > g;
+          if (cnt <= kXsegMax)
+            pick = g;
+        }
+        int nseg = -1, total = 0;
+        if (pick) {
+          nseg = 0;
+          int start = s_rs[0];
+          for (int i = 1; i <= nrs; ++i)
+            if (i == nrs || (s_rs[i] - s_re[i - 1]) > pick) {
+              s_mline[nseg] = start;
+              s_moff[nseg] = total;
+              total += s_re[i - 1] - start;
+              ++nseg;
+              if (i < nrs)
+                start = s_rs[i];
+            }
+          if (total > kXlinesMax)
+            nseg = -1;
+        }
+        s_mseg = nseg;
+        s_mlines = total;
+      }
+      __syncthreads();
+      merged = s_mseg > 0;
+    }
+    ok = plain || merged;
+    if (merged) {
+      const int nseg = s_mseg;
+      if (tid < kXsegMax) {
+        xd->line[tid] = tid < nseg ? lo + s_mline[tid] : 0;
+        xd->off[tid] = tid < nseg ? (unsigned short)s_moff[tid] : (unsigned short)0;
+      }
+      if (tid < 6)
+        xd->pad[tid] = 0;
+      if (tid == 0) {
+        xd->nseg = nseg;
+        xd->nlines = s_mlines;
+        atomicMax(status + 1, s_mlines);
+      }
+      for (int k = e0 + tid; k < e1; k += 256) {
+        const int c = __ldg(col + k);
+        const int l = (c >> 4) - lo;
+        int sgm = 0;
+        for (int j = 1; j < nseg; ++j)
+          sgm = s_mline[j] <= l ? j : sgm;
+        const int rank = s_moff[sgm] + (l - s_mline[sgm]);
+        lcol[(long long)k - lcol_base] = (unsigned short)((rank << 4) | (c & 15));
+      }
+    } else if (ok) {
       int base = s_scan[warp] + icnt - cnt, rbase = s_runs[warp] + iruns - runs; // exclusive prefixes of this thread
       for (int j = 0; j < per; ++j) {
         const int w = tid * per + j;

@@ -65,6 +65,7 @@ struct __align__(16) TileDesc {
 constexpr int kXsegMax = 16;          // segments per row block (a 27-point stencil has 9, a 5-point stencil 3)
 constexpr int kXlinesMax = 256;       // staged lines per row block (32 KB), upper limit
 constexpr int kXspanLinesMax = 65536; // lines between the smallest and the largest column of a row block (bitmap size)
+constexpr int kXrunsCap = 1024;       // runs of lines examined when too many segments are merged across small gaps
 struct __align__(16) XDesc {
   int nseg;   // -1: the row block does not qualify
   int nlines; // staged lines

@@ -129,6 +129,56 @@ def test_staged_x_arrays_bit_exact_and_only_for_regular_matrices():
         plan.destroy()
 
 
+def _mesh_like(m, strides, reach, seed):
+    """Every row references itself +-1..reach along each of the given strides: many short runs of columns a few lines
+    of x apart (the shape an unstructured-mesh matrix has after a bandwidth-reducing ordering)."""
+    offs = sorted({0} | {sg * k * st for st in strides for k in range(1, reach + 1) for sg in (1, -1)})
+    r = np.arange(m, dtype=np.int64)[:, None] + np.asarray(offs, dtype=np.int64)[None, :]
+    ok = (r >= 0) & (r < m)
+    rp = np.zeros(m + 1, dtype=np.int32)
+    rp[1:] = np.cumsum(ok.sum(1))
+    col = r[ok].astype(np.int32)
+    rng = np.random.default_rng(seed)
+    return synth.Csr(m, m, rp, col, rng.standard_normal(col.size))
+
+
+def test_staged_x_merges_runs_of_lines_across_small_gaps():
+    """Row blocks with more than 16 runs of x lines qualify when merging runs at most g lines apart (g = 1, 2, 4 ...
+    32) leaves at most 16 segments of at most 256 lines in total: segment tables and 16-bit indices equal the CPU
+    restatement bit for bit, the staged copy then holds lines no element references, and y is still right."""
+    import torch
+    from gpu_helpers import assert_parity
+    cases = {"strides_1_200_reach_10_T2048": _mesh_like(50000, (1, 200), 10, 1),
+             "strides_1_120_14400_reach_7": _mesh_like(120000, (1, 120, 14400), 7, 2),
+             "strides_1_97_9409_reach_6": _mesh_like(30000, (1, 97, 9409), 6, 3),
+             "strides_1_200_reach_10_T1024": _mesh_like(50000, (1, 200), 10, 4)}
+    merged_somewhere = False
+    for name, h in cases.items():
+        d = synth.to_device(h)
+        plan = SpmvPlan(desc_of(d), make_options(2048 if name.endswith("T2048") else 1024 if name.endswith("T1024") else 0))
+        info = plan.info()
+        ref = oracle.port_xstage(h.col, plan.export("tile_elem"))
+        assert (ref["failed"] == 0) == bool(info.xstage), (name, ref["failed"], info.xstage)
+        if info.xstage:
+            assert ref["max_lines"] == info.xstage_lines, name
+            assert np.array_equal(plan.export("xdesc"), ref["xdesc"]), f"{name}: xdesc differs"
+            assert np.array_equal(plan.export("lcol"), ref["lcol"]), f"{name}: lcol differs"
+            xd = ref["xdesc"].reshape(-1, 32)
+            # a merged tile stages more lines than its elements reference
+            te = plan.export("tile_elem")
+            for t in range(0, xd.shape[0], max(1, xd.shape[0] // 50)):
+                referenced = np.unique(h.col[te[t]:te[t + 1]] >> 4).size
+                merged_somewhere |= xd[t, 1] > referenced
+                assert xd[t, 1] >= referenced and 1 <= xd[t, 0] <= 16
+            x, y0 = synth.vector_numpy(h.cols, 2), synth.vector_numpy(h.rows, 3)
+            dy = torch.from_numpy(y0).cuda()
+            plan.execute(0.75, -0.5, torch.from_numpy(x).cuda(), dy)
+            torch.cuda.synchronize()
+            assert_parity(h, x, y0, 0.75, -0.5, dy.cpu().numpy(), what=f"merged staged x {name}")
+        plan.destroy()
+    assert merged_somewhere, "no case exercised the merge path"
+
+
 def test_tile_partition_equals_reference_merge_path_partition_kernel():
     """TILE_PART (T = 2048) against the reference's `partition` kernel, compiled in place into oracle/_ref/libref_gpu.so
     (benchmark/merge-path/merge_path_partition.h:7-17; launch shape of merge_path_spmv.cu:44)."""
