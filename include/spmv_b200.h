@@ -166,6 +166,10 @@ int spmv_b200_enable_peer_access(int32_t peer_device);
 #define SPMV_B200_MAX_RANGES 16
 #define SPMV_B200_HALO_NO_GRAPH 1u     /* enqueue every iteration separately */
 #define SPMV_B200_HALO_MULTI_LAUNCH 2u /* never use the single-launch kernel */
+#define SPMV_B200_HALO_ALIGN_PUSH 4u   /* pushed row blocks deal their rows to the lane groups by absolute row index, so
+                                          that every peer store is a full aligned 128-byte line (costs such a block a
+                                          second pass now and then: worth it when the link, not the SpMV, bounds the
+                                          iteration, i.e. all-gather pushes on 4 or more GPUs) */
 typedef struct spmv_b200_halo_loop_desc {
   spmv_b200_plan *plan;
   double *buf[2];

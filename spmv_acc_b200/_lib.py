@@ -58,6 +58,7 @@ class HaloLoopInfo(C.Structure):
 
 HALO_NO_GRAPH = 1
 HALO_MULTI_LAUNCH = 2
+HALO_ALIGN_PUSH = 4
 ERR_TIMEOUT = 4
 
 

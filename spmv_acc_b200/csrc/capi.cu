@@ -274,6 +274,7 @@ static int convert_push(const spmv_b200_plan *plan, const spmv_b200_push *push, 
     return SPMV_B200_ERR_ARG;
   }
   pa->count = push->count;
+  pa->align_rows = 0;
   pa->multicast_mask = push->count >= 32 ? push->multicast_mask : (push->multicast_mask & ((1u << push->count) - 1u));
   for (int j = 0; j < kMaxPush; ++j) {
     pa->row_lo[j] = j < push->count ? push->row_lo[j] : 0;
@@ -425,11 +426,13 @@ int spmv_b200_halo_loop_create(spmv_b200_halo_loop **out, const spmv_b200_halo_l
     return SPMV_B200_ERR_ARG;
   }
   L->d = *d;
-  for (int b = 0; b < 2; ++b)
+  for (int b = 0; b < 2; ++b) {
     if (int rc = convert_push(p, &d->push[b], &L->push[b], "halo_loop_create")) {
       delete L;
       return rc;
     }
+    L->push[b].align_rows = (d->flags & SPMV_B200_HALO_ALIGN_PUSH) ? 1 : 0;
+  }
   cudaError_t e = cudaMalloc(&L->state, 4 * sizeof(unsigned int));
   if (e == cudaSuccess)
     e = cudaMemset(L->state, 0, 4 * sizeof(unsigned int));

@@ -82,6 +82,7 @@ constexpr int kMaxPush = SPMV_B200_MAX_PUSH;
 struct PushArgs {
   int count;
   unsigned int multicast_mask; // bit j: dst[j] is an NVLink multicast address (stored to with multimem.st)
+  int align_rows;              // pushed row blocks deal rows by absolute row index (SPMV_B200_HALO_ALIGN_PUSH)
   int row_lo[kMaxPush], row_hi[kMaxPush];
   double *dst[kMaxPush];
 };

@@ -689,13 +689,13 @@ __global__ void __launch_bounds__(kRingThreads, VEC ? 2 : 3) k_spmv_ring(const S
     const int lv = VEC ? lanes_log2(e1 - e0, nrows, a.vec_div) : 0; // lanes per row, as in rows_tile
     const int Gr = kThreads >> lv, g = tid >> lv, l = tid & ((1 << lv) - 1);
     const uint32_t sval_s = smem_u32(st.sval), sx_s = smem_u32(st.sx), scol_s = smem_u32(st.slcol);
-    // A row block whose rows are pushed to other GPUs deals its rows to the lane groups by absolute row index, so that
-    // the 16 (or 8, 32) rows a warp finishes together are one aligned line of the destination: a peer store of a full
-    // 128-byte line needs no read-modify-write of partial sectors on the receiving side. (May cost the block a second
-    // pass; only boundary row blocks pay it in the halo loop, every block in the all-gather loop, where the link and
-    // not the SpMV bounds the iteration.)
+    // SPMV_B200_HALO_ALIGN_PUSH: a row block whose rows are pushed to other GPUs deals its rows to the lane groups by
+    // absolute row index, so that the 16 (or 8, 32) rows a warp finishes together are one aligned line of the
+    // destination: a peer store of a full 128-byte line needs no read-modify-write of partial sectors on the receiving
+    // side (all-gather push at 8 GPUs: 0.954 -> 0.771 ms per iteration). It may cost the block a second pass, so the
+    // caller asks for it only where the link and not the SpMV bounds the iteration (2 GPUs: 1.35 -> 1.47 ms with it).
     int shift = 0;
-    if (a.push.count) {
+    if (a.push.count && a.push.align_rows) {
       bool pushed = false;
       for (int j = 0; j < a.push.count; ++j)
         pushed |= r0 < a.push.row_hi[j] && r0 + nrows > a.push.row_lo[j];

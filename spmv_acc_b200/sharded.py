@@ -448,6 +448,16 @@ class FusedHaloLoop:
             # push descriptors for both buffer parities: destination = neighbour's buffer, indexed by my local row
             push = [[(a - self.lo, e - self.lo, peer_address[p] + b * self.xbytes + 8 * self.lo)
                      for p, a, e in base.sends] for b in (0, 1)]
+        # Full aligned lines per peer store (SPMV_B200_HALO_ALIGN_PUSH) where the link bounds the iteration: what
+        # arrives in a GPU per iteration at the ~400 GB/s small peer stores are absorbed with, against the SpMV's own
+        # time at the HBM rate. All-gather pushes on 4 or more GPUs qualify; halo pushes and 2 GPUs do not.
+        from . import _lib as _l
+        info = plan.info()
+        bytes_in = 8 * sum(e - a for _, a, e in base.recvs)
+        t_push, t_spmv = bytes_in / 4.0e11, (10.0 * info.nnz + 20.0 * info.m) / 6.5e12
+        self.align_push = t_push > t_spmv
+        if self.align_push:
+            flags |= _l.HALO_ALIGN_PUSH
         # boundary-first schedule only if the boundary blocks are known to contain every reader of halo entries
         self.split = bool(getattr(base, "overlapped", False) and getattr(base, "boundary_reads_all_halo", False))
         desc = make_halo_desc(

@@ -62,7 +62,8 @@ def _build_ranks(N, world, flags, allgather=False):
                 flag_words=flag_words, recvs=all_recvs)
 
 
-@pytest.mark.parametrize("world,N,flags", [(2, 40, 0), (3, 40, 0), (2, 64, 0), (3, 64, 0), (3, 64, 3), (2, 40, 3)])
+@pytest.mark.parametrize("world,N,flags", [(2, 40, 0), (3, 40, 0), (2, 64, 0), (3, 64, 0), (3, 64, 3), (2, 40, 3),
+                                           (3, 64, 4), (2, 40, 7)])  # 4 = SPMV_B200_HALO_ALIGN_PUSH
 def test_fused_halo_loop_equals_sequential_shards_and_oracle(world, N, flags):
     import torch
     import oracle
@@ -73,7 +74,7 @@ def test_fused_halo_loop_equals_sequential_shards_and_oracle(world, N, flags):
     for lp, plan in zip(R["loops"], R["plans"]):
         i, kinds = lp.info(), list(plan.info().tiles_per_kind)
         one_row_kind = kinds[2] == 0 and (kinds[0] == 0 or kinds[1] == 0)
-        if flags == 0 and one_row_kind:  # one launch per iteration, flag protocol inside the kernel
+        if (flags & 3) == 0 and one_row_kind:  # one launch per iteration, flag protocol inside the kernel
             assert i.single_launch == 1 and i.launches_per_iteration == 1
         else:
             assert i.single_launch == 0 and i.launches_per_iteration >= 3
@@ -116,7 +117,7 @@ def test_fused_halo_loop_equals_sequential_shards_and_oracle(world, N, flags):
         p.destroy()
 
 
-@pytest.mark.parametrize("world,N,flags", [(3, 40, 0), (4, 48, 0), (3, 40, 3)])
+@pytest.mark.parametrize("world,N,flags", [(3, 40, 0), (4, 48, 0), (3, 40, 3), (3, 40, 4), (4, 48, 4), (3, 48, 7)])
 def test_fused_allgather_push_leaves_the_whole_x_everywhere(world, N, flags):
     """The all-gather done by the SpMV kernels: every rank pushes its whole slice to every other rank (whole-shard
     schedule: all peers' flags are awaited before the first row block, the own flag is raised after the last). After k
