@@ -178,6 +178,7 @@ def ctx() -> C.CDLL:
         X.spmv_b200_ctx_cub_destroy.argtypes = [vp]
         X.spmv_b200_ctx_gather_bound.argtypes = [i64, vp, vp, vp, vp, i32, i32, i32, vp]
         X.spmv_b200_ctx_gather4_bound.argtypes = [i64, vp, vp, i64, vp, i32, i32, vp]
+        X.spmv_b200_ctx_gather_affine.argtypes = [i64, vp, vp, vp, vp, vp, i32, i32, vp]
         _ctx = X
     return _ctx
 

@@ -155,6 +155,81 @@ CTX_API int spmv_b200_ctx_gather_bound(long long nnz, const int *d_col, const do
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Gather bound with SM affinity (context, not product): does it help to let one group of SMs gather only from one half
+// of x? Data read by every SM is cached in both halves of the L2 (one per die), so a table larger than ~63 MB misses;
+// if the SMs of one die read only one half of the table, an L2 half holds its home lines plus the far copies of that
+// half only. Two column streams (indices into the lower / upper half of x); every CTA reads its SM id, picks its
+// group by `map`, and takes chunks of its group's stream from a ticket counter until the stream is empty.
+//   map 0: smid & 1          map 1: (smid >> 1) & 1 (TPC parity)     map 2: smid >= #SMs / 2
+//   map 3: ((smid >> 1) % 8) < 4      map 4: (smid / 18) & 1 ... guesses of how SM ids map to the two dies
+//   map 9: blockIdx.x & 1 (control: groups unrelated to the SM)
+__device__ __forceinline__ unsigned smid() {
+  unsigned v;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_gather_affine(long long nnz_half, const int *__restrict__ col_lo,
+                                                       const int *__restrict__ col_hi, const double *__restrict__ x,
+                                                       double *__restrict__ out, unsigned long long *tickets, int map,
+                                                       int nsm) {
+  __shared__ long long s_base;
+  const unsigned sm = smid();
+  int group;
+  switch (map) {
+  case 0: group = sm & 1; break;
+  case 1: group = (sm >> 1) & 1; break;
+  case 2: group = sm >= (unsigned)nsm / 2; break;
+  case 3: group = ((sm >> 1) % 8) < 4; break;
+  case 4: group = (sm / 18) & 1; break;
+  default: group = blockIdx.x & 1; break;
+  }
+  const int *__restrict__ col = group ? col_hi : col_lo;
+  constexpr long long kChunk = 256 * 8;
+  double sum = 0.0;
+  for (;;) {
+    if (threadIdx.x == 0)
+      s_base = (long long)atomicAdd(tickets + group, (unsigned long long)kChunk);
+    __syncthreads();
+    const long long base = s_base;
+    __syncthreads();
+    if (base >= nnz_half)
+      break;
+    int c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long k = base + threadIdx.x + 256 * j;
+      c[j] = k < nnz_half ? __ldg(col + k) : -1;
+    }
+    double v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = c[j] >= 0 ? __ldg(x + c[j]) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sum += v[j];
+  }
+  out[(size_t)blockIdx.x * 256 + threadIdx.x] = sum;
+}
+
+// d_tickets: two zeroed 64-bit counters; out: grid * 256 doubles; returns the grid size when d_out == nullptr
+CTX_API int spmv_b200_ctx_gather_affine(long long nnz_half, const int *d_col_lo, const int *d_col_hi, const double *d_x,
+                                        double *d_out, unsigned long long *d_tickets, int map, int ctas_per_sm,
+                                        void *stream) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = sms * (ctas_per_sm > 0 ? ctas_per_sm : 8);
+  if (!d_out)
+    return grid;
+  if (cudaMemsetAsync(d_tickets, 0, 2 * sizeof(unsigned long long), static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    return -2;
+  k_gather_affine<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(nnz_half, d_col_lo, d_col_hi, d_x, d_out,
+                                                                       d_tickets, map, sms);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Gather bound through the TMA unit (context, not product): the same column stream, but x is fetched with
 // cp.async.bulk.tensor ... tile::gather4 instead of LSU loads. x is described as a 2-D tensor [n/2][2] of fp64 (16-byte
 // rows, the smallest box TMA accepts); one instruction names four rows (col >> 1) and lands their 4 x 16 bytes in
