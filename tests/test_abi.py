@@ -142,3 +142,14 @@ def test_direct_kernel_uses_no_shared_memory_and_lane_contiguous_stream_loads():
     assert len(re.findall(r"LDG\.E\.EF\.64", head)) >= 4      # value: element 32j + lane, j = 0..3
     assert len(re.findall(r"LDG\.E\.EF ", head)) >= 4          # colindex
     assert len(re.findall(r"LDG\.E\.64\.CONSTANT", head)) >= 4  # x gathers
+
+
+def test_push_descriptor_marks_multicast_destinations():
+    """(row_lo, row_hi, address[, is_multicast]) tuples -> spmv_b200_push: the mask bit of a destination is set only for
+    entries flagged as NVLink multicast addresses; the plain three-field form keeps working."""
+    from spmv_acc_b200 import api
+    ps = api._fill_push(_lib.Push(), [(0, 10, 0x1000), (10, 20, 0x2000, True), (5, 6, 0x3000, False)])
+    assert ps.count == 3 and ps.multicast_mask == 0b010
+    assert [ps.row_lo[j] for j in range(3)] == [0, 10, 5] and [ps.row_hi[j] for j in range(3)] == [10, 20, 6]
+    assert [ps.dst[j] for j in range(3)] == [0x1000, 0x2000, 0x3000]
+    assert api._fill_push(_lib.Push(), []).count == 0
