@@ -161,3 +161,59 @@ def test_port_adaptive_choice_on_the_baseline_shapes():
     assert oracle.port_adaptive_choice(rp) == "vector-row, two data blocks"
     rp = (np.arange(1001, dtype=np.int32) * 9)                                     # small, avg 9 -> line-enhance (adaptive)
     assert oracle.port_adaptive_choice(rp) == "adaptive line-enhance"
+
+
+def _decode_staged_columns(col, tile_elem, ref):
+    """Inverse of the staged-x encoding: the column an lcol entry stands for, from the tile's segment table."""
+    xd = ref["xdesc"].reshape(-1, 32)
+    out = np.empty_like(col)
+    for t in range(xd.shape[0]):
+        e0, e1 = int(tile_elem[t]), int(tile_elem[t + 1])
+        nseg, nlines = int(xd[t, 0]), int(xd[t, 1])
+        line = xd[t, 2:2 + nseg].astype(np.int64)
+        off = xd[t, 18:26].copy().view(np.uint16)[:nseg].astype(np.int64)
+        assert nseg >= 1 and np.all(np.diff(line) > 0) and off[0] == 0 and np.all(np.diff(off) > 0) and off[-1] < nlines
+        lc = ref["lcol"][e0:e1].astype(np.int64)
+        rank = lc >> 4
+        assert rank.max(initial=0) < nlines
+        seg = np.searchsorted(off, rank, side="right") - 1
+        out[e0:e1] = ((line[seg] + (rank - off[seg])) << 4) | (lc & 15)
+    return out
+
+
+def test_staged_x_port_encoding_decodes_back_to_the_columns():
+    """oracle.port_xstage (the specification the GPU analysis is compared with bit for bit): for stencils, banded and
+    mesh-like matrices -- including row blocks whose runs of x lines had to be merged across gaps -- every 16-bit local
+    index, decoded through its row block's segment table, is the original column; segment tables are sorted, ranks fit
+    the staged line count, and merged tables stage at least the referenced lines."""
+    rng = np.random.default_rng(5)
+    cases = [synth.stencil2d_numpy(40), synth.stencil3d_numpy(12)]
+    for m, strides, reach in ((20000, (1, 200), 10), (30000, (1, 97, 9409), 6), (8000, (1, 64), 3)):
+        offs = sorted({0} | {sg * k * st for st in strides for k in range(1, reach + 1) for sg in (1, -1)})
+        r = np.arange(m, dtype=np.int64)[:, None] + np.asarray(offs, dtype=np.int64)[None, :]
+        ok = (r >= 0) & (r < m)
+        rp = np.zeros(m + 1, dtype=np.int32)
+        rp[1:] = np.cumsum(ok.sum(1))
+        cases.append(synth.Csr(m, m, rp, r[ok].astype(np.int32), rng.standard_normal(int(ok.sum()))))
+    merged = 0
+    for h in cases:
+        for T in (512, 2048):
+            te = [0]
+            while te[-1] < h.nnz:  # row-aligned blocks of about T non-zeros
+                r = int(np.searchsorted(h.rowptr, min(h.nnz, te[-1] + T), side="left"))
+                nxt = int(h.rowptr[min(r, h.rows)])
+                te.append(nxt if nxt > te[-1] else h.nnz)
+            te = np.asarray(te, dtype=np.int32)
+            ref = oracle.port_xstage(h.col, te)
+            xd = ref["xdesc"].reshape(-1, 32)
+            good = xd[:, 0] > 0
+            assert ref["failed"] == int((~good).sum())
+            if ref["failed"]:
+                continue
+            assert np.array_equal(_decode_staged_columns(h.col, te, ref), h.col)
+            assert ref["max_lines"] == int(xd[:, 1].max()) <= 256 and int(xd[:, 0].max()) <= 16
+            for t in range(0, xd.shape[0], max(1, xd.shape[0] // 40)):
+                referenced = np.unique(h.col[te[t]:te[t + 1]] >> 4).size
+                assert xd[t, 1] >= referenced
+                merged += int(xd[t, 1] > referenced)
+    assert merged > 0, "no row block needed the merge path"
