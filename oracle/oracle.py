@@ -17,7 +17,7 @@ REFERENCE = Path("/root/reference")
 __all__ = [
     "build", "have_ref", "port_host_spmv", "port_host_spmv_ax", "port_verify_y", "port_verify", "port_row_bound",
     "port_generate_vector", "port_merge_path_partition", "port_flat_break_points_v2", "port_analysis",
-    "port_shard_bounds", "port_gather_stat", "port_tiled_spmv", "port_direct_arrays", "port_adaptive_choice", "port_xstage", "ref_host_spmv", "ref_host_spmv_ax", "ref_verify_y",
+    "port_shard_bounds", "port_gather_stat", "port_tiled_spmv", "port_direct_arrays", "port_adaptive_choice", "ref_adaptive_choice", "have_ref_selector", "ADAPTIVE_CHOICES", "port_xstage", "ref_host_spmv", "ref_host_spmv_ax", "ref_verify_y",
     "ref_adaptive_plus_analyze", "ref_read", "ref_generate_vector", "best_host_spmv", "check_rows",
 ]
 
@@ -37,7 +37,7 @@ def build(with_ref: bool = True) -> None:
     """Compile the C restatement and, when /root/reference is present, the reference itself (oracle/_ref)."""
     targets = ["all"]
     if with_ref and REFERENCE.exists():
-        targets += ["ref", "ref-gpu"]
+        targets += ["ref", "ref-gpu", "ref-selector"]
         if (HERE.parent / "spmv_acc_b200" / "lib" / "libspmv_b200.so").exists():
             targets += ["ref-cli", "ref-harness"]
     res = subprocess.run(["make", "-s", "-C", str(HERE), *targets], capture_output=True, text=True)
@@ -281,6 +281,22 @@ def port_adaptive_choice(rowptr) -> str:
     lib = _port_lib()
     lib.port_adaptive_choice.restype = C.c_int
     return ADAPTIVE_CHOICES[int(lib.port_adaptive_choice(_p(rowptr, C.c_int), C.c_int(rowptr.size - 1)))]
+
+
+def have_ref_selector() -> bool:
+    return (HERE / "_ref" / "libref_selector.so").exists()
+
+
+def ref_adaptive_choice(rowptr) -> str:
+    """The same decision taken by the reference's own adaptive.cpp, compiled in place (oracle/_ref/libref_selector.so)."""
+    so = HERE / "_ref" / "libref_selector.so"
+    if not so.exists():
+        raise FileNotFoundError("oracle/_ref/libref_selector.so is missing: run `make -C oracle ref-selector` where "
+                                "/root/reference is mounted")
+    rowptr = _c(rowptr, _i32)
+    lib = C.CDLL(str(so))
+    lib.ref_adaptive_choice.restype = C.c_int
+    return ADAPTIVE_CHOICES[int(lib.ref_adaptive_choice(_p(rowptr, C.c_int), C.c_int(rowptr.size - 1)))]
 
 
 def port_gather_stat(rowptr, col, medium_max=128):

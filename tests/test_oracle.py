@@ -217,3 +217,43 @@ def test_staged_x_port_encoding_decodes_back_to_the_columns():
                 assert xd[t, 1] >= referenced
                 merged += int(xd[t, 1] > referenced)
     assert merged > 0, "no row block needed the merge path"
+
+
+@pytest.mark.skipif(not oracle.have_ref_selector(), reason="oracle/_ref/libref_selector.so not built (needs /root/reference)")
+def test_selector_restatement_equals_the_reference_selector_compiled_in_place():
+    """port_adaptive_choice (quoted by the selector study) against the reference's own src/acc/hip-adaptive/adaptive.cpp
+    compiled unmodified (its five launchers replaced by recorders): row-pointer arrays that reach every branch -- two
+    unbalanced halves in both directions, short rows, small and large matrices, empty leading rows -- and random ones.
+    Only rowptr[m/4], [m/2], [3m/4], [m] matter to the selector, so large nnz are produced with scaled row pointers."""
+    rng = np.random.default_rng(11)
+    cases = []
+
+    def rp_from_lens(lens):
+        return np.concatenate([[0], np.cumsum(np.asarray(lens, dtype=np.int64))]).astype(np.int32)
+
+    cases.append(rp_from_lens(np.full(1000, 3)))                               # avg <= 4 -> line
+    cases.append(rp_from_lens(np.full(1000, 5)))                               # small -> adaptive line-enhance
+    cases.append(rp_from_lens(np.full(400_000, 32)))                           # 12.8 M nnz -> flat
+    cases.append(rp_from_lens(np.full(300_000, 40)))                           # 12.0 M nnz -> line-enhance (adaptive)
+    cases.append(rp_from_lens(np.r_[np.full(500, 1), np.full(500, 40)]))       # second half 40x heavier
+    cases.append(rp_from_lens(np.r_[np.full(500, 40), np.full(500, 1)]))       # first half heavier
+    cases.append(rp_from_lens(np.r_[np.full(500, 10), np.full(500, 39)]))      # ratio 3.9 by integer division -> no split
+    cases.append(rp_from_lens(np.r_[np.full(500, 10), np.full(500, 40)]))      # ratio 4 -> split
+    cases.append(rp_from_lens(np.full(2_200_000, 4)))                          # avg 4 exactly, 8.8 M nnz
+    cases.append(rp_from_lens(np.full(1_700_000, 5)))                          # 8.5 M nnz: between 2^23 and 0xC00000
+    for _ in range(60):
+        m = int(rng.integers(8, 5000))
+        scale = int(rng.choice([1, 7, 300, 3000]))
+        lens = rng.integers(1, 12, m) * scale
+        if rng.random() < 0.3:
+            lens[: m // 2] = rng.integers(1, 3, m // 2)
+        cases.append(rp_from_lens(lens))
+    seen = set()
+    for rp in cases:
+        if int(rp[(rp.size - 1) // 2]) == 0 or int(rp[-1]) == int(rp[(rp.size - 1) // 2]):
+            continue  # the reference divides by the non-zeros of a half: an empty half is undefined behaviour there
+        a, b = oracle.ref_adaptive_choice(rp), oracle.port_adaptive_choice(rp)
+        assert a == b, (a, b, rp.size - 1, int(rp[-1]))
+        seen.add(a)
+    # the selector's last arm (plain line-enhance) needs nnz > 0xC00000 and nnz <= 2^23 at once: dead code in the reference
+    assert seen == set(oracle.ADAPTIVE_CHOICES) - {"line-enhance"}, seen

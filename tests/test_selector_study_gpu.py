@@ -28,6 +28,8 @@ def test_reference_selector_next_to_our_analysis():
         d = make()
         choice = oracle.port_adaptive_choice(d.rowptr.cpu().numpy())
         assert choice == expected, (name, choice)
+        if oracle.have_ref_selector():  # the reference's own adaptive.cpp compiled in place agrees
+            assert oracle.ref_adaptive_choice(d.rowptr.cpu().numpy()) == choice, name
         plan = SpmvPlan(desc_of(d))
         i = plan.info()
         ours = ("direct: one warp per row block, no shared memory" if i.direct else
@@ -67,6 +69,8 @@ def test_selector_study_on_suitesparse_shaped_matrices():
         rows_ref, cols_ref, avg_ref, family = synth.SUITESPARSE_SHAPES[name]
         assert (d.rows, d.cols) == (rows_ref, cols_ref) and abs(d.nnz / d.rows - avg_ref) <= 0.2 * avg_ref, name
         choice = oracle.port_adaptive_choice(d.rowptr.cpu().numpy())
+        if oracle.have_ref_selector():
+            assert oracle.ref_adaptive_choice(d.rowptr.cpu().numpy()) == choice, name
         plan = SpmvPlan(desc_of(d))
         i = plan.info()
         x, y0 = synth.vector_device(d.cols, 2), synth.vector_device(d.rows, 3)
