@@ -313,7 +313,11 @@ def verify_sampled(torch, csr, plan, alpha, beta, seed_x=2, seed_y=3, count=2000
         return {"ok": False, "error": f"{type(e).__name__}: {e}"}
 
 
-def time_plan(torch, dist, world, plan, alpha, beta, x, y, reps, warm=5):
+def time_plan(torch, dist, world, plan, alpha, beta, x, y, reps, warm=5, stats=None):
+    """Mean ms per SpMV over `reps` back-to-back launches (one event pair around all of them: what the lines report).
+    With `stats` (a dict) a second pass times every launch with its own event pair and adds the median and the minimum
+    (SURVEY.md §8d asks for both; an event record between launches costs a few microseconds, so the mean stays the
+    back-to-back figure)."""
     for _ in range(warm):
         plan.execute(alpha, beta, x, y)
     sync_all(torch, dist, world)
@@ -323,8 +327,20 @@ def time_plan(torch, dist, world, plan, alpha, beta, x, y, reps, warm=5):
         plan.execute(alpha, beta, x, y)
     e1.record()
     e1.synchronize()
+    mean = e0.elapsed_time(e1) / reps
+    if stats is not None:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            plan.execute(alpha, beta, x, y)
+            ev[i + 1].record()
+        ev[-1].synchronize()
+        per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+        stats["ms_median_per_launch_events"] = per[len(per) // 2]
+        stats["ms_min_per_launch_events"] = per[0]
+        stats["reps"] = reps
     sync_all(torch, dist, world)
-    return e0.elapsed_time(e1) / reps
+    return mean
 
 
 def run_b200(args, rank, world, local_rank):
@@ -541,11 +557,13 @@ def run_other_configs(torch, dist, rank, world, args, peak, peak_src):
             info = plan.info()
             x = synth.vector_device(csr.cols, 2)
             y = synth.vector_device(hi - lo, 3 + rank)
-            ms_local = time_plan(torch, dist, world, plan, 1.0, 1.0, x, y, 30)
+            tstats = {}
+            ms_local = time_plan(torch, dist, world, plan, 1.0, 1.0, x, y, 30, stats=tstats)
             ms = max_over_ranks(torch, dist, world, ms_local)
             b_local = alg_bytes(hi - lo, csr.cols, nnz_local)  # per rank: its rows, its non-zeros, the whole x
             rec = {"ms": ms, "gflops": 2.0 * csr.nnz / (ms * 1e-3) / 1e9, "n_gpus": world,
                    "scaling": "strong" if world > 1 else "single GPU", "alpha_beta": [1.0, 1.0],
+                   "timing_rank0": tstats,
                    "roofline": roofline(b_local, ms_local, peak, peak_src, dominant_kernel(info),
                                         key if world == 1 else None, hi - lo, nnz_local,
                                         streamed=streamed_bytes(info, hi - lo, csr.cols, nnz_local)),
